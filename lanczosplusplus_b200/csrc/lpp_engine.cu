@@ -1,0 +1,962 @@
+// lpp_engine.cu -- host side of liblpp_b200.so: handle management, device basis/table construction, kernel
+// dispatch, the device-resident Krylov loops (PsimagLite::LanczosSolver role) and the C-ABI of include/lpp_b200.h.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lpp_b200.h"
+#include "lpp_kernels.cuh"
+#include "lpp_tiled.cuh"
+#include "lpp_setup.h"
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg)
+{
+	g_err = msg;
+	return code;
+}
+#define CK(call)                                                                                               \
+	do {                                                                                                       \
+		cudaError_t e_ = (call);                                                                               \
+		if (e_ != cudaSuccess)                                                                                 \
+			return fail(LPP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+			                          std::to_string(__LINE__) + ")");                                         \
+	} while (0)
+#define CKR(expr)               \
+	do {                        \
+		int r_ = (expr);        \
+		if (r_ != 0) return r_; \
+	} while (0)
+
+extern "C" const char* lpp_last_error(void) { return g_err.c_str(); }
+extern "C" int lpp_version(void) { return 100; }
+
+// ------------------------------------------------------------------ NCCL (resolved lazily; only needed for nranks>1)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	int (*CommDestroy)(ncclComm_t) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int kNcclFloat64 = 8, kNcclSum = 0;
+
+static int nccl_load()
+{
+	if (g_nccl.lib) return 0;
+	void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!lib) return fail(LPP_ERR_NCCL, std::string("dlopen libnccl.so.2: ") + dlerror());
+#define SYM(field, name)                                                    \
+	*(void**)(&g_nccl.field) = dlsym(lib, name);                            \
+	if (!g_nccl.field) return fail(LPP_ERR_NCCL, std::string("dlsym ") + name)
+	SYM(GetUniqueId, "ncclGetUniqueId");
+	SYM(CommInitRank, "ncclCommInitRank");
+	SYM(CommDestroy, "ncclCommDestroy");
+	SYM(AllReduce, "ncclAllReduce");
+	SYM(Broadcast, "ncclBroadcast");
+	SYM(GroupStart, "ncclGroupStart");
+	SYM(GroupEnd, "ncclGroupEnd");
+	SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+	g_nccl.lib = lib;
+	return 0;
+}
+#define CKN(call)                                                                                         \
+	do {                                                                                                  \
+		int e_ = (call);                                                                                  \
+		if (e_ != 0) return fail(LPP_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(e_));   \
+	} while (0)
+
+// ------------------------------------------------------------------ handle
+struct lpp_handle {
+	lpp_desc desc;
+	std::vector<double> hop, jzz, U, V, D;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	ModelDev md;
+	std::vector<void*> allocs;
+	uint64_t rows = 0, row0 = 0, nloc = 0;
+	std::vector<uint64_t> shard_row0, shard_nloc;
+	// product tables
+	bool tables_ready = false;
+	HopTable up{}, dn{};
+	DiagTables dt{};
+	TiledPlan* tiled = nullptr;
+	// CRS
+	bool crs_ready = false;
+	int64_t* rowptr = nullptr;
+	int64_t* colind = nullptr;
+	double* values = nullptr;
+	int64_t nnz = 0;
+	// vectors
+	double* vx = nullptr;
+	double* vy = nullptr;
+	double* yfull = nullptr;
+	double* gs = nullptr;
+	double* modified = nullptr;
+	double* partials = nullptr;
+	int partials_cap = 0;
+	double* scal_dev = nullptr;
+	double* scal_host = nullptr;
+	// comm
+	ncclComm_t comm = nullptr;
+	// stats
+	int64_t launches = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+template <class T>
+static int dev_alloc(lpp_handle* h, T** p, size_t count)
+{
+	void* q = nullptr;
+	CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+	h->allocs.push_back(q);
+	*p = (T*)q;
+	return 0;
+}
+
+template <class T>
+static int dev_upload(lpp_handle* h, T** p, const T* src, size_t count)
+{
+	CKR(dev_alloc(h, p, count));
+	if (count) CK(cudaMemcpy(*p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+static void dev_free(lpp_handle* h, void* p)
+{
+	if (!p) return;
+	auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+	if (it != h->allocs.end()) h->allocs.erase(it);
+	cudaFree(p);
+}
+
+extern "C" int lpp_device_check(int32_t device)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(LPP_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+		                              " (liblpp_b200 has no CPU fallback)");
+	if (device < 0 || device >= n) return fail(LPP_ERR_ARG, "device ordinal out of range");
+	cudaDeviceProp p;
+	CK(cudaGetDeviceProperties(&p, device));
+	if (p.major != 10) return fail(LPP_ERR_CUDA, std::string("device is sm_") + std::to_string(p.major * 10 + p.minor) +
+	                                                 ", kernels are built for sm_100a only");
+	return 0;
+}
+
+static int setup_feas_spin(lpp_handle* h, int spin, const std::vector<uint64_t>& binom, uint64_t* nout)
+{
+	const int npart = spin ? h->desc.ndown : h->desc.nup;
+	LppFeasLayout L = lpp_feas_layout(binom, h->desc.nsite, h->desc.orbitals, npart);
+	uint64_t* d_off; uint64_t* d_start; int* d_pn;
+	CKR(dev_upload(h, &d_off, L.off.data(), L.off.size()));
+	CKR(dev_upload(h, &d_start, L.start.data(), L.start.size()));
+	CKR(dev_upload(h, &d_pn, L.pn.data(), L.pn.size()));
+	if (spin == 0) { h->md.part_off1 = d_off; h->md.part_start1 = d_start; h->md.part_n1 = d_pn; h->md.nparts1 = (int)L.start.size() - 1; }
+	else { h->md.part_off2 = d_off; h->md.part_start2 = d_start; h->md.part_n2 = d_pn; h->md.nparts2 = (int)L.start.size() - 1; }
+	*nout = L.total;
+	return 0;
+}
+
+static void shard_range(uint64_t n, int rank, int nranks, uint64_t* first, uint64_t* count)
+{
+	uint64_t base = n / nranks, rem = n % nranks;
+	*first = base * rank + std::min<uint64_t>(rank, rem);
+	*count = base + ((uint64_t)rank < rem ? 1 : 0);
+}
+
+extern "C" int lpp_shard_range(uint64_t n, int32_t rank, int32_t nranks, uint64_t* first, uint64_t* count)
+{
+	if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LPP_ERR_ARG, "bad rank/nranks");
+	shard_range(n, rank, nranks, first, count);
+	return 0;
+}
+
+extern "C" int lpp_destroy(lpp_handle* h)
+{
+	if (!h) return 0;
+	cudaSetDevice(h->device);
+	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+	if (h->tiled) lpp_tiled_destroy(h->tiled);
+	for (void* p : h->allocs) cudaFree(p);
+	if (h->scal_host) cudaFreeHost(h->scal_host);
+	if (h->ev0) cudaEventDestroy(h->ev0);
+	if (h->ev1) cudaEventDestroy(h->ev1);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	delete h;
+	return 0;
+}
+
+static int create_impl(const lpp_desc* d, lpp_handle* h)
+{
+	h->desc = *d;
+	const int model = d->model, nsite = d->nsite;
+	const int no = (model == LPP_MODEL_FEAS) ? d->orbitals : 1;
+	h->desc.orbitals = no;
+	const int nb = nsite * no;
+	if (model < 0 || model > 2) return fail(LPP_ERR_ARG, "unknown model");
+	if (nsite < 1 || nb > 62) return fail(LPP_ERR_ARG, "nsite*orbitals must be in [1,62]");
+	if (no < 1 || no > LPP_MAX_ORB) return fail(LPP_ERR_ARG, "orbitals must be in [1,4]");
+	if (d->nup < 0 || d->nup > nb || (model != LPP_MODEL_HEISENBERG && (d->ndown < 0 || d->ndown > nb)))
+		return fail(LPP_ERR_ARG, "particle numbers out of range");
+	if (!d->hop) return fail(LPP_ERR_ARG, "hop matrix is required");
+	if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) return fail(LPP_ERR_ARG, "bad rank/nranks");
+	CKR(lpp_device_check(d->device));
+	h->device = d->device;
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&h->ev0));
+	CK(cudaEventCreate(&h->ev1));
+
+	h->hop.assign(d->hop, d->hop + (size_t)nb * nb);
+	h->jzz.assign((size_t)nb * nb, 0.0);
+	if (d->jzz) h->jzz.assign(d->jzz, d->jzz + (size_t)nb * nb);
+	const int needU = (model == LPP_MODEL_FEAS) ? 6 : nsite;
+	h->U.assign(needU, 0.0);
+	if (d->U) for (int i = 0; i < std::min(needU, d->nU); i++) h->U[i] = d->U[i];
+	if (model == LPP_MODEL_FEAS) {
+		if (d->nU < 4 || d->nU > 6) return fail(LPP_ERR_ARG, "FeAsMode INT_PAPER33 expects 4, 5 or 6 U values");
+		if (d->nU == 4 || d->nU == 5) { h->U[4] = h->U[2]; h->U[5] = 0.0; }  // ParametersModelFeAs.h:147-151
+	}
+	const int needV = (model == LPP_MODEL_FEAS) ? 2 * no * nsite : nsite;
+	h->V.assign(needV, 0.0);
+	if (d->V) for (int i = 0; i < std::min(needV, d->nV); i++) h->V[i] = d->V[i];
+	h->D.assign(std::max(nsite, 1), 0.0);
+	if (d->D) for (int i = 0; i < std::min(nsite, d->nD); i++) h->D[i] = d->D[i];
+
+	std::vector<uint64_t> binom = lpp_make_binom();
+	ModelDev& m = h->md;
+	memset(&m, 0, sizeof(m));
+	m.model = model; m.nsite = nsite; m.orbitals = no; m.nbits = nb;
+	m.nup = d->nup; m.ndn = d->ndown; m.u3_all_pairs = d->feas_u3_all_pairs;
+	uint64_t* d_binom;
+	CKR(dev_upload(h, &d_binom, binom.data(), binom.size()));
+	m.binom = d_binom;
+	double* p;
+	CKR(dev_upload(h, &p, h->hop.data(), h->hop.size())); m.hop = p;
+	CKR(dev_upload(h, &p, h->jzz.data(), h->jzz.size())); m.jzz = p;
+	CKR(dev_upload(h, &p, h->U.data(), h->U.size())); m.U = p;
+	CKR(dev_upload(h, &p, h->V.data(), h->V.size())); m.V = p;
+	CKR(dev_upload(h, &p, h->D.data(), h->D.size())); m.D = p;
+
+	// bases on device
+	word_t* b1 = nullptr; word_t* b2 = nullptr;
+	if (model == LPP_MODEL_FEAS) {
+		CKR(setup_feas_spin(h, 0, binom, &m.n1));
+		CKR(setup_feas_spin(h, 1, binom, &m.n2));
+		CKR(dev_alloc(h, &b1, m.n1));
+		CKR(dev_alloc(h, &b2, m.n2));
+		lpp_launch_build_feas(m, 0, m.n1, b1, h->stream);
+		lpp_launch_build_feas(m, 1, m.n2, b2, h->stream);
+	} else {
+		m.n1 = binom[nsite * LPP_BINOM_N + d->nup];
+		m.n2 = (model == LPP_MODEL_HUBBARD) ? binom[nsite * LPP_BINOM_N + d->ndown] : 1;
+		CKR(dev_alloc(h, &b1, m.n1));
+		CKR(dev_alloc(h, &b2, m.n2));
+		lpp_launch_build_colex(m.binom, nsite, d->nup, m.n1, b1, h->stream);
+		if (model == LPP_MODEL_HUBBARD) lpp_launch_build_colex(m.binom, nsite, d->ndown, m.n2, b2, h->stream);
+		else CK(cudaMemsetAsync(b2, 0, sizeof(word_t), h->stream));
+	}
+	m.b1 = b1; m.b2 = b2;
+	m.rows = m.n1 * m.n2;
+	h->rows = m.rows;
+	CK(cudaGetLastError());
+
+	// rank accelerators
+	if (model != LPP_MODEL_FEAS && nb <= 40 && m.n1 < (1ull << 32) && m.n2 < (1ull << 32)) {
+		int lobits = (nb + 1) / 2;
+		uint32_t* rlo; uint32_t* rhi;
+		CKR(dev_alloc(h, &rlo, (size_t)1 << lobits));
+		CKR(dev_alloc(h, &rhi, (size_t)(lobits + 1) << (nb - lobits)));
+		lpp_launch_split_tables(m.binom, nb, lobits, rlo, rhi, h->stream);
+		CK(cudaStreamSynchronize(h->stream));
+		m.rlo = rlo; m.rhi = rhi; m.lobits = lobits;
+	}
+	if (model == LPP_MODEL_FEAS && nb <= 26) {
+		uint32_t* l1; uint32_t* l2;
+		CKR(dev_alloc(h, &l1, (size_t)1 << nb));
+		CKR(dev_alloc(h, &l2, (size_t)1 << nb));
+		CK(cudaMemsetAsync(l1, 0xff, sizeof(uint32_t) << nb, h->stream));
+		CK(cudaMemsetAsync(l2, 0xff, sizeof(uint32_t) << nb, h->stream));
+		lpp_launch_lut(m.b1, m.n1, l1, h->stream);
+		lpp_launch_lut(m.b2, m.n2, l2, h->stream);
+		CK(cudaStreamSynchronize(h->stream));
+		m.lut1 = l1; m.lut2 = l2;
+	}
+
+	// sharding over the slow index (product bases: whole up-segments; Heisenberg: contiguous rows)
+	h->shard_row0.resize(d->nranks);
+	h->shard_nloc.resize(d->nranks);
+	for (int r = 0; r < d->nranks; r++) {
+		uint64_t f, c;
+		if (model == LPP_MODEL_HEISENBERG) shard_range(m.rows, r, d->nranks, &f, &c);
+		else { shard_range(m.n2, r, d->nranks, &f, &c); f *= m.n1; c *= m.n1; }
+		h->shard_row0[r] = f;
+		h->shard_nloc[r] = c;
+	}
+	h->row0 = h->shard_row0[d->rank];
+	h->nloc = h->shard_nloc[d->rank];
+
+	CKR(dev_alloc(h, &h->scal_dev, 8));
+	CK(cudaMallocHost((void**)&h->scal_host, 8 * sizeof(double)));
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int lpp_create(const lpp_desc* d, lpp_handle** out)
+{
+	if (!d || !out) return fail(LPP_ERR_ARG, "null argument");
+	lpp_handle* h = new lpp_handle();
+	int rc = create_impl(d, h);
+	if (rc != 0) {
+		std::string keep = g_err;
+		lpp_destroy(h);
+		g_err = keep;
+		*out = nullptr;
+		return rc;
+	}
+	*out = h;
+	return 0;
+}
+
+extern "C" int lpp_rows(const lpp_handle* h, uint64_t* rows)
+{
+	if (!h || !rows) return fail(LPP_ERR_ARG, "null argument");
+	*rows = h->rows;
+	return 0;
+}
+
+extern "C" int lpp_local_rows(const lpp_handle* h, uint64_t* first, uint64_t* count)
+{
+	if (!h) return fail(LPP_ERR_ARG, "null argument");
+	if (first) *first = h->row0;
+	if (count) *count = h->nloc;
+	return 0;
+}
+
+extern "C" int lpp_basis_size(const lpp_handle* h, int32_t spin, uint64_t* n)
+{
+	if (!h || !n) return fail(LPP_ERR_ARG, "null argument");
+	*n = spin ? h->md.n2 : h->md.n1;
+	return 0;
+}
+
+extern "C" int lpp_basis_export(const lpp_handle* h, int32_t spin, uint64_t* words)
+{
+	if (!h || !words) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	CK(cudaMemcpy(words, spin ? h->md.b2 : h->md.b1, sizeof(word_t) * (spin ? h->md.n2 : h->md.n1), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int lpp_rank(const lpp_handle* hc, int32_t spin, const uint64_t* words, uint64_t n, uint64_t* index)
+{
+	lpp_handle* h = const_cast<lpp_handle*>(hc);
+	if (!h || !words || !index) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	word_t* dw; uint64_t* di;
+	CK(cudaMalloc((void**)&dw, sizeof(word_t) * std::max<uint64_t>(n, 1)));
+	CK(cudaMalloc((void**)&di, sizeof(uint64_t) * std::max<uint64_t>(n, 1)));
+	CK(cudaMemcpy(dw, words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
+	lpp_launch_rank(h->md, spin, dw, n, di, h->stream);
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaMemcpy(index, di, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+	cudaFree(dw); cudaFree(di);
+	return 0;
+}
+
+// ------------------------------------------------------------------ tables / CRS
+static int ensure_tables(lpp_handle* h)
+{
+	if (h->tables_ready) return 0;
+	if (h->md.model == LPP_MODEL_HEISENBERG) return fail(LPP_ERR_ARG, "hop tables exist for product bases only");
+	const ModelDev& m = h->md;
+	for (int spin = 0; spin < 2; spin++) {
+		HopTable& t = spin ? h->dn : h->up;
+		t.n = spin ? m.n2 : m.n1;
+		CKR(dev_alloc(h, &t.cnt, t.n));
+		uint32_t* dmax = (uint32_t*)h->scal_dev;
+		CK(cudaMemsetAsync(dmax, 0, sizeof(uint32_t), h->stream));
+		lpp_launch_hop_count(m, spin, t.n, t.cnt, dmax, h->stream);
+		uint32_t hmax = 0;
+		CK(cudaMemcpyAsync(&hmax, dmax, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		t.width = (int)hmax;
+		CKR(dev_alloc(h, &t.idx, (size_t)t.width * t.n));
+		CKR(dev_alloc(h, &t.val, (size_t)t.width * t.n));
+		lpp_launch_hop_fill(m, spin, t, h->stream);
+		double* dv;
+		CKR(dev_alloc(h, &dv, t.n));
+		lpp_launch_spin_diag(m, spin, t.n, dv, h->stream);
+		if (spin) h->dt.dv2 = dv; else h->dt.dv1 = dv;
+	}
+	h->dt.uniformU = 1;
+	h->dt.U0 = h->U[0];
+	if (m.model == LPP_MODEL_HUBBARD)
+		for (int i = 1; i < m.nsite; i++) if (h->U[i] != h->U[0]) h->dt.uniformU = 0;
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaGetLastError());
+	h->tables_ready = true;
+	return 0;
+}
+
+extern "C" int lpp_crs_build(lpp_handle* h, int64_t* nnz)
+{
+	if (!h) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	if (!h->crs_ready) {
+		CKR(dev_alloc(h, &h->rowptr, h->nloc + 1));
+		int* dflag = (int*)h->scal_dev;
+		CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
+		CK(cudaMemsetAsync(h->rowptr, 0, sizeof(int64_t) * (h->nloc + 1), h->stream));
+		lpp_launch_crs_count(h->md, h->row0, h->nloc, h->rowptr, dflag, h->stream);
+		int flag = 0;
+		CK(cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+		lpp_exclusive_scan(h->rowptr, h->nloc, nullptr, h->stream);
+		CK(cudaMemcpyAsync(&h->nnz, h->rowptr + h->nloc, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		if (flag) return fail(LPP_ERR_OVERFLOW, "a Hamiltonian row has more than 256 entries");
+		CKR(dev_alloc(h, &h->colind, (size_t)h->nnz));
+		CKR(dev_alloc(h, &h->values, (size_t)h->nnz));
+		lpp_launch_crs_fill(h->md, h->row0, h->nloc, h->rowptr, h->colind, h->values, h->stream);
+		CK(cudaStreamSynchronize(h->stream));
+		CK(cudaGetLastError());
+		h->crs_ready = true;
+	}
+	if (nnz) *nnz = h->nnz;
+	return 0;
+}
+
+extern "C" int lpp_crs_export(const lpp_handle* h, int64_t* rowptr, int64_t* colind, double* values)
+{
+	if (!h) return fail(LPP_ERR_ARG, "null argument");
+	if (!h->crs_ready) return fail(LPP_ERR_STATE, "lpp_crs_build has not been called");
+	CK(cudaSetDevice(h->device));
+	if (rowptr) CK(cudaMemcpy(rowptr, h->rowptr, sizeof(int64_t) * (h->nloc + 1), cudaMemcpyDeviceToHost));
+	if (colind) CK(cudaMemcpy(colind, h->colind, sizeof(int64_t) * h->nnz, cudaMemcpyDeviceToHost));
+	if (values) CK(cudaMemcpy(values, h->values, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// ------------------------------------------------------------------ SpMV dispatch
+static int resolve_kernel(const lpp_handle* h, int kernel)
+{
+	if (kernel == LPP_KERNEL_AUTO) return (h->md.model == LPP_MODEL_HEISENBERG) ? LPP_KERNEL_GENERIC : LPP_KERNEL_TILED;
+	return kernel;
+}
+
+static int ensure_partials(lpp_handle* h, int n)
+{
+	if (n <= h->partials_cap) return 0;
+	if (h->partials) dev_free(h, h->partials);
+	h->partials = nullptr;
+	CKR(dev_alloc(h, &h->partials, (size_t)n));
+	h->partials_cap = n;
+	return 0;
+}
+
+// x = beta x + alpha H y ; if want_dot, returns in *npartials the number of block partial sums left in h->partials
+static int do_spmv(lpp_handle* h, int kernel, double alpha, double beta, double* x, const double* y, bool want_dot,
+                   int* npartials)
+{
+	kernel = resolve_kernel(h, kernel);
+	SpmvArgs a;
+	a.alpha = alpha; a.beta = beta; a.x = x; a.y = y; a.row0 = h->row0; a.nloc = h->nloc;
+	a.dot_partials = nullptr;
+	int nb = 0;
+	if (kernel == LPP_KERNEL_GENERIC) {
+		nb = lpp_spmv_generic_blocks(h->nloc);
+		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
+		lpp_launch_spmv_generic(h->md, a, h->stream);
+		h->launches += 1;
+	} else if (kernel == LPP_KERNEL_TABLE) {
+		CKR(ensure_tables(h));
+		nb = lpp_spmv_table_blocks(h->md, h->nloc);
+		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
+		lpp_launch_spmv_table(h->md, h->up, h->dn, h->dt, a, h->stream);
+		h->launches += 1;
+	} else if (kernel == LPP_KERNEL_TILED) {
+		CKR(ensure_tables(h));
+		if (!h->tiled) {
+			int rc = lpp_tiled_create(h->md, h->hop.data(), h->up, h->dn, h->row0, h->nloc, h->stream, &h->tiled);
+			if (rc != 0) return fail(LPP_ERR_CUDA, std::string("tiled plan: ") + lpp_tiled_error());
+		}
+		nb = lpp_tiled_dot_blocks(h->tiled);
+		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
+		int nl = lpp_tiled_spmv(h->tiled, h->md, h->up, h->dn, h->dt, a, h->stream);
+		if (nl < 0) return fail(LPP_ERR_CUDA, std::string("tiled spmv: ") + lpp_tiled_error());
+		h->launches += nl;
+	} else if (kernel == LPP_KERNEL_STORED) {
+		CKR(lpp_crs_build(h, nullptr));
+		nb = lpp_spmv_crs_blocks(h->nloc);
+		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
+		lpp_launch_spmv_crs(h->rowptr, h->colind, h->values, a, h->stream);
+		h->launches += 1;
+	} else {
+		return fail(LPP_ERR_ARG, "unknown kernel id");
+	}
+	CK(cudaGetLastError());
+	if (npartials) *npartials = nb;
+	return 0;
+}
+
+extern "C" int lpp_matvec_device(lpp_handle* h, int32_t kernel, double* x_dev, const double* y_dev)
+{
+	if (!h || !x_dev || !y_dev) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	CKR(do_spmv(h, kernel, 1.0, 1.0, x_dev, y_dev, false, nullptr));
+	CK(cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int lpp_matvec_host(lpp_handle* h, int32_t kernel, double* x, const double* y)
+{
+	if (!h || !x || !y) return fail(LPP_ERR_ARG, "null argument");
+	if (h->desc.nranks != 1) return fail(LPP_ERR_STATE, "lpp_matvec_host needs the whole Hilbert space on one GPU");
+	CK(cudaSetDevice(h->device));
+	double* dx; double* dy;
+	CK(cudaMalloc((void**)&dx, sizeof(double) * h->rows));
+	CK(cudaMalloc((void**)&dy, sizeof(double) * h->rows));
+	CK(cudaMemcpyAsync(dx, x, sizeof(double) * h->rows, cudaMemcpyHostToDevice, h->stream));
+	CK(cudaMemcpyAsync(dy, y, sizeof(double) * h->rows, cudaMemcpyHostToDevice, h->stream));
+	int rc = do_spmv(h, kernel, 1.0, 1.0, dx, dy, false, nullptr);
+	if (rc == 0) {
+		cudaError_t e = cudaMemcpyAsync(x, dx, sizeof(double) * h->rows, cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		if (e != cudaSuccess) rc = fail(LPP_ERR_CUDA, std::string("matvec_host: ") + cudaGetErrorString(e));
+	}
+	cudaFree(dx); cudaFree(dy);
+	return rc;
+}
+
+// ------------------------------------------------------------------ tridiagonal eigen-solvers (host)
+// lowest eigenvalue by Sturm-sequence bisection (used every Lanczos step for the convergence test)
+static double tridiag_lowest(int n, const double* a, const double* b)
+{
+	if (n == 1) return a[0];
+	double lo = a[0], hi = a[0];
+	for (int i = 0; i < n; i++) {
+		double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i < n - 1 ? fabs(b[i]) : 0.0);
+		lo = std::min(lo, a[i] - r);
+		hi = std::max(hi, a[i] + r);
+	}
+	auto count_below = [&](double x) {  // number of eigenvalues < x
+		int c = 0;
+		double q = a[0] - x;
+		if (q < 0) c++;
+		for (int i = 1; i < n; i++) {
+			double bb = b[i - 1] * b[i - 1];
+			if (q == 0.0) q = 1e-300;
+			q = a[i] - x - bb / q;
+			if (q < 0) c++;
+		}
+		return c;
+	};
+	for (int it = 0; it < 200; it++) {
+		double mid = 0.5 * (lo + hi);
+		if (mid <= lo || mid >= hi) break;
+		if (count_below(mid) >= 1) hi = mid; else lo = mid;
+	}
+	return 0.5 * (lo + hi);
+}
+
+// full decomposition: implicit-shift QL on (d, e); z (n*n, z[i*n+k] = component i of vector k) optional
+static int tridiag_full(int n, std::vector<double>& d, std::vector<double>& e, double* z)
+{
+	e.resize(n + 1);
+	e[n - 1] = 0.0;
+	if (z) {
+		std::fill(z, z + (size_t)n * n, 0.0);
+		for (int i = 0; i < n; i++) z[(size_t)i * n + i] = 1.0;
+	}
+	const double eps = 2.220446049250313e-16;
+	for (int l = 0; l < n; l++) {
+		for (int iter = 0;; iter++) {
+			int m = l;
+			for (; m < n - 1; m++) {
+				double dd = fabs(d[m]) + fabs(d[m + 1]);
+				if (fabs(e[m]) <= eps * dd) break;
+			}
+			if (m == l) break;
+			if (iter >= 300) return -1;
+			// Wilkinson shift from the leading 2x2 of the unreduced block
+			double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+			double r = std::hypot(g, 1.0);
+			g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
+			double s = 1.0, c = 1.0, p = 0.0;
+			bool underflow = false;
+			for (int i = m - 1; i >= l; i--) {
+				double f = s * e[i], bq = c * e[i];
+				r = std::hypot(f, g);
+				e[i + 1] = r;
+				if (r == 0.0) {
+					d[i + 1] -= p;
+					e[m] = 0.0;
+					underflow = true;
+					break;
+				}
+				s = f / r;
+				c = g / r;
+				g = d[i + 1] - p;
+				r = (d[i] - g) * s + 2.0 * c * bq;
+				p = s * r;
+				d[i + 1] = g + p;
+				g = c * r - bq;
+				if (z) {
+					for (int k = 0; k < n; k++) {
+						double zk1 = z[(size_t)k * n + i + 1], zk0 = z[(size_t)k * n + i];
+						z[(size_t)k * n + i + 1] = s * zk0 + c * zk1;
+						z[(size_t)k * n + i] = c * zk0 - s * zk1;
+					}
+				}
+			}
+			if (underflow) continue;
+			d[l] -= p;
+			e[l] = g;
+			e[m] = 0.0;
+		}
+	}
+	// ascending order
+	std::vector<int> perm(n);
+	for (int i = 0; i < n; i++) perm[i] = i;
+	std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return d[x] < d[y]; });
+	std::vector<double> d2(n);
+	for (int i = 0; i < n; i++) d2[i] = d[perm[i]];
+	if (z) {
+		std::vector<double> z2((size_t)n * n);
+		for (int i = 0; i < n; i++)
+			for (int k = 0; k < n; k++) z2[(size_t)i * n + k] = z[(size_t)i * n + perm[k]];
+		std::copy(z2.begin(), z2.end(), z);
+	}
+	d = d2;
+	return 0;
+}
+
+extern "C" int lpp_tridiag_eig(int32_t n, const double* a, const double* b, double* eigs, double* z)
+{
+	if (n < 1 || !a || !eigs) return fail(LPP_ERR_ARG, "bad argument");
+	std::vector<double> d(a, a + n), e(n, 0.0);
+	for (int i = 0; i + 1 < n; i++) e[i] = b[i];
+	if (tridiag_full(n, d, e, z) != 0) return fail(LPP_ERR_STATE, "tridiagonal QL did not converge");
+	std::copy(d.begin(), d.end(), eigs);
+	return 0;
+}
+
+extern "C" int lpp_cf_eval(int32_t n, const double* a, const double* b, double eg, double weight, int32_t isign,
+                           int32_t nomega, const double* omega, double delta, double* out)
+{
+	if (n < 1 || !a || !b || !omega || !out) return fail(LPP_ERR_ARG, "bad argument");
+	std::vector<double> d(a, a + n), e(n, 0.0), z((size_t)n * n);
+	for (int i = 0; i + 1 < n; i++) e[i] = b[i];
+	if (tridiag_full(n, d, e, z.data()) != 0) return fail(LPP_ERR_STATE, "tridiagonal QL did not converge");
+	for (int w = 0; w < nomega; w++) {
+		double re = 0, im = 0;
+		for (int l = 0; l < n; l++) {
+			double inten = z[l] * z[l];  // first component of eigenvector l
+			double xr = omega[w] - isign * (d[l] - eg);
+			double den = xr * xr + delta * delta;
+			re += weight * inten * xr / den;
+			im -= weight * inten * delta / den;
+		}
+		out[2 * w] = re;
+		out[2 * w + 1] = im;
+	}
+	return 0;
+}
+
+// ------------------------------------------------------------------ Krylov loop
+static int ensure_vectors(lpp_handle* h)
+{
+	if (!h->vx) CKR(dev_alloc(h, &h->vx, h->nloc));
+	if (!h->vy) CKR(dev_alloc(h, &h->vy, h->nloc));
+	if (h->desc.nranks > 1 && !h->yfull) CKR(dev_alloc(h, &h->yfull, h->rows));
+	CKR(ensure_partials(h, lpp_vec_blocks(h->nloc)));
+	return 0;
+}
+
+// sum of n block partials (+ allreduce over ranks) -> host double
+static int reduce_scalar(lpp_handle* h, int npartials, double* out)
+{
+	lpp_launch_finalize_sum(h->partials, npartials, h->scal_dev, h->stream);
+	h->launches += 1;
+	if (h->desc.nranks > 1) {
+		if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
+		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+	}
+	CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	*out = h->scal_host[0];
+	return 0;
+}
+
+// gather the row-sharded vector into the full-length buffer every rank needs as gather source (halo = whole vector)
+static int gather_full(lpp_handle* h, const double* local, const double** src)
+{
+	if (h->desc.nranks == 1) { *src = local; return 0; }
+	if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
+	CKN(g_nccl.GroupStart());
+	for (int r = 0; r < h->desc.nranks; r++)
+		CKN(g_nccl.Broadcast(local, h->yfull + h->shard_row0[r], h->shard_nloc[r], kNcclFloat64, r, h->comm, h->stream));
+	CKN(g_nccl.GroupEnd());
+	*src = h->yfull;
+	return 0;
+}
+
+struct LoopTiming {
+	int from = -1, to = -1;  // record ev0 before iteration `from`, ev1 after iteration `to-1`
+	int64_t launches_at_from = 0, launches_at_to = 0;
+};
+
+// PsimagLite::LanczosSolver::decomposition with the three vector sweeps fused into two:
+// the dot <y,x> rides on the SpMV epilogue, the swap/scale sweep is folded into scalar coefficients.
+// State: y = U_j (unnormalised Lanczos vector, v_j = U_j/n_j), x = U_{j-1}.
+static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bool check_convergence,
+                        const double* zcoef, double* z, double* a, double* b, int* nsteps, double* init_norm2,
+                        LoopTiming* tm)
+{
+	const uint64_t n = h->nloc;
+	double* x = h->vx;
+	double* y = h->vy;
+	int np = lpp_vec_blocks(n);
+	lpp_launch_dot(y, y, n, h->partials, h->stream);
+	h->launches += 1;
+	double nrm2 = 0;
+	CKR(reduce_scalar(h, np, &nrm2));
+	if (init_norm2) *init_norm2 = nrm2;
+	if (!(nrm2 > 0)) return fail(LPP_ERR_ARG, "initial Lanczos vector has zero norm");
+	double nj = sqrt(nrm2), nprev = 1.0, bprev = 0.0, eold = 100.0;
+	if ((uint64_t)steps > h->rows) steps = (int)h->rows;
+	int j = 0;
+	for (; j < steps; j++) {
+		if (tm && j == tm->from) { CK(cudaEventRecord(h->ev0, h->stream)); tm->launches_at_from = h->launches; }
+		if (zcoef) { lpp_launch_axpy(z, y, zcoef[j] / nj, n, h->stream); h->launches += 1; }
+		const double* src = nullptr;
+		CKR(gather_full(h, y, &src));
+		int nparts = 0;
+		CKR(do_spmv(h, p->kernel, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, src, true, &nparts));
+		double dot = 0;
+		CKR(reduce_scalar(h, nparts, &dot));
+		double aj = dot / nj;
+		lpp_launch_axpy_norm(x, y, aj / nj, n, h->partials, h->stream);
+		h->launches += 1;
+		double b2 = 0;
+		CKR(reduce_scalar(h, np, &b2));
+		double bj = sqrt(b2);
+		a[j] = aj;
+		b[j] = bj;
+		if (tm && j + 1 == tm->to) { CK(cudaEventRecord(h->ev1, h->stream)); tm->launches_at_to = h->launches; }
+		nprev = nj;
+		bprev = bj;
+		nj = (bj < 1e-10) ? 1.0 : bj;
+		std::swap(x, y);
+		if (check_convergence && p->eps > 0) {
+			double enew = tridiag_lowest(j + 1, a, b);
+			if (fabs(enew - eold) < p->eps && (j >= p->minsteps || h->rows <= 4)) { j++; break; }
+			eold = enew;
+		}
+	}
+	*nsteps = j;
+	return 0;
+}
+
+static int load_init(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int use_modified)
+{
+	CKR(ensure_vectors(h));
+	if (init_host) {
+		CK(cudaMemcpyAsync(h->vy, init_host + h->row0, sizeof(double) * h->nloc, cudaMemcpyHostToDevice, h->stream));
+	} else if (use_modified) {
+		if (!h->modified) return fail(LPP_ERR_STATE, "no modified vector in this handle (call lpp_apply_op first)");
+		CK(cudaMemcpyAsync(h->vy, h->modified, sizeof(double) * h->nloc, cudaMemcpyDeviceToDevice, h->stream));
+	} else {
+		lpp_launch_fill_random(h->vy, h->row0, h->nloc, p->seed, h->stream);
+		h->launches += 1;
+	}
+	return 0;
+}
+
+extern "C" int lpp_lanczos_decomposition(lpp_handle* h, const lpp_solver_params* p, const double* init_host,
+                                         int32_t use_modified, double* a, double* b, int32_t* nsteps, double* init_norm2)
+{
+	if (!h || !p || !a || !b || !nsteps) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	CKR(load_init(h, p, init_host, use_modified));
+	int ns = 0;
+	CKR(lanczos_loop(h, p, p->steps, true, nullptr, nullptr, a, b, &ns, init_norm2, nullptr));
+	*nsteps = ns;
+	return 0;
+}
+
+extern "C" int lpp_ground_state(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int32_t want_vector,
+                                double* energy, double* z_host, double* a, double* b, int32_t* nsteps)
+{
+	if (!h || !p || !energy) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	int cap = (int)std::min<uint64_t>((uint64_t)p->steps, h->rows);
+	std::vector<double> aa(cap + 1), bb(cap + 1);
+	CKR(load_init(h, p, init_host, 0));
+	int ns = 0;
+	CKR(lanczos_loop(h, p, p->steps, true, nullptr, nullptr, aa.data(), bb.data(), &ns, nullptr, nullptr));
+	std::vector<double> d(aa.begin(), aa.begin() + ns), e(ns, 0.0), zz((size_t)ns * ns);
+	for (int i = 0; i + 1 < ns; i++) e[i] = bb[i];
+	if (tridiag_full(ns, d, e, zz.data()) != 0) return fail(LPP_ERR_STATE, "tridiagonal QL did not converge");
+	*energy = d[0];
+	if (want_vector || z_host) {
+		// second pass: replay the identical recurrence, accumulating z = sum_j c_j v_j
+		std::vector<double> coef(ns);
+		for (int j = 0; j < ns; j++) coef[j] = zz[(size_t)j * ns + 0];
+		if (!h->gs) CKR(dev_alloc(h, &h->gs, h->nloc));
+		CK(cudaMemsetAsync(h->gs, 0, sizeof(double) * h->nloc, h->stream));
+		CKR(load_init(h, p, init_host, 0));
+		std::vector<double> a2(ns + 1), b2(ns + 1);
+		int ns2 = 0;
+		CKR(lanczos_loop(h, p, ns, false, coef.data(), h->gs, a2.data(), b2.data(), &ns2, nullptr, nullptr));
+		CK(cudaStreamSynchronize(h->stream));
+		if (z_host) CK(cudaMemcpy(z_host + h->row0, h->gs, sizeof(double) * h->nloc, cudaMemcpyDeviceToHost));
+	}
+	if (a) std::copy(aa.begin(), aa.begin() + ns, a);
+	if (b) std::copy(bb.begin(), bb.begin() + ns, b);
+	if (nsteps) *nsteps = ns;
+	return 0;
+}
+
+// ------------------------------------------------------------------ operator application / vectors
+extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb,
+                            double factor, int32_t accumulate)
+{
+	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
+	if (src->md.model != LPP_MODEL_HUBBARD || dst->md.model != LPP_MODEL_HUBBARD || orb != 0)
+		return fail(LPP_ERR_ARG, "lpp_apply_op supports HubbardOneBand bases (c, cdagger, n)");
+	if (op != LPP_OP_C && op != LPP_OP_CDAGGER && op != LPP_OP_N) return fail(LPP_ERR_ARG, "unsupported operator");
+	if (site < 0 || site >= src->md.nsite || spin < 0 || spin > 1) return fail(LPP_ERR_ARG, "bad site/spin");
+	if (!src->gs) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
+	if (src->desc.nranks != dst->desc.nranks || src->desc.rank != dst->desc.rank || src->device != dst->device)
+		return fail(LPP_ERR_ARG, "source and destination must share device and sharding");
+	if (src->desc.nranks > 1 && spin != 0)
+		return fail(LPP_ERR_ARG, "row-sharded operator application is local for spin-up operators only");
+	int dup = (op == LPP_OP_C) ? -1 : (op == LPP_OP_CDAGGER ? 1 : 0);
+	int eu = src->md.nup + (spin == 0 ? dup : 0), ed = src->md.ndn + (spin == 1 ? dup : 0);
+	if (dst->md.nup != eu || dst->md.ndn != ed || dst->md.nsite != src->md.nsite)
+		return fail(LPP_ERR_ARG, "destination sector does not match operator (hasNewParts, HubbardOneOrbital.h:212-230)");
+	CK(cudaSetDevice(dst->device));
+	if (!dst->modified) {
+		CKR(dev_alloc(dst, &dst->modified, dst->nloc));
+		accumulate = 0;
+	}
+	if (!accumulate) CK(cudaMemsetAsync(dst->modified, 0, sizeof(double) * dst->nloc, dst->stream));
+	CK(cudaStreamSynchronize(src->stream));
+	// source vector is indexed globally inside the kernel: shift the local pointer by the shard's first row
+	const double* srcv = src->gs - src->row0;
+	lpp_launch_apply_op(src->md, dst->md, op, site, spin, factor, srcv, dst->modified, dst->row0, dst->nloc, dst->stream);
+	dst->launches += 1;
+	CK(cudaStreamSynchronize(dst->stream));
+	CK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int lpp_get_vector(lpp_handle* h, int32_t which, double* out_host)
+{
+	if (!h || !out_host) return fail(LPP_ERR_ARG, "null argument");
+	const double* v = which == 0 ? h->gs : h->modified;
+	if (!v) return fail(LPP_ERR_STATE, "vector not available");
+	CK(cudaSetDevice(h->device));
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaMemcpy(out_host + h->row0, v, sizeof(double) * h->nloc, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int lpp_set_groundstate(lpp_handle* h, const double* z_host)
+{
+	if (!h || !z_host) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	if (!h->gs) CKR(dev_alloc(h, &h->gs, h->nloc));
+	CK(cudaMemcpy(h->gs, z_host + h->row0, sizeof(double) * h->nloc, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+// ------------------------------------------------------------------ communicator
+extern "C" int lpp_comm_unique_id(uint8_t id[128])
+{
+	CKR(nccl_load());
+	ncclUniqueId u;
+	CKN(g_nccl.GetUniqueId(&u));
+	memcpy(id, u.internal, 128);
+	return 0;
+}
+
+extern "C" int lpp_comm_init(lpp_handle* h, const uint8_t id[128])
+{
+	if (!h || !id) return fail(LPP_ERR_ARG, "null argument");
+	CKR(nccl_load());
+	CK(cudaSetDevice(h->device));
+	ncclUniqueId u;
+	memcpy(u.internal, id, 128);
+	CKN(g_nccl.CommInitRank(&h->comm, h->desc.nranks, u, h->desc.rank));
+	return 0;
+}
+
+// ------------------------------------------------------------------ measurement hooks
+extern "C" int lpp_bench_spmv(lpp_handle* h, int32_t kernel, int32_t iters, int32_t warmup, lpp_timing* t)
+{
+	if (!h || !t || iters < 1) return fail(LPP_ERR_ARG, "bad argument");
+	CK(cudaSetDevice(h->device));
+	CKR(ensure_vectors(h));
+	lpp_solver_params p{};
+	p.seed = 42;
+	lpp_launch_fill_random(h->vy, h->row0, h->nloc, 42, h->stream);
+	CK(cudaMemsetAsync(h->vx, 0, sizeof(double) * h->nloc, h->stream));
+	const double* src = nullptr;
+	CKR(gather_full(h, h->vy, &src));
+	for (int i = 0; i < warmup; i++) CKR(do_spmv(h, kernel, 1.0, 1.0, h->vx, src, false, nullptr));
+	CK(cudaStreamSynchronize(h->stream));
+	int64_t l0 = h->launches;
+	CK(cudaEventRecord(h->ev0, h->stream));
+	for (int i = 0; i < iters; i++) CKR(do_spmv(h, kernel, 1.0, 1.0, h->vx, src, false, nullptr));
+	CK(cudaEventRecord(h->ev1, h->stream));
+	CK(cudaEventSynchronize(h->ev1));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+	t->spmv_ms = ms / iters;
+	t->iter_ms = 0;
+	t->launches = h->launches - l0;
+	return 0;
+}
+
+extern "C" int lpp_bench_lanczos(lpp_handle* h, const lpp_solver_params* p, int32_t iters, int32_t warmup, lpp_timing* t)
+{
+	if (!h || !p || !t || iters < 1) return fail(LPP_ERR_ARG, "bad argument");
+	CK(cudaSetDevice(h->device));
+	lpp_solver_params q = *p;
+	q.eps = 0;
+	CKR(load_init(h, &q, nullptr, 0));
+	int total = warmup + iters;
+	if ((uint64_t)total > h->rows) return fail(LPP_ERR_ARG, "warmup+iters exceeds the Hilbert-space dimension");
+	std::vector<double> a(total + 1), b(total + 1);
+	LoopTiming tm;
+	tm.from = warmup;
+	tm.to = total;
+	int ns = 0;
+	CKR(lanczos_loop(h, &q, total, false, nullptr, nullptr, a.data(), b.data(), &ns, nullptr, &tm));
+	CK(cudaEventSynchronize(h->ev1));
+	float ms = 0;
+	CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+	t->iter_ms = ms / iters;
+	t->spmv_ms = 0;
+	t->launches = tm.launches_at_to - tm.launches_at_from;
+	return 0;
+}

@@ -1,0 +1,507 @@
+// lpp_kernels.cu -- sm_100a kernels: device basis construction (K1), per-spin hop tables, diagonal tables (K2),
+// generic / table-driven on-the-fly x = beta x + alpha H y (K3, K4), stored CRS build + SpMV (K5), the fused Lanczos
+// vector sweeps (K6, K7, K8) and operator application (K9).  The shared-memory tiled fast path is in lpp_tiled.cu.
+#include <cub/cub.cuh>
+#include "lpp_kernels.cuh"
+
+#define LPP_TPB 256
+
+// ------------------------------------------------------------------ reductions (fixed order => deterministic)
+__device__ __forceinline__ double lpp_warp_sum(double v)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	return v;
+}
+
+__device__ __forceinline__ double lpp_block_sum(double v)
+{
+	__shared__ double red[32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	v = lpp_warp_sum(v);
+	if (lane == 0) red[wid] = v;
+	__syncthreads();
+	const int nw = (blockDim.x + 31) >> 5;
+	v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+	if (wid == 0) v = lpp_warp_sum(v);
+	__syncthreads();
+	return v;  // valid in thread 0
+}
+
+// ------------------------------------------------------------------ K1: bases, ranks, tables
+__global__ void k_build_colex(const uint64_t* __restrict__ binom, int nsite, int npart, uint64_t n, word_t* __restrict__ out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = lpp_unrank_colex(binom, nsite, npart, i);
+}
+
+__global__ void k_build_feas(ModelDev m, int spin, uint64_t n, word_t* __restrict__ out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = lpp_unrank_feas(m, spin, i);
+}
+
+__global__ void k_rank(ModelDev m, int spin, const word_t* __restrict__ w, uint64_t n, uint64_t* __restrict__ out)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = lpp_rank_onespin(m, spin, w[i]);
+}
+
+// split colex rank tables: rank(w) = rlo[lo] + rhi[popc(lo)][hi]
+__global__ void k_split_tables(const uint64_t* __restrict__ binom, int nbits, int lobits, uint32_t* __restrict__ rlo,
+                               uint32_t* __restrict__ rhi)
+{
+	const int hibits = nbits - lobits;
+	const uint64_t nlo = 1ull << lobits, nhi = 1ull << hibits;
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < nlo) rlo[i] = lpp_split_lo_entry(binom, i);
+	if (i < (uint64_t)(lobits + 1) * nhi) rhi[i] = lpp_split_hi_entry(binom, lobits, hibits, i);
+}
+
+__global__ void k_lut(const word_t* __restrict__ b, uint64_t n, uint32_t* __restrict__ lut)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) lut[b[i]] = (uint32_t)i;
+}
+
+struct CountEmit {
+	int n;
+	__device__ void operator()(uint64_t, double) { n++; }
+};
+
+template <class Emit>
+__device__ __forceinline__ void lpp_spin_hops(const ModelDev& m, int spin, word_t ket, Emit& e)
+{
+	if (m.model == LPP_MODEL_HUBBARD) lpp_hubbard_spin_hops(m, spin, ket, e);
+	else lpp_feas_spin_hops(m, spin, ket, e);
+}
+
+__global__ void k_hop_count(ModelDev m, int spin, uint64_t n, uint32_t* __restrict__ cnt, uint32_t* __restrict__ maxcnt)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	CountEmit e{0};
+	lpp_spin_hops(m, spin, (spin ? m.b2 : m.b1)[i], e);
+	cnt[i] = (uint32_t)e.n;
+	atomicMax(maxcnt, (uint32_t)e.n);
+}
+
+struct EllEmit {
+	uint32_t* idx;
+	double* val;
+	uint64_t n, s;
+	int k;
+	__device__ void operator()(uint64_t t, double v)
+	{
+		idx[(uint64_t)k * n + s] = (uint32_t)t;
+		val[(uint64_t)k * n + s] = v;
+		k++;
+	}
+};
+
+__global__ void k_hop_fill(ModelDev m, int spin, HopTable t)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= t.n) return;
+	EllEmit e{t.idx, t.val, t.n, i, 0};
+	lpp_spin_hops(m, spin, (spin ? m.b2 : m.b1)[i], e);
+	for (int k = e.k; k < t.width; k++) {
+		t.idx[(uint64_t)k * t.n + i] = (uint32_t)i;
+		t.val[(uint64_t)k * t.n + i] = 0.0;
+	}
+}
+
+// K2: per-spin potential sums (Hubbard: HubbardHelper.h:180-183 ; FeAs: FeBasedSc.h:557-561)
+__global__ void k_spin_diag(ModelDev m, int spin, uint64_t n, double* __restrict__ dv)
+{
+	uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	word_t w = (spin ? m.b2 : m.b1)[i];
+	double s = 0;
+	if (m.model == LPP_MODEL_HUBBARD) {
+		for (int k = 0; k < m.nsite; k++) s += m.V[k] * (double)((w >> k) & 1);
+	} else {
+		for (int k = 0; k < m.nsite; k++)
+			for (int o = 0; o < m.orbitals; o++)
+				s += m.V[k + (o + m.orbitals * spin) * m.nsite] * (double)lpp_feas_occ(w, k, o, m.orbitals);
+	}
+	dv[i] = s;
+}
+
+void lpp_launch_build_colex(const uint64_t* binom, int nsite, int npart, uint64_t n, word_t* out, cudaStream_t s)
+{
+	k_build_colex<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(binom, nsite, npart, n, out);
+}
+void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out, cudaStream_t s)
+{
+	k_build_feas<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, n, out);
+}
+void lpp_launch_rank(const ModelDev& m, int spin, const word_t* w, uint64_t n, uint64_t* out, cudaStream_t s)
+{
+	k_rank<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, w, n, out);
+}
+void lpp_launch_split_tables(const uint64_t* binom, int nbits, int lobits, uint32_t* rlo, uint32_t* rhi, cudaStream_t s)
+{
+	uint64_t total = (uint64_t)(lobits + 1) << (nbits - lobits);
+	uint64_t nlo = 1ull << lobits;
+	uint64_t n = total > nlo ? total : nlo;
+	k_split_tables<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(binom, nbits, lobits, rlo, rhi);
+}
+void lpp_launch_lut(const word_t* b, uint64_t n, uint32_t* lut, cudaStream_t s)
+{
+	k_lut<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(b, n, lut);
+}
+void lpp_launch_hop_count(const ModelDev& m, int spin, uint64_t n, uint32_t* cnt, uint32_t* maxcnt, cudaStream_t s)
+{
+	k_hop_count<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, n, cnt, maxcnt);
+}
+void lpp_launch_hop_fill(const ModelDev& m, int spin, HopTable t, cudaStream_t s)
+{
+	k_hop_fill<<<(unsigned)((t.n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, t);
+}
+void lpp_launch_spin_diag(const ModelDev& m, int spin, uint64_t n, double* dv, cudaStream_t s)
+{
+	k_spin_diag<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, n, dv);
+}
+
+// ------------------------------------------------------------------ K3/K4 generic on-the-fly SpMV
+struct AccEmit {
+	const double* __restrict__ y;
+	double acc;
+	__device__ void operator()(uint64_t c, double v) { acc += v * y[c]; }
+};
+
+// One thread per row: hops enumerated with ffs/popc, signs from masked popcounts, target states ranked on the fly
+// (HubbardHelper.h:119-129 / FeBasedSc.h:66-105 / Heisenberg.h:94-106 as a gather).
+__global__ void __launch_bounds__(LPP_TPB) k_spmv_generic(ModelDev m, SpmvArgs a)
+{
+	uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x;
+	double contrib = 0.0;
+	if (t < a.nloc) {
+		uint64_t r = a.row0 + t;
+		LppRowKets k = lpp_row_kets(m, r);
+		double yr = a.y[r];
+		AccEmit e{a.y, lpp_row_diag(m, k) * yr};
+		lpp_row_offdiag(m, k, 0, e);
+		double xn = a.alpha * e.acc;
+		if (a.beta != 0.0) xn += a.beta * a.x[t];
+		a.x[t] = xn;
+		contrib = yr * xn;
+	}
+	if (a.dot_partials) {
+		double s = lpp_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+int lpp_spmv_generic_blocks(uint64_t nloc) { return (int)((nloc + LPP_TPB - 1) / LPP_TPB); }
+void lpp_launch_spmv_generic(const ModelDev& m, const SpmvArgs& a, cudaStream_t s)
+{
+	k_spmv_generic<<<lpp_spmv_generic_blocks(a.nloc), LPP_TPB, 0, s>>>(m, a);
+}
+
+// ------------------------------------------------------------------ K3 table-driven SpMV for product bases
+// bit-parallel form of findSnoDecay (FeBasedSc.h:573-623) without the potential part
+__device__ __forceinline__ double lpp_feas_diag_fast(const ModelDev& m, word_t k1, word_t k2)
+{
+	const int no = m.orbitals;
+	double s = m.U[0] * (double)lpp_popc(k1 & k2);
+	word_t m0 = 0;
+	for (int i = 0; i < m.nsite; i++) m0 |= lpp_bit(i * no);
+	for (int a = 0; a < no; a++) {
+		word_t A1 = (k1 >> a) & m0, A2 = (k2 >> a) & m0;
+		for (int b = a + 1; b < no; b++) {
+			word_t B1 = (k1 >> b) & m0, B2 = (k2 >> b) & m0;
+			int uu = lpp_popc(A1 & B1), ud = lpp_popc(A1 & B2), du = lpp_popc(A2 & B1), dd = lpp_popc(A2 & B2);
+			s += m.U[1] * (double)(uu + ud + du + dd);
+			s += m.U[4] * 0.25 * (double)(uu - ud - du + dd);
+			s += m.U[5] * (double)(uu + dd);
+		}
+	}
+	if (m.D[0] != 0.0) {
+		for (int i = 0; i < m.nsite; i++) {
+			word_t sm = lpp_below(no) << (i * no);
+			double sz = 0.5 * (double)(lpp_popc(k1 & sm) - lpp_popc(k2 & sm));
+			s += m.D[0] * sz * sz;
+		}
+	}
+	return s;
+}
+
+__device__ __forceinline__ double lpp_product_diag(const ModelDev& m, const DiagTables& dt, word_t k1, word_t k2,
+                                                   uint64_t i1, uint64_t i2)
+{
+	double s;
+	if (m.model == LPP_MODEL_HUBBARD) {
+		if (dt.uniformU) s = dt.U0 * (double)lpp_popc(k1 & k2);
+		else {
+			s = 0;
+			word_t b = k1 & k2;
+			while (b) { s += m.U[lpp_ctz(b)]; b &= b - 1; }
+		}
+	} else {
+		s = lpp_feas_diag_fast(m, k1, k2);
+	}
+	return s + dt.dv1[i1] + dt.dv2[i2];
+}
+
+struct TwoAccEmit {
+	const double* __restrict__ y;
+	uint64_t n1;
+	double acc;
+	__device__ void operator()(uint64_t a, uint64_t b, double v) { acc += v * y[a + b * n1]; }
+};
+
+// thread (u, d): x[d,u] = beta x + alpha ( diag*y + sum_k up[k][u] y[d, upidx] + sum_k dn[k][d] y[dnidx, u] (+ two-spin) )
+__global__ void __launch_bounds__(LPP_TPB) k_spmv_table(ModelDev m, HopTable up, HopTable dn, DiagTables dt, SpmvArgs a,
+                                                       uint32_t nbx)
+{
+	const uint64_t dl = blockIdx.x / nbx;                 // local slow index
+	const uint64_t u = (uint64_t)(blockIdx.x % nbx) * LPP_TPB + threadIdx.x;
+	const uint64_t d = a.row0 / m.n1 + dl;
+	double contrib = 0.0;
+	if (u < m.n1) {
+		const double* __restrict__ y = a.y;
+		const uint64_t base = d * m.n1;
+		word_t k1 = m.b1[u], k2 = m.b2[d];
+		double yr = y[base + u];
+		double acc = lpp_product_diag(m, dt, k1, k2, u, d) * yr;
+		const int cd = (int)dn.cnt[d];
+		for (int k = 0; k < cd; k++)
+			acc += dn.val[(uint64_t)k * dn.n + d] * y[(uint64_t)dn.idx[(uint64_t)k * dn.n + d] * m.n1 + u];
+		const int cu = (int)up.cnt[u];
+		for (int k = 0; k < cu; k++)
+			acc += up.val[(uint64_t)k * up.n + u] * y[base + up.idx[(uint64_t)k * up.n + u]];
+		if (m.model == LPP_MODEL_FEAS) {
+			TwoAccEmit e{y, m.n1, 0.0};
+			lpp_feas_twospin(m, k1, k2, m.u3_all_pairs, e);
+			acc += e.acc;
+		}
+		const uint64_t t = dl * m.n1 + u;
+		double xn = a.alpha * acc;
+		if (a.beta != 0.0) xn += a.beta * a.x[t];
+		a.x[t] = xn;
+		contrib = yr * xn;
+	}
+	if (a.dot_partials) {
+		double s = lpp_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+int lpp_spmv_table_blocks(const ModelDev& m, uint64_t nloc)
+{
+	uint64_t nbx = (m.n1 + LPP_TPB - 1) / LPP_TPB;
+	return (int)(nbx * (nloc / m.n1));
+}
+void lpp_launch_spmv_table(const ModelDev& m, const HopTable& up, const HopTable& dn, const DiagTables& dt,
+                           const SpmvArgs& a, cudaStream_t s)
+{
+	uint32_t nbx = (uint32_t)((m.n1 + LPP_TPB - 1) / LPP_TPB);
+	k_spmv_table<<<lpp_spmv_table_blocks(m, a.nloc), LPP_TPB, 0, s>>>(m, up, dn, dt, a, nbx);
+}
+
+// ------------------------------------------------------------------ K5 stored CRS
+__global__ void __launch_bounds__(128) k_crs_count(ModelDev m, uint64_t row0, uint64_t nloc, int64_t* __restrict__ counts,
+                                                   int* overflow)
+{
+	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nloc) return;
+	uint64_t c[LPP_ROW_CAP];
+	double v[LPP_ROW_CAP];
+	int n = lpp_stored_row(m, row0 + t, c, v);
+	if (n < 0) { *overflow = 1; n = 0; }
+	counts[t] = n;
+}
+
+__global__ void __launch_bounds__(128) k_crs_fill(ModelDev m, uint64_t row0, uint64_t nloc, const int64_t* __restrict__ rowptr,
+                                                  int64_t* __restrict__ colind, double* __restrict__ values)
+{
+	uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nloc) return;
+	uint64_t c[LPP_ROW_CAP];
+	double v[LPP_ROW_CAP];
+	int n = lpp_stored_row(m, row0 + t, c, v);
+	int64_t p = rowptr[t];
+	for (int i = 0; i < n; i++) { colind[p + i] = (int64_t)c[i]; values[p + i] = v[i]; }
+}
+
+void lpp_launch_crs_count(const ModelDev& m, uint64_t row0, uint64_t nloc, int64_t* counts, int* overflow, cudaStream_t s)
+{
+	k_crs_count<<<(unsigned)((nloc + 127) / 128), 128, 0, s>>>(m, row0, nloc, counts, overflow);
+}
+void lpp_launch_crs_fill(const ModelDev& m, uint64_t row0, uint64_t nloc, const int64_t* rowptr, int64_t* colind,
+                         double* values, cudaStream_t s)
+{
+	k_crs_fill<<<(unsigned)((nloc + 127) / 128), 128, 0, s>>>(m, row0, nloc, rowptr, colind, values);
+}
+
+void lpp_exclusive_scan(int64_t* data, uint64_t n, int64_t* total_dev, cudaStream_t s)
+{
+	// data[0..n) counts, data[n] = 0 on entry; exclusive scan over n+1 slots puts the total in data[n]
+	void* tmp = nullptr;
+	size_t bytes = 0;
+	cub::DeviceScan::ExclusiveSum(tmp, bytes, data, data, (int64_t)(n + 1), s);
+	cudaMallocAsync(&tmp, bytes, s);
+	cub::DeviceScan::ExclusiveSum(tmp, bytes, data, data, (int64_t)(n + 1), s);
+	cudaFreeAsync(tmp, s);
+	if (total_dev) cudaMemcpyAsync(total_dev, data + n, sizeof(int64_t), cudaMemcpyDeviceToDevice, s);
+}
+
+// PsimagLite::CrsMatrix::matrixVectorProduct: x += A y, LANES lanes per row
+template <int LANES>
+__global__ void __launch_bounds__(LPP_TPB) k_spmv_crs(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ colind,
+                                                     const double* __restrict__ values, SpmvArgs a)
+{
+	const uint64_t t = ((uint64_t)blockIdx.x * LPP_TPB + threadIdx.x) / LANES;
+	const int lane = threadIdx.x % LANES;
+	double contrib = 0.0;
+	double sum = 0.0;
+	if (t < a.nloc) {
+		for (int64_t k = rowptr[t] + lane; k < rowptr[t + 1]; k += LANES) sum += values[k] * a.y[colind[k]];
+	}
+#pragma unroll
+	for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LANES);
+	if (t < a.nloc && lane == 0) {
+		double xn = a.alpha * sum;
+		if (a.beta != 0.0) xn += a.beta * a.x[t];
+		a.x[t] = xn;
+		contrib = a.y[a.row0 + t] * xn;
+	}
+	if (a.dot_partials) {
+		double s = lpp_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+#define LPP_CRS_LANES 8
+int lpp_spmv_crs_blocks(uint64_t nloc) { return (int)((nloc * LPP_CRS_LANES + LPP_TPB - 1) / LPP_TPB); }
+void lpp_launch_spmv_crs(const int64_t* rowptr, const int64_t* colind, const double* values, const SpmvArgs& a,
+                         cudaStream_t s)
+{
+	k_spmv_crs<LPP_CRS_LANES><<<lpp_spmv_crs_blocks(a.nloc), LPP_TPB, 0, s>>>(rowptr, colind, values, a);
+}
+
+// ------------------------------------------------------------------ K6/K7/K8 Lanczos vector sweeps
+#define LPP_VEC_MAXBLOCKS (148 * 8)
+int lpp_vec_blocks(uint64_t n)
+{
+	uint64_t b = (n / 2 + LPP_TPB - 1) / LPP_TPB;
+	if (b < 1) b = 1;
+	return (int)(b > LPP_VEC_MAXBLOCKS ? LPP_VEC_MAXBLOCKS : b);
+}
+
+__global__ void __launch_bounds__(LPP_TPB) k_fill_random(double* __restrict__ v, uint64_t row0, uint64_t n, uint64_t seed)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LPP_TPB)
+		v[i] = lpp_splitmix_uniform(seed, row0 + i);
+}
+
+__global__ void __launch_bounds__(LPP_TPB) k_dot(const double* __restrict__ a, const double* __restrict__ b, uint64_t n,
+                                                double* __restrict__ partials)
+{
+	double s = 0.0;
+	const uint64_t n2 = n / 2;
+	const double2* a2 = reinterpret_cast<const double2*>(a);
+	const double2* b2 = reinterpret_cast<const double2*>(b);
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * LPP_TPB) {
+		double2 p = a2[i], q = b2[i];
+		s += p.x * q.x + p.y * q.y;
+	}
+	if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) s += a[n - 1] * b[n - 1];
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// PsimagLite oneStepDecomposition sweep 2: x -= a y ; b2 += |x|^2
+__global__ void __launch_bounds__(LPP_TPB) k_axpy_norm(double* __restrict__ x, const double* __restrict__ y, double coef,
+                                                      uint64_t n, double* __restrict__ partials)
+{
+	double s = 0.0;
+	const uint64_t n2 = n / 2;
+	double2* x2 = reinterpret_cast<double2*>(x);
+	const double2* y2 = reinterpret_cast<const double2*>(y);
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * LPP_TPB) {
+		double2 p = x2[i], q = y2[i];
+		p.x -= coef * q.x;
+		p.y -= coef * q.y;
+		x2[i] = p;
+		s += p.x * p.x + p.y * p.y;
+	}
+	if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+		double p = x[n - 1] - coef * y[n - 1];
+		x[n - 1] = p;
+		s += p * p;
+	}
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(LPP_TPB) k_axpy(double* __restrict__ z, const double* __restrict__ v, double coef, uint64_t n)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LPP_TPB)
+		z[i] += coef * v[i];
+}
+
+__global__ void __launch_bounds__(LPP_TPB) k_scale(double* __restrict__ v, double coef, uint64_t n)
+{
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LPP_TPB)
+		v[i] *= coef;
+}
+
+__global__ void __launch_bounds__(1024) k_finalize_sum(const double* __restrict__ partials, int n, double* __restrict__ out)
+{
+	double s = 0.0;
+	for (int i = threadIdx.x; i < n; i += 1024) s += partials[i];
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) out[0] = s;
+}
+
+void lpp_launch_fill_random(double* v, uint64_t row0, uint64_t n, uint64_t seed, cudaStream_t s)
+{
+	k_fill_random<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(v, row0, n, seed);
+}
+void lpp_launch_dot(const double* a, const double* b, uint64_t n, double* partials, cudaStream_t s)
+{
+	k_dot<<<lpp_vec_blocks(n), LPP_TPB, 0, s>>>(a, b, n, partials);
+}
+void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s)
+{
+	k_axpy_norm<<<lpp_vec_blocks(n), LPP_TPB, 0, s>>>(x, y, coef, n, partials);
+}
+void lpp_launch_axpy(double* z, const double* v, double coef, uint64_t n, cudaStream_t s)
+{
+	k_axpy<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(z, v, coef, n);
+}
+void lpp_launch_scale(double* v, double coef, uint64_t n, cudaStream_t s)
+{
+	k_scale<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(v, coef, n);
+}
+void lpp_launch_finalize_sum(const double* partials, int n, double* out, cudaStream_t s)
+{
+	k_finalize_sum<<<1, 1024, 0, s>>>(partials, n, out);
+}
+
+// ------------------------------------------------------------------ K9 operator application
+// Engine.h:416-458 as a gather on the destination basis: every destination state has at most one source.
+// c:       dst word has the site empty, source = dst | bit      (BasisOneSpin.h:127-134)
+// cdagger: dst word has the site occupied, source = dst ^ bit   (:135-142)
+// n:       same sector, site occupied                            (:143-147)
+__global__ void __launch_bounds__(LPP_TPB) k_apply_op(ModelDev src, ModelDev dst, int op, int site, int spin, double factor,
+                                                     const double* __restrict__ srcv, double* __restrict__ z,
+                                                     uint64_t dst_row0, uint64_t dst_nloc)
+{
+	uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x;
+	if (t >= dst_nloc) return;
+	uint64_t srow;
+	double sg;
+	if (!lpp_apply_op_source(src, dst, op, site, spin, dst_row0 + t, &srow, &sg)) return;
+	z[t] += factor * sg * srcv[srow];
+}
+
+void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, double factor,
+                         const double* srcv, double* z, uint64_t dst_row0, uint64_t dst_nloc, cudaStream_t s)
+{
+	k_apply_op<<<(unsigned)((dst_nloc + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(src, dst, op, site, spin, factor, srcv, z,
+	                                                                            dst_row0, dst_nloc);
+}

@@ -1,0 +1,72 @@
+// lpp_kernels.cuh -- launch wrappers of the sm_100a kernels (definitions in lpp_kernels.cu, lpp_tiled.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "lpp_device.cuh"
+
+// per-spin hop table in ELL form, column-major: entry k of one-spin state s is idx[k*n+s], val[k*n+s];
+// padded entries have val = 0 and idx = s.
+struct HopTable {
+	uint32_t* idx;
+	double* val;
+	uint32_t* cnt;
+	int width;
+	uint64_t n;
+};
+
+// per-spin diagonal pieces of product-basis models
+struct DiagTables {
+	const double* dv1;   // sum_i V_i n_i for each up state
+	const double* dv2;   // same, down
+	int uniformU;        // Hubbard: all U equal -> U0 * popc(up & dn)
+	double U0;
+};
+
+struct SpmvArgs {
+	double alpha, beta;      // x = beta*x + alpha*(H y)
+	double* x;               // local rows
+	const double* y;         // full vector (global indexing)
+	double* dot_partials;    // optional: per-block partial sums of y_local . x_new
+	uint64_t row0, nloc;     // first global row and number of local rows
+};
+
+void lpp_launch_build_colex(const uint64_t* binom, int nsite, int npart, uint64_t n, word_t* out, cudaStream_t s);
+void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out, cudaStream_t s);
+void lpp_launch_rank(const ModelDev& m, int spin, const word_t* w, uint64_t n, uint64_t* out, cudaStream_t s);
+void lpp_launch_split_tables(const uint64_t* binom, int nbits, int lobits, uint32_t* rlo, uint32_t* rhi, cudaStream_t s);
+void lpp_launch_lut(const word_t* b, uint64_t n, uint32_t* lut, cudaStream_t s);
+void lpp_launch_hop_count(const ModelDev& m, int spin, uint64_t n, uint32_t* cnt, uint32_t* maxcnt, cudaStream_t s);
+void lpp_launch_hop_fill(const ModelDev& m, int spin, HopTable t, cudaStream_t s);
+void lpp_launch_spin_diag(const ModelDev& m, int spin, uint64_t n, double* dv, cudaStream_t s);
+
+int lpp_spmv_generic_blocks(uint64_t nloc);
+void lpp_launch_spmv_generic(const ModelDev& m, const SpmvArgs& a, cudaStream_t s);
+int lpp_spmv_table_blocks(const ModelDev& m, uint64_t nloc);
+void lpp_launch_spmv_table(const ModelDev& m, const HopTable& up, const HopTable& dn, const DiagTables& dt,
+                           const SpmvArgs& a, cudaStream_t s);
+
+// stored CRS
+void lpp_launch_crs_count(const ModelDev& m, uint64_t row0, uint64_t nloc, int64_t* counts, int* overflow, cudaStream_t s);
+void lpp_launch_crs_fill(const ModelDev& m, uint64_t row0, uint64_t nloc, const int64_t* rowptr, int64_t* colind,
+                         double* values, cudaStream_t s);
+void lpp_exclusive_scan(int64_t* data, uint64_t n, int64_t* total_dev, cudaStream_t s);  // in place; data has n+1 slots
+int lpp_spmv_crs_blocks(uint64_t nloc);
+void lpp_launch_spmv_crs(const int64_t* rowptr, const int64_t* colind, const double* values, const SpmvArgs& a,
+                         cudaStream_t s);
+
+// Lanczos vector kernels
+int lpp_vec_blocks(uint64_t n);
+void lpp_launch_fill_random(double* v, uint64_t row0, uint64_t n, uint64_t seed, cudaStream_t s);
+void lpp_launch_dot(const double* a, const double* b, uint64_t n, double* partials, cudaStream_t s);
+// x -= coef*y ; partials <- block sums of x_new^2
+void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_axpy(double* z, const double* v, double coef, uint64_t n, cudaStream_t s);
+void lpp_launch_scale(double* v, double coef, uint64_t n, cudaStream_t s);
+// out[0] = sum of partials[0..n) in a fixed order
+void lpp_launch_finalize_sum(const double* partials, int n, double* out, cudaStream_t s);
+
+// operator application (Engine.h:416-458), gather form on the destination basis
+void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, double factor,
+                         const double* srcv, double* z, uint64_t dst_row0, uint64_t dst_nloc, cudaStream_t s);
+
+// tiled two-sweep kernels (lpp_tiled.cu)
+struct TiledPlan;

@@ -768,30 +768,29 @@ void orc_crs_matvec(size_t rows, const int64_t* rowptr, const int64_t* colind, c
 	}
 }
 
-/* x += H y on the fly.
+/* x += H y on the fly, rows [r0, r1); x is indexed from r0 (x[r - r0]), y is the full vector.
  * faithful=1: HubbardHelper.h:105-134 (serial diagonal pass recomputed per call, per-row heap SparseRow),
  *             FeBasedSc.h:66-105 (diag inline per row).  Heisenberg has no OTF in the reference
  *             (ModelBase.h:73-79 throws); its semantics are those of the stored builder.
  * faithful=0: same arithmetic, diagonal inline and row buffer reused (tuned CPU baseline). */
-void orc_matvec(const orc_model* m, double* x, const double* y, int faithful)
+void orc_matvec_range(const orc_model* m, double* x, const double* y, int faithful, int64_t r0, int64_t r1)
 {
-	int64_t hilbert = (int64_t)orc_rows(m);
 	if (faithful && m->model == ORC_HUBBARD) {
-		double* diag = (double*)malloc(sizeof(double) * hilbert);
-		for (int64_t r = 0; r < hilbert; r++) {
+		double* diag = (double*)malloc(sizeof(double) * (size_t)(r1 - r0));
+		for (int64_t r = r0; r < r1; r++) {
 			word_t k1, k2;
 			row_kets(m, r, &k1, &k2);
-			diag[r] = hubbard_diag(m, k1, k2);
+			diag[r - r0] = hubbard_diag(m, k1, k2);
 		}
-		for (int64_t r = 0; r < hilbert; r++) x[r] += diag[r] * y[r];
+		for (int64_t r = r0; r < r1; r++) x[r - r0] += diag[r - r0] * y[r];
 		free(diag);
 #pragma omp parallel for schedule(static)
-		for (int64_t r = 0; r < hilbert; r++) {
+		for (int64_t r = r0; r < r1; r++) {
 			srow row = {0};
 			word_t k1, k2;
 			row_kets(m, r, &k1, &k2);
 			row_offdiag(m, &row, k1, k2, 0);
-			x[r] += srow_dot(&row, y);
+			x[r - r0] += srow_dot(&row, y);
 			free(row.cols); free(row.vals);
 		}
 		return;
@@ -800,17 +799,46 @@ void orc_matvec(const orc_model* m, double* x, const double* y, int faithful)
 	{
 		srow row = {0};
 #pragma omp for schedule(static)
-		for (int64_t r = 0; r < hilbert; r++) {
+		for (int64_t r = r0; r < r1; r++) {
 			word_t k1, k2;
 			row_kets(m, r, &k1, &k2);
 			row.n = 0;
-			x[r] += row_diag(m, k1, k2) * y[r];
+			x[r - r0] += row_diag(m, k1, k2) * y[r];
 			row_offdiag(m, &row, k1, k2, 0);
-			x[r] += srow_dot(&row, y);
+			x[r - r0] += srow_dot(&row, y);
 			if (faithful) { free(row.cols); free(row.vals); row.cols = NULL; row.vals = NULL; row.cap = 0; }
 		}
 		free(row.cols); free(row.vals);
 	}
+}
+
+void orc_matvec(const orc_model* m, double* x, const double* y, int faithful)
+{
+	orc_matvec_range(m, x, y, faithful, 0, (int64_t)orc_rows(m));
+}
+
+/* the three PsimagLite vector sweeps of one Lanczos step on n elements; used by the timed
+ * CPU baseline on a bounded sample. returns b. */
+double orc_lanczos_sweeps(double* x, double* y, int64_t n)
+{
+	double a = 0;
+#pragma omp parallel for reduction(+ : a) schedule(static)
+	for (int64_t i = 0; i < n; i++) a += y[i] * x[i];
+	double b = 0;
+#pragma omp parallel for reduction(+ : b) schedule(static)
+	for (int64_t i = 0; i < n; i++) {
+		x[i] -= a * y[i];
+		b += x[i] * x[i];
+	}
+	b = sqrt(b);
+	double bb = b < 1e-10 ? 1.0 : b;
+#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < n; i++) {
+		double tmp = y[i];
+		y[i] = x[i] / bb;
+		x[i] = -b * tmp;
+	}
+	return b;
 }
 
 /* ------------------------------------------------- tridiagonal eigen-solver */

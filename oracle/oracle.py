@@ -55,6 +55,9 @@ def lib():
         L.orc_crs_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_crs_matvec.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_matvec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_matvec_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64]
+        L.orc_lanczos_sweeps.restype = C.c_double
+        L.orc_lanczos_sweeps.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.orc_tridiag_eig.restype = C.c_int
         L.orc_tridiag_eig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_lanczos_decomposition.restype = C.c_int
@@ -169,6 +172,11 @@ class OracleModel:
         lib().orc_matvec(self.h, x.ctypes.data, y.ctypes.data, 1 if faithful else 0)
         return x
 
+    def matvec_range(self, x_local, y, r0, r1, faithful=True):
+        """x_local[r - r0] += (H y)[r] for r in [r0, r1): bounded-sample CPU baseline."""
+        lib().orc_matvec_range(self.h, x_local.ctypes.data, y.ctypes.data, 1 if faithful else 0, r0, r1)
+        return x_local
+
     def decomposition(self, init, steps=200, eps=1e-12, minsteps=4, faithful=False):
         n = self.rows()
         cap = min(steps, n) + 1
@@ -212,6 +220,10 @@ def decomposition_crs(rowptr, colind, vals, init, steps=200, eps=1e-12, minsteps
     ns = lib().orc_lanczos_decomposition_crs(n, rowptr.ctypes.data, colind.ctypes.data, vals.ctypes.data,
                                              init.ctypes.data, steps, eps, minsteps, a.ctypes.data, b.ctypes.data)
     return a[:ns].copy(), b[:ns].copy()
+
+
+def lanczos_sweeps(x, y):
+    return lib().orc_lanczos_sweeps(x.ctypes.data, y.ctypes.data, x.size)
 
 
 def num_threads():

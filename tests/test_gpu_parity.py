@@ -1,0 +1,177 @@
+"""GPU parity tests (run on a real B200 with `pytest -m gpu`): the CUDA path, called through the C-ABI, against the
+CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): basis words, ranks, CRS rowptr/colind bit-exact; x += H y <= 1e-13 relative;
+tridiagonal alpha/beta and ground-state energies <= 1e-10 relative; continued-fraction spectra <= 1e-8.
+"""
+import numpy as np
+import pytest
+
+from lanczosplusplus_b200 import geometry as geo
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def kernels_for(lpp, case):
+    if case["model"] == cases.HEISENBERG:
+        return [lpp.KERNEL_GENERIC, lpp.KERNEL_STORED, lpp.KERNEL_AUTO]
+    return [lpp.KERNEL_GENERIC, lpp.KERNEL_TABLE, lpp.KERNEL_TILED, lpp.KERNEL_STORED, lpp.KERNEL_AUTO]
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(1.0, np.abs(b).max())
+
+
+@pytest.mark.parametrize("name", sorted(cases.SMALL_CASES))
+def test_small_cases_full_parity(lpp, oracle, name):
+    case = cases.SMALL_CASES[name]
+    o = cases.make_oracle(oracle, case, fast_rank=0)
+    e = cases.make_engine(lpp, case)
+    assert e.rows() == o.rows()
+    nspin = 1 if case["model"] == cases.HEISENBERG else 2
+    for spin in range(nspin):
+        b = o.basis(spin)
+        assert np.array_equal(b, e.basis(spin))                          # bit-exact, built on device
+        assert np.array_equal(e.perfectIndex(spin, b), np.arange(len(b), dtype=np.uint64))
+    rp0, ci0, v0 = o.crs()
+    rp1, ci1, v1 = e.setupHamiltonian()
+    assert np.array_equal(rp0, rp1) and np.array_equal(ci0, ci1)        # bit-exact CRS structure
+    assert np.abs(v0 - v1).max() <= 1e-14 * max(1.0, np.abs(v0).max())
+    y = geo.splitmix64_vector(o.rows(), 42)
+    x0 = geo.splitmix64_vector(o.rows(), 7)
+    xref = x0.copy()
+    o.matvec(xref, y, faithful=True)                                      # x += H y, reference semantics
+    for k in kernels_for(lpp, case):
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, xref) <= 1e-13, (name, k)
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["c1_hub8", "hub_rand7", "feas4", "feas_2x2", "heis12", "hub6_pbc_V"])
+def test_lanczos_tridiagonal_and_energy(lpp, oracle, name):
+    case = cases.SMALL_CASES[name]
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    init = geo.splitmix64_vector(o.rows(), 1234)
+    e0, z0, a0, b0 = o.ground_state(init, 200, 1e-12, 4)
+    for k in kernels_for(lpp, case):
+        e = cases.make_engine(lpp, case, kernel=k)
+        solver = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=200, eps=1e-12, minsteps=4))
+        e1, z1, a1, b1 = solver.computeOneState(init, want_vector=True, copy_vector=True)
+        assert abs(e1 - e0) <= 1e-10 * max(1.0, abs(e0)), (name, k)
+        n = min(len(a0), len(a1), 25)                                     # before rounding noise is amplified
+        assert relerr(a1[:n], a0[:n]) <= 1e-10 and relerr(b1[:n], b0[:n]) <= 1e-10, (name, k)
+        assert abs(len(a1) - len(a0)) <= 2
+        assert abs(np.linalg.norm(z1) - 1.0) < 1e-9
+        r = -e1 * z1
+        o.matvec(r, z1, faithful=False)
+        assert np.linalg.norm(r) < 1e-5                                   # Ritz residual ||H z - E z||
+        assert abs(abs(z1 @ z0) - 1.0) < 1e-8
+        # device-generated initial vector == geometry.splitmix64_vector
+        e2, _, a2, b2 = solver.computeOneState(None, want_vector=False)
+        assert abs(e2 - e1) <= 1e-12 * max(1.0, abs(e1)) and np.array_equal(a2, a1)
+        e.close()
+
+
+def test_known_answers(lpp):
+    pins = [("input0", -2.0 * np.sqrt(5.0)), ("hub2", 2.0 - np.sqrt(8.0)), ("c1_hub8", -4.235806999130),
+            ("heis4", -2.0), ("heis12", -5.387390917445), ("feas4", -1.957490136573)]
+    for name, ref in pins:
+        for k in (lpp.KERNEL_AUTO, lpp.KERNEL_STORED):
+            e = cases.make_engine(lpp, cases.SMALL_CASES[name], kernel=k)
+            en = lpp.Engine(e, {"LanczosSteps": 300, "LanczosEps": 1e-13})
+            assert abs(en.energies(0) - ref) <= 1e-10 * max(1.0, abs(ref)), (name, k)
+            e.close()
+
+
+def test_medium_sizes(lpp, oracle):
+    # input100.inp sector (dim 48400): survey-time value; Heisenberg 16-ring; Hubbard 12 sites (dim 853776) mat-vec
+    e = cases.make_engine(lpp, cases.feas_chain(6, 3, 3))
+    assert abs(lpp.Engine(e, {"LanczosSteps": 400}).energies(0) - (-3.099464014219)) < 1e-9
+    e.close()
+    e = cases.make_engine(lpp, cases.heisenberg_ring(16, 8))
+    assert abs(lpp.Engine(e, {"LanczosSteps": 400}).energies(0) - (-7.142296360617)) < 1e-9
+    e.close()
+    case = cases.hubbard_chain(12, 6, 6, periodic=True)
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    e = cases.make_engine(lpp, case)
+    y = geo.splitmix64_vector(o.rows(), 42)
+    xref = np.zeros(o.rows())
+    o.matvec(xref, y, faithful=False)
+    for k in (lpp.KERNEL_GENERIC, lpp.KERNEL_TABLE, lpp.KERNEL_TILED):
+        x = np.zeros(o.rows())
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, xref) <= 1e-13, k
+    e.close()
+    case = cases.feas_cluster(2, 3, 4, 4)                                  # dim 245025, orbital hoppings + U2/U3
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    e = cases.make_engine(lpp, case)
+    y = geo.splitmix64_vector(o.rows(), 42)
+    xref = np.zeros(o.rows())
+    o.matvec(xref, y, faithful=False)
+    for k in (lpp.KERNEL_GENERIC, lpp.KERNEL_TABLE, lpp.KERNEL_TILED):
+        x = np.zeros(o.rows())
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, xref) <= 1e-13, k
+    e.close()
+
+
+def test_continued_fraction_parity(lpp, oracle):
+    """Engine::spectralFunction (Engine.h:133-206) for c at sites (1,1) and (1,3), spin up, 6-site chain."""
+    case = cases.hubbard_chain(6, 3, 3)
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 1234)
+    e0, z0, _, _ = o.ground_state(init, 300, 1e-13, 4)
+    eng = cases.make_engine(lpp, case)
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13, "SpectralSteps": 150, "SpectralEps": 0.0}, init=init)
+    omega = np.linspace(-8, 8, 161)
+    for (isite, jsite) in ((1, 1), (1, 3)):
+        cfs = en.spectralFunction(lpp.OP_C, isite, jsite, spin=0)
+        assert len(cfs) == (2 if isite == jsite else 4)
+        for typ, cf in cfs:
+            lop = oracle.OP_C if (typ & 1) else oracle.OP_CDAGGER
+            dn = -1 if lop == oracle.OP_C else 1
+            od = cases.make_oracle(oracle, cases.hubbard_chain(6, 3 + dn, 3))
+            phi = np.zeros(od.rows())
+            o.apply_op(od, lop, isite, 0, 1.0, z0, phi)
+            o.apply_op(od, lop, jsite, 0, -1.0 if typ > 1 else 1.0, z0, phi)
+            a, b = od.decomposition(phi, steps=150, eps=0.0)
+            weight = (phi @ phi) * (-1.0 if typ > 1 else 1.0) * (1.0 if isite == jsite else 0.5)
+            s = -1 if (typ & 1) else 1
+            gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
+            g = cf(omega, 0.1)
+            assert np.abs(g - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max()), (isite, jsite, typ)
+    eng.close()
+
+
+def test_full_size_properties_c3(lpp):
+    """Config 3 (4x4 Hubbard, 8 up 8 down, dim 165 636 900): size-independent checks at the benchmark size."""
+    case = cases.hubbard_square(4, 4, 8, 8, U=4.0)
+    e = cases.make_engine(lpp, case)
+    n = e.rows()
+    assert n == 165636900
+    y1 = geo.splitmix64_vector(n, 42)
+    y2 = geo.splitmix64_vector(n, 43)
+    h1 = np.zeros(n)
+    e.matrixVectorProduct(h1, y1, kernel=lpp.KERNEL_TILED)
+    h1t = np.zeros(n)
+    e.matrixVectorProduct(h1t, y1, kernel=lpp.KERNEL_TABLE)
+    assert relerr(h1, h1t) <= 1e-13                                       # independent kernels agree
+    h2 = np.zeros(n)
+    e.matrixVectorProduct(h2, y2, kernel=lpp.KERNEL_TILED)
+    assert abs(y2 @ h1 - y1 @ h2) <= 1e-10 * abs(y2 @ h1)                 # Hermiticity <y2|H y1> = <y1|H y2>
+    h12 = h1.copy()
+    e.matrixVectorProduct(h12, y2, kernel=lpp.KERNEL_TILED)              # accumulate semantics + linearity
+    assert relerr(h12, h1 + h2) <= 1e-13
+    del h1, h1t, h2, h12, y1, y2
+    e.close()
+    # U = 0: free fermions, analytic ground state = 2 * sum of the 8 lowest single-particle levels
+    levels = np.sort(np.linalg.eigvalsh(geo.square(4, 4, -1.0)))
+    # the half-filled shell is degenerate: any of the degenerate ground states has this energy
+    eref = 2.0 * levels[:8].sum()
+    e = cases.make_engine(lpp, cases.hubbard_square(4, 4, 8, 8, U=0.0))
+    solver = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=120, eps=1e-11))
+    en, _, a, b = solver.computeOneState(None, want_vector=False)
+    assert abs(en - eref) <= 1e-8 * abs(eref)
+    e.close()

@@ -1,0 +1,69 @@
+"""CPU-side parity of the product's host/device code (lpp_device.cuh compiled by g++) against the oracle:
+basis words, ranks and CRS structure bit-exact; values and x += H y to 1e-13 relative."""
+import numpy as np
+import pytest
+
+from lanczosplusplus_b200 import geometry as geo
+from tests import cases
+from tests.hostcheck import HostModel, lib as hclib
+
+
+@pytest.mark.parametrize("name", sorted(cases.SMALL_CASES))
+@pytest.mark.parametrize("tables", [0, 1])
+def test_basis_rank_crs_matvec(oracle, name, tables):
+    case = cases.SMALL_CASES[name]
+    o = cases.make_oracle(oracle, case, fast_rank=0)
+    h = HostModel(case, use_tables=tables)
+    assert h.rows() == o.rows()
+    nspin = 1 if case["model"] == cases.HEISENBERG else 2
+    for spin in range(nspin):
+        bo, bh = o.basis(spin), h.basis(spin)
+        assert np.array_equal(bo, bh)                       # bit-exact ordering
+        step = max(1, len(bo) // 97)
+        for i in range(0, len(bo), step):
+            assert h.rank(spin, bo[i]) == i == o.rank(spin, bo[i])
+    rp0, ci0, v0 = o.crs()
+    rp1, ci1, v1 = h.crs()
+    assert np.array_equal(rp0, rp1) and np.array_equal(ci0, ci1)   # bit-exact structure
+    assert np.abs(v0 - v1).max() <= 1e-14 * max(1.0, np.abs(v0).max())
+    y = geo.splitmix64_vector(o.rows(), 42)
+    x0 = geo.splitmix64_vector(o.rows(), 7)
+    x1 = x0.copy()
+    o.matvec(x0, y, faithful=True)
+    h.matvec(x1, y)
+    assert np.abs(x0 - x1).max() <= 1e-13 * max(1.0, np.abs(x0).max())
+
+
+def test_bigger_bases_bit_exact(oracle):
+    for case in (cases.hubbard_square(4, 4, 8, 8), cases.feas_cluster(2, 4, 6, 6), cases.heisenberg_ring(16, 8),
+                 cases.hubbard_chain(18, 9, 9)):
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        h = HostModel(case, use_tables=1)
+        nspin = 1 if case["model"] == cases.HEISENBERG else 2
+        for spin in range(nspin):
+            b = o.basis(spin)
+            assert np.array_equal(b, h.basis(spin))
+            idx = np.random.default_rng(3).integers(0, len(b), 200)
+            for i in idx:
+                assert h.rank(spin, b[i]) == i
+
+
+def test_apply_op_matches_oracle(oracle):
+    src_case = cases.hubbard_chain(6, 3, 3)
+    for op, spin, dn in ((oracle.OP_C, 0, -1), (oracle.OP_CDAGGER, 0, 1), (oracle.OP_C, 1, -1), (oracle.OP_CDAGGER, 1, 1),
+                         (oracle.OP_N, 0, 0), (oracle.OP_N, 1, 0)):
+        dst_case = cases.hubbard_chain(6, 3 + (dn if spin == 0 else 0), 3 + (dn if spin == 1 else 0))
+        os_, od = cases.make_oracle(oracle, src_case), cases.make_oracle(oracle, dst_case)
+        hs, hd = HostModel(src_case), HostModel(dst_case)
+        v = geo.splitmix64_vector(os_.rows(), 5)
+        for site in range(6):
+            z0, z1 = np.zeros(od.rows()), np.zeros(od.rows())
+            os_.apply_op(od, op, site, spin, 0.7, v, z0)
+            hs.apply_op(hd, op, site, spin, 0.7, v, z1)
+            assert np.array_equal(z0, z1)
+
+
+def test_splitmix_matches_numpy():
+    v = geo.splitmix64_vector(64, 1234, offset=10**12)
+    for i in range(64):
+        assert hclib().hc_splitmix(1234, 10**12 + i) == v[i]
