@@ -1,0 +1,186 @@
+/*
+ * InternalProductCuda.h -- the drop-in a LanczosPlusPlus maintainer adds next to
+ * src/Engine/InternalProductOnTheFly.h and src/Engine/InternalProductStored.h.
+ *
+ * It satisfies the template-template slot `InternalProductTemplate` of Engine (Engine.h:37-52,
+ * LanczosDriver1.h:47-56): same typedefs, same two constructors, rows(), matrixVectorProduct(x,y) with
+ * x += H y semantics (InternalProductOnTheFly.h:76,115-123), specialSymmetrySector(), reflectionSector(),
+ * fullDiag().  All arithmetic happens in liblpp_b200.so (include/lpp_b200.h); this header only marshals the
+ * model description and converts status codes into the reference's err() exceptions.
+ *
+ * Compiles inside the reference tree (needs PsimagLite for SizeType, err(), Vector.h, Matrix.h); it is NOT
+ * compiled in this repository because PsimagLite is not available here.  The standalone
+ * equivalent used by this repository's own driver and tests is lanczosplusplus_b200/engine.py +
+ * host/lanczos_b200.cpp, which call the same C-ABI.
+ *
+ * Requirements on ModelType beyond the reference's ModelBase (three one-line accessors):
+ *   const ParametersModelType& params() const;     // hubbardU / potentialV / orbitals / anisotropyD ...
+ *   static int cudaModelId();                       // LPP_MODEL_HUBBARD | LPP_MODEL_FEAS | LPP_MODEL_HEISENBERG
+ */
+#ifndef INTERNALPRODUCT_CUDA_H
+#define INTERNALPRODUCT_CUDA_H
+
+#include <vector>
+#include <cassert>
+#include "Vector.h"
+#include "Matrix.h"
+#include "lpp_b200.h"
+
+namespace LanczosPlusPlus {
+
+template<typename ModelType_, typename SpecialSymmetryType_>
+class InternalProductCuda {
+
+public:
+
+	typedef ModelType_ ModelType;
+	typedef SpecialSymmetryType_ SpecialSymmetryType;
+	typedef typename ModelType::BasisBaseType BasisType;
+	typedef typename SpecialSymmetryType::SparseMatrixType SparseMatrixType;
+	typedef typename ModelType::RealType RealType;
+	typedef typename ModelType::GeometryType GeometryType;
+	typedef typename GeometryType::ComplexOrRealType ComplexOrRealType;
+	typedef PsimagLite::Matrix<ComplexOrRealType> MatrixType;
+	typedef typename PsimagLite::Vector<RealType>::Type VectorRealType;
+	typedef typename PsimagLite::Vector<ComplexOrRealType>::Type VectorType;
+
+	// Engine::spectralFunction path: a new-sector basis (Engine.h:186-187)
+	InternalProductCuda(const ModelType& model,
+	                    const BasisType& basis,
+	                    SpecialSymmetryType&)
+	    : model_(model), basis_(basis), handle_(0)
+	{
+		init();
+	}
+
+	// Engine::computeAllStatesBelow path (Engine.h:608)
+	InternalProductCuda(const ModelType& model,
+	                    SpecialSymmetryType&)
+	    : model_(model), basis_(model.basis()), handle_(0)
+	{
+		init();
+	}
+
+	~InternalProductCuda()
+	{
+		if (handle_) lpp_destroy(handle_);
+	}
+
+	SizeType rows() const
+	{
+		return basis_.size();
+	}
+
+	// x += H y.  Host vectors cross PCIe on every call: kept for drop-in completeness and parity tests.
+	// The production path is decomposition()/groundState() below, which keep the Krylov loop on the GPU.
+	void matrixVectorProduct(VectorType& x, const VectorType& y) const
+	{
+		assert(x.size() == rows() && y.size() == rows());
+		check(lpp_matvec_host(handle_, LPP_KERNEL_AUTO, &(x[0]), &(y[0])));
+	}
+
+	SizeType reflectionSector() const { return 0; }
+
+	void specialSymmetrySector(SizeType) { }
+
+	void fullDiag(VectorRealType&,
+	              MatrixType&)
+	{
+		err("no fullDiag possible when on the GPU\n");
+	}
+
+	// Device-resident replacement of LanczosSolver::decomposition(init, ab) (Engine.h:474-478).
+	template<typename TridiagonalMatrixType>
+	void decomposition(const VectorType& init,
+	                   TridiagonalMatrixType& ab,
+	                   SizeType steps,
+	                   RealType eps,
+	                   SizeType minSteps) const
+	{
+		lpp_solver_params p;
+		p.steps = steps; p.minsteps = minSteps; p.eps = eps; p.kernel = LPP_KERNEL_AUTO; p.reortho = 0; p.seed = 0;
+		typename PsimagLite::Vector<RealType>::Type a(steps + 1), b(steps + 1);
+		int32_t n = 0;
+		double nrm2 = 0;
+		check(lpp_lanczos_decomposition(handle_, &p, &(init[0]), 0, &(a[0]), &(b[0]), &n, &nrm2));
+		ab.resize(n);
+		for (SizeType i = 0; i < SizeType(n); ++i) {
+			ab.a(i) = a[i];
+			ab.b(i) = b[i];
+		}
+	}
+
+	// Device-resident replacement of LanczosSolver::computeOneState (Engine.h:626 with excited = 0).
+	void groundState(RealType& energy,
+	                 VectorType& z,
+	                 const VectorType& init,
+	                 SizeType steps,
+	                 RealType eps,
+	                 SizeType minSteps) const
+	{
+		lpp_solver_params p;
+		p.steps = steps; p.minsteps = minSteps; p.eps = eps; p.kernel = LPP_KERNEL_AUTO; p.reortho = 0; p.seed = 0;
+		z.resize(rows());
+		int32_t n = 0;
+		check(lpp_ground_state(handle_, &p, &(init[0]), 1, &energy, &(z[0]), 0, 0, &n));
+	}
+
+private:
+
+	static void check(int status)
+	{
+		if (status == 0) return;
+		err(PsimagLite::String("InternalProductCuda: ") + lpp_last_error() + "\n");
+	}
+
+	void init()
+	{
+		if (!PsimagLite::IsSame<ComplexOrRealType, double>::True)
+			err("InternalProductCuda: real double precision only (do not use useComplex)\n");
+
+		const GeometryType& geometry = model_.geometry();
+		const SizeType nsite = geometry.numberOfSites();
+		const int modelId = ModelType::cudaModelId();
+		const SizeType orbitals = (modelId == LPP_MODEL_FEAS) ? model_.orbitals(0) : 1;
+		const SizeType nb = nsite*orbitals;
+
+		// term 0 (and term 1 for Heisenberg): the values the models read through geometry_(i,orb,j,orb2,term)
+		// HubbardHelper.h:60-71 ; FeBasedSc.h:320-323 ; Heisenberg.h:54-58
+		std::vector<double> hop(nb*nb, 0.0), jzz;
+		for (SizeType i = 0; i < nsite; ++i)
+			for (SizeType o1 = 0; o1 < orbitals; ++o1)
+				for (SizeType j = 0; j < nsite; ++j)
+					for (SizeType o2 = 0; o2 < orbitals; ++o2)
+						hop[(i*orbitals + o1)*nb + j*orbitals + o2] = geometry(i, o1, j, o2, 0);
+		if (modelId == LPP_MODEL_HEISENBERG) {
+			jzz.resize(nb*nb, 0.0);
+			for (SizeType i = 0; i < nsite; ++i)
+				for (SizeType j = 0; j < nsite; ++j)
+					jzz[i*nb + j] = geometry(i, 0, j, 0, 1);
+		}
+
+		typename ProgramGlobals::PairIntType parts = basis_.parts();   // (nup, ndown) or (twiceS, szPlusConst)
+
+		lpp_desc d;
+		d.model = modelId;
+		d.nsite = nsite;
+		d.orbitals = orbitals;
+		d.nup = (modelId == LPP_MODEL_HEISENBERG) ? parts.second : parts.first;
+		d.ndown = (modelId == LPP_MODEL_HEISENBERG) ? 0 : parts.second;
+		d.feas_u3_all_pairs = 1;
+		d.hop = &(hop[0]);
+		d.jzz = jzz.size() ? &(jzz[0]) : 0;
+		model_.params().exportForCuda(d);   // fills U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy
+		d.device = 0;
+		d.rank = 0;
+		d.nranks = 1;
+		check(lpp_create(&d, &handle_));
+	}
+
+	const ModelType& model_;
+	const BasisType& basis_;
+	lpp_handle* handle_;
+}; // class InternalProductCuda
+} // namespace LanczosPlusPlus
+
+#endif // INTERNALPRODUCT_CUDA_H

@@ -1,27 +1,78 @@
-// lpp_tiled.cu -- product-basis fast path (HubbardOneBand, FeAsBasedSc hopping part):
-//   x = beta x + alpha (D + 1 (x) T_dn) y      sweep A: column panels, down-hops are whole coalesced row segments
-//   x += alpha (T_up (x) 1) y                  sweep B: one up-segment (row of the Ndn x Nup matrix) staged in shared memory
-//   x += alpha (two-spin on-site terms) y      sweep C: FeAs U2/U3 only
-// The vector is viewed as the matrix Y[idn][iup] (index = iup + idn*Nup, BasisHubbardLanczos.h:59-63).
+// lpp_tiled.cu -- product-basis fast path (HubbardOneBand, FeAsBasedSc hopping part).
+//
+// The vector is the matrix Y[idn][iup] (index = iup + idn*Nup, BasisHubbardLanczos.h:59-63) and
+// H = D + 1 (x) T_dn + T_up (x) 1 (+ on-site two-spin terms for FeAs), applied as
+//   sweep A  x = beta x + alpha (D + 1 (x) T_dn) y : tile = (hop-closed block of down states) x (W contiguous columns).
+//            The block (all arrangements of the particles on the lower sites for one fixed pattern of the top F sites)
+//            is staged in shared memory; hops inside the block are conflict-free shared-memory reads with a
+//            sub-warp-uniform table entry, hops that leave the block are coalesced W*8-byte reads served by L2.
+//   sweep B  x += alpha (T_up (x) 1) y             : tile = (R rows) x (contiguous block of up states), rows interleaved in
+//            shared memory so one 16-byte gather serves both rows; table entries are 4 bytes.
+//   sweep C  x += alpha (two-spin terms) y         : FeAs U2/U3 only.
+// Hop tables are per spin species (O(N_spin * z) entries), built on device; the Hamiltonian itself is never stored.
+#include <algorithm>
+#include <cstdlib>
 #include <string>
+#include <vector>
 #include "lpp_tiled.cuh"
 
 static thread_local std::string g_terr;
 const char* lpp_tiled_error() { return g_terr.c_str(); }
 
+#define TCK(call)                                                                  \
+	do {                                                                           \
+		cudaError_t e_ = (call);                                                   \
+		if (e_ != cudaSuccess) { g_terr = std::string(#call) + ": " + cudaGetErrorString(e_); return -1; } \
+	} while (0)
+
+// compressed table entry: [31] sign, [30] leaves the block, [24..29] magnitude index, [0..23] index
+// (index = position inside the block for internal hops, one-spin state index for external hops)
+#define TE_SIGN 0x80000000u
+#define TE_EXT 0x40000000u
+#define TE_IDX 0x00ffffffu
+#define LPP_MAXMAG 16
+
+struct MagTable {
+	double mag[LPP_MAXMAG];
+	int nmag;
+};
+
+struct SpinPlan {
+	uint32_t* tab = nullptr;      // down: row-major [s][width]; up: column-major [k][n]
+	uint32_t* meta = nullptr;     // per state: cnt | (next << 8)   (externals are sorted first)
+	uint32_t* rowlist = nullptr;  // states grouped by block
+	uint32_t* blk_off = nullptr;  // nblocks+1
+	uint32_t* local = nullptr;    // position of a state inside its block
+	uint32_t* blk_of = nullptr;   // block of a state
+	int width = 0, nblocks = 0;
+	uint32_t max_block = 0;
+	uint64_t n = 0;
+};
+
 struct TiledPlan {
-	uint64_t d0, dcount;
-	uint32_t nrowchunks, npanels;
-	int up_in_smem;
-	size_t up_smem_bytes;
-	int has_twospin;
-	int sm_count;
-	int dot_blocks;
+	uint64_t d0 = 0, dcount = 0, nloc = 0;
+	int v2 = 0;                   // 1: block kernels usable, 0: fall back to the v1 sweeps
+	MagTable mt;
+	SpinPlan dn, up;
+	int W = 16;                   // columns per sweep-A tile
+	int R = 2;                    // rows per sweep-B tile
+	size_t smemA = 0, smemB = 0;
+	std::vector<uint32_t> tilesA_host;
+	uint32_t* tilesA = nullptr;   // (block, panel) pairs intersecting the local rows: block ids only, panel-major grid
+	uint32_t ntilesA_blocks = 0, npanels = 0;
+	int has_twospin = 0;
+	int dot_blocks = 0;
+	std::vector<void*> allocs;
+	// v1 fallback
+	uint32_t nrowchunks = 0, npanels_v1 = 0;
+	int up_in_smem = 0;
+	size_t up_smem_bytes = 0;
 };
 
 #define PA_COLS 256
 #define PA_ROWS 8
 #define PB_THREADS 1024
+#define TA_THREADS 1024
 
 __device__ __forceinline__ double tiled_warp_sum(double v)
 {
@@ -86,9 +137,199 @@ __device__ __forceinline__ double tiled_diag(const ModelDev& m, const DiagTables
 	return s + dt.dv1[i1] + dt.dv2[i2];
 }
 
-// sweep A: thread = one column u of a 256-column panel, CTA walks PA_ROWS rows.  Every down-hop of row d is a
-// contiguous 2 KB read of another row of the same panel (CTA-uniform table entry, broadcast through L1).
-// blockIdx is panel-major so the panels in flight (a few tens of MB) stay L2 resident.
+__device__ __forceinline__ double te_amp(const MagTable& mt, uint32_t e)
+{
+	double a = mt.mag[(e >> 24) & 63u];
+	return (e & TE_SIGN) ? -a : a;
+}
+
+// =====================================================================================================
+// table compression: ELL (idx, val) -> 4-byte entries, externals first
+// =====================================================================================================
+__global__ void k_compress(HopTable t, MagTable mt, const uint32_t* __restrict__ blk_of, const uint32_t* __restrict__ local,
+                           uint32_t* __restrict__ tab, uint32_t* __restrict__ meta, int row_major, int* bad)
+{
+	uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= t.n) return;
+	const int cnt = (int)t.cnt[s];
+	const uint32_t myblk = blk_of[s];
+	int pos = 0, next = 0;
+	for (int pass = 0; pass < 2; pass++) {   // pass 0: hops leaving the block, pass 1: hops inside it
+		for (int k = 0; k < cnt; k++) {
+			uint32_t tgt = t.idx[(uint64_t)k * t.n + s];
+			double v = t.val[(uint64_t)k * t.n + s];
+			bool ext = blk_of[tgt] != myblk;
+			if (ext != (pass == 0)) continue;
+			double av = fabs(v);
+			int mi = -1;
+			for (int q = 0; q < mt.nmag; q++)
+				if (mt.mag[q] == av) mi = q;
+			if (mi < 0) { *bad = 1; mi = 0; }
+			uint32_t e = (ext ? (tgt | TE_EXT) : local[tgt]) | ((uint32_t)mi << 24) | (v < 0 ? TE_SIGN : 0u);
+			if (row_major) tab[s * (uint64_t)t.width + pos] = e;
+			else tab[(uint64_t)pos * t.n + s] = e;
+			pos++;
+		}
+		if (pass == 0) next = pos;
+	}
+	for (int k = pos; k < t.width; k++) {
+		if (row_major) tab[s * (uint64_t)t.width + k] = 0;
+		else tab[(uint64_t)k * t.n + s] = 0;
+	}
+	meta[s] = (uint32_t)cnt | ((uint32_t)next << 8);
+}
+
+// =====================================================================================================
+// sweep A v2: hop-closed block of down states in shared memory, W contiguous columns
+// =====================================================================================================
+template <int W>
+__global__ void __launch_bounds__(TA_THREADS, 1)
+k_sweep_down_blocks(ModelDev m, SpinPlan dn, MagTable mt, DiagTables dt, SpmvArgs a, uint64_t d0, uint64_t dcount,
+                    const uint32_t* __restrict__ tiles, uint32_t ntile_blocks)
+{
+	extern __shared__ double ys[];                       // [block row][W]
+	constexpr int RPW = 32 / W;                          // rows handled by one warp at a time
+	const uint32_t panel = blockIdx.x / ntile_blocks;
+	const uint32_t blk = tiles[blockIdx.x % ntile_blocks];
+	const uint32_t boff = dn.blk_off[blk], bsize = dn.blk_off[blk + 1] - boff;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = TA_THREADS / 32;
+	const int sub = lane / W, col = lane % W;
+	const unsigned submask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (sub * W));
+	const uint64_t n1 = m.n1;
+	const uint64_t u = (uint64_t)panel * W + col;
+	const bool ucol = u < n1;
+	const double* __restrict__ y = a.y;
+
+	// stage the whole block (gather sources) : W*8-byte row segments
+	for (uint32_t r = warp * RPW + sub; r < bsize; r += nwarps * RPW) {
+		const uint64_t d = dn.rowlist[boff + r];
+		ys[r * W + col] = ucol ? y[d * n1 + u] : 0.0;
+	}
+	__syncthreads();
+	// lanes past the last column stay alive (they take part in the shuffles) but neither load nor store
+	const uint64_t uc = ucol ? u : 0;
+	const word_t k1 = m.b1[uc];
+	const int width = dn.width;
+	for (uint32_t r = warp * RPW + sub; r < bsize; r += nwarps * RPW) {
+		const uint64_t d = dn.rowlist[boff + r];
+		if (d < d0 || d >= d0 + dcount) continue;        // row sharding: only local output rows (uniform per sub-warp)
+		const uint32_t meta = dn.meta[d];
+		const int cnt = (int)(meta & 0xffu), next = (int)((meta >> 8) & 0xffu);
+		// the sub-warp reads the row's (<= 4W) table entries with coalesced loads and broadcasts them by shuffle
+		const uint32_t* __restrict__ trow = dn.tab + d * (uint64_t)width;
+		const uint32_t e0 = (col < width) ? trow[col] : 0u;
+		const uint32_t e1 = (col + W < width) ? trow[col + W] : 0u;
+		const uint32_t e2 = (col + 2 * W < width) ? trow[col + 2 * W] : 0u;
+		const uint32_t e3 = (col + 3 * W < width) ? trow[col + 3 * W] : 0u;
+#define TA_ENTRY(kk) __shfl_sync(submask, ((kk) < W ? e0 : (kk) < 2 * W ? e1 : (kk) < 3 * W ? e2 : e3), ((kk) % W) + sub * W)
+		double acc = tiled_diag(m, dt, k1, m.b2[d], uc, d) * ys[r * W + col];
+		double acc2 = 0.0;
+		int k = 0;
+		for (; k + 1 < next; k += 2) {                   // hops leaving the block: coalesced reads served by L2
+			const uint32_t ea = TA_ENTRY(k);
+			const uint32_t eb = TA_ENTRY(k + 1);
+			const double va = y[(uint64_t)(ea & TE_IDX) * n1 + uc];
+			const double vb = y[(uint64_t)(eb & TE_IDX) * n1 + uc];
+			acc += te_amp(mt, ea) * va;
+			acc2 += te_amp(mt, eb) * vb;
+		}
+		for (; k < next; k++) {
+			const uint32_t ea = TA_ENTRY(k);
+			acc += te_amp(mt, ea) * y[(uint64_t)(ea & TE_IDX) * n1 + uc];
+		}
+		for (; k < cnt; k++) {                           // hops inside the block: shared memory, conflict free
+			const uint32_t ea = TA_ENTRY(k);
+			acc2 += te_amp(mt, ea) * ys[(ea & TE_IDX) * W + col];
+		}
+#undef TA_ENTRY
+		acc += acc2;
+		if (ucol) {
+			const uint64_t t = (d - d0) * n1 + u;
+			double xn = a.alpha * acc;
+			if (a.beta != 0.0) xn += a.beta * a.x[t];
+			a.x[t] = xn;
+		}
+	}
+}
+
+// =====================================================================================================
+// sweep B v2: R rows x one contiguous block of up states, rows interleaved in shared memory
+// =====================================================================================================
+template <int R>
+__global__ void __launch_bounds__(PB_THREADS, 1)
+k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0, uint64_t dcount, int want_dot)
+{
+	extern __shared__ double ys[];                       // [block position][R]
+	const uint32_t blk = blockIdx.x % up.nblocks;
+	const uint64_t dl0 = (uint64_t)(blockIdx.x / up.nblocks) * R;
+	const uint32_t boff = up.blk_off[blk], bsize = up.blk_off[blk + 1] - boff;  // up blocks are contiguous: state = boff + i
+	const uint64_t n1 = m.n1;
+	const double* __restrict__ y = a.y;
+	const double* yrow[R];
+	double* xrow[R];
+	bool live[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		live[r] = dl0 + r < dcount;
+		const uint64_t dl = live[r] ? dl0 + r : dl0;
+		yrow[r] = y + (d0 + dl) * n1;
+		xrow[r] = a.x + dl * n1;
+	}
+	for (uint32_t i = threadIdx.x; i < bsize; i += PB_THREADS) {
+		if (R == 2) {
+			double2 v;
+			v.x = yrow[0][boff + i];
+			v.y = live[1] ? yrow[1][boff + i] : 0.0;
+			reinterpret_cast<double2*>(ys)[i] = v;
+		} else {
+			ys[i] = yrow[0][boff + i];
+		}
+	}
+	__syncthreads();
+	double contrib = 0.0;
+	for (uint32_t i = threadIdx.x; i < bsize; i += PB_THREADS) {
+		const uint64_t u = boff + i;
+		const uint32_t meta = up.meta[u];
+		const int cnt = (int)(meta & 0xffu), next = (int)((meta >> 8) & 0xffu);
+		double acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0;
+		int k = 0;
+		for (; k < next; k++) {                          // hops leaving the block (only when the up basis is split)
+			const uint32_t e = up.tab[(uint64_t)k * n1 + u];
+			const double amp = te_amp(mt, e);
+#pragma unroll
+			for (int r = 0; r < R; r++) acc[r] += amp * yrow[r][e & TE_IDX];
+		}
+#pragma unroll 4
+		for (; k < cnt; k++) {
+			const uint32_t e = up.tab[(uint64_t)k * n1 + u];
+			const double amp = te_amp(mt, e);
+			if (R == 2) {
+				const double2 v = reinterpret_cast<const double2*>(ys)[e & TE_IDX];
+				acc[0] += amp * v.x;
+				acc[1] += amp * v.y;
+			} else {
+				acc[0] += amp * ys[e & TE_IDX];
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (!live[r]) continue;
+			double xn = xrow[r][u] + a.alpha * acc[r];
+			xrow[r][u] = xn;
+			contrib += ys[i * R + r] * xn;
+		}
+	}
+	if (want_dot && a.dot_partials) {
+		double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+// =====================================================================================================
+// v1 sweeps (fallbacks: too many distinct amplitudes, or one-spin bases that cannot be blocked)
+// =====================================================================================================
 __global__ void __launch_bounds__(PA_COLS) k_sweep_down(ModelDev m, HopTable dn, DiagTables dt, SpmvArgs a, uint64_t d0,
                                                        uint64_t dcount, uint32_t nrowchunks)
 {
@@ -115,7 +356,6 @@ __global__ void __launch_bounds__(PA_COLS) k_sweep_down(ModelDev m, HopTable dn,
 	}
 }
 
-// sweep B: CTA = one up-segment Y[d][0..Nup) staged in shared memory; up-hops are shared-memory gathers.
 __global__ void __launch_bounds__(PB_THREADS, 1) k_sweep_up_smem(ModelDev m, HopTable up, SpmvArgs a, uint64_t d0, int want_dot)
 {
 	extern __shared__ double ys[];
@@ -140,7 +380,6 @@ __global__ void __launch_bounds__(PB_THREADS, 1) k_sweep_up_smem(ModelDev m, Hop
 	}
 }
 
-// sweep B fallback when one up-segment does not fit in shared memory: gathers from global memory (L1/L2)
 __global__ void __launch_bounds__(256) k_sweep_up_global(ModelDev m, HopTable up, SpmvArgs a, uint64_t d0, uint32_t nbx,
                                                         int want_dot)
 {
@@ -191,36 +430,199 @@ __global__ void __launch_bounds__(256) k_sweep_twospin(ModelDev m, SpmvArgs a)
 	}
 }
 
+// =====================================================================================================
+// plan construction
+// =====================================================================================================
+template <class T>
+static int plan_upload(TiledPlan* p, T** out, const std::vector<T>& v)
+{
+	void* q = nullptr;
+	TCK(cudaMalloc(&q, std::max<size_t>(v.size(), 1) * sizeof(T)));
+	p->allocs.push_back(q);
+	if (!v.empty()) TCK(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+	*out = (T*)q;
+	return 0;
+}
+template <class T>
+static int plan_alloc(TiledPlan* p, T** out, size_t n)
+{
+	void* q = nullptr;
+	TCK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+	p->allocs.push_back(q);
+	*out = (T*)q;
+	return 0;
+}
+
+// group the one-spin states by the occupation pattern of the top `fsites` sites; keep basis order inside a group
+static void make_blocks(const std::vector<word_t>& words, int nbits_per_site, int nsite, int fsites,
+                        std::vector<uint32_t>& rowlist, std::vector<uint32_t>& blk_off, std::vector<uint32_t>& local,
+                        std::vector<uint32_t>& blk_of, uint32_t* max_block)
+{
+	const size_t n = words.size();
+	const int shift = (nsite - fsites) * nbits_per_site;
+	std::vector<uint64_t> key(n);
+	std::vector<uint64_t> keys;
+	for (size_t i = 0; i < n; i++) { key[i] = fsites ? (words[i] >> shift) : 0; keys.push_back(key[i]); }
+	std::sort(keys.begin(), keys.end());
+	keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+	const size_t nb = keys.size();
+	std::vector<uint32_t> count(nb, 0);
+	blk_of.resize(n);
+	for (size_t i = 0; i < n; i++) {
+		blk_of[i] = (uint32_t)(std::lower_bound(keys.begin(), keys.end(), key[i]) - keys.begin());
+		count[blk_of[i]]++;
+	}
+	blk_off.assign(nb + 1, 0);
+	for (size_t b = 0; b < nb; b++) blk_off[b + 1] = blk_off[b] + count[b];
+	std::vector<uint32_t> fill(nb, 0);
+	rowlist.resize(n);
+	local.resize(n);
+	*max_block = 0;
+	for (size_t i = 0; i < n; i++) {
+		uint32_t b = blk_of[i];
+		local[i] = fill[b];
+		rowlist[blk_off[b] + fill[b]++] = (uint32_t)i;
+	}
+	for (size_t b = 0; b < nb; b++) *max_block = std::max(*max_block, count[b]);
+}
+
+static int build_spin_plan(TiledPlan* p, SpinPlan* sp, const HopTable& t, const std::vector<word_t>& words, int bits_per_site,
+                           int nsite, uint32_t cap, bool need_contiguous, bool row_major, cudaStream_t s)
+{
+	std::vector<uint32_t> rowlist, blk_off, local, blk_of;
+	uint32_t mx = 0;
+	int f = 0;
+	for (; f <= nsite; f++) {
+		make_blocks(words, bits_per_site, nsite, f, rowlist, blk_off, local, blk_of, &mx);
+		if (mx <= cap) break;
+	}
+	if (mx > cap) { g_terr = "cannot block the one-spin basis"; return 1; }
+	if (need_contiguous) {
+		for (size_t i = 0; i < rowlist.size(); i++)
+			if (rowlist[i] != i) { g_terr = "up blocks are not contiguous"; return 1; }
+	}
+	sp->n = t.n;
+	sp->width = t.width;
+	sp->nblocks = (int)blk_off.size() - 1;
+	sp->max_block = mx;
+	if (plan_upload(p, &sp->rowlist, rowlist)) return -1;
+	if (plan_upload(p, &sp->blk_off, blk_off)) return -1;
+	if (plan_upload(p, &sp->local, local)) return -1;
+	if (plan_upload(p, &sp->blk_of, blk_of)) return -1;
+	if (plan_alloc(p, &sp->tab, (size_t)std::max(t.width, 1) * t.n)) return -1;
+	if (plan_alloc(p, &sp->meta, (size_t)t.n)) return -1;
+	int* bad = nullptr;
+	if (plan_alloc(p, &bad, 1)) return -1;
+	TCK(cudaMemsetAsync(bad, 0, sizeof(int), s));
+	k_compress<<<(unsigned)((t.n + 255) / 256), 256, 0, s>>>(t, p->mt, sp->blk_of, sp->local, sp->tab, sp->meta, row_major ? 1 : 0, bad);
+	int hbad = 0;
+	TCK(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+	TCK(cudaStreamSynchronize(s));
+	TCK(cudaGetLastError());
+	if (hbad) { g_terr = "hop amplitude not in the magnitude table"; return 1; }
+	return 0;
+}
+
 int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& up, const HopTable& dn, uint64_t row0,
                      uint64_t nloc, cudaStream_t s, TiledPlan** out)
 {
-	(void)hop_host; (void)up; (void)dn; (void)s;
 	if (m.model == LPP_MODEL_HEISENBERG) { g_terr = "tiled path is for product bases"; return -1; }
 	TiledPlan* p = new TiledPlan();
 	p->d0 = row0 / m.n1;
 	p->dcount = nloc / m.n1;
-	p->nrowchunks = (uint32_t)((p->dcount + PA_ROWS - 1) / PA_ROWS);
-	p->npanels = (uint32_t)((m.n1 + PA_COLS - 1) / PA_COLS);
-	p->up_smem_bytes = (size_t)m.n1 * sizeof(double);
+	p->nloc = nloc;
+	p->has_twospin = (m.model == LPP_MODEL_FEAS) ? 1 : 0;
 	int dev = 0, maxsm = 0;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-	cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev);
-	p->up_in_smem = (p->up_smem_bytes + 1024 <= (size_t)maxsm) ? 1 : 0;
-	if (p->up_in_smem) {
-		cudaError_t e = cudaFuncSetAttribute(k_sweep_up_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->up_smem_bytes);
-		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
+
+	// distinct hop magnitudes
+	p->mt.nmag = 0;
+	bool mags_ok = true;
+	for (int i = 0; i < m.nbits * m.nbits; i++) {
+		double av = fabs(hop_host[i]);
+		if (av == 0) continue;
+		bool found = false;
+		for (int q = 0; q < p->mt.nmag; q++) found = found || p->mt.mag[q] == av;
+		if (found) continue;
+		if (p->mt.nmag == LPP_MAXMAG) { mags_ok = false; break; }
+		p->mt.mag[p->mt.nmag++] = av;
 	}
-	p->has_twospin = (m.model == LPP_MODEL_FEAS) ? 1 : 0;
+	const char* env = getenv("LPP_TILED_V1");
+	bool try_v2 = mags_ok && up.width <= 255 && dn.width <= 255 && up.n < (1u << 24) && dn.n < (1u << 24) && !(env && env[0] == '1');
+	const char* envw = getenv("LPP_TILED_W");
+	p->W = envw ? atoi(envw) : 16;
+	if (p->W != 8 && p->W != 16 && p->W != 32) p->W = 16;
+	if (dn.width > 4 * p->W) try_v2 = false;
+	const char* envr = getenv("LPP_TILED_R");
+	p->R = envr ? atoi(envr) : 2;
+	if (p->R != 1 && p->R != 2) p->R = 2;
+	if (try_v2) {
+		std::vector<word_t> w1(m.n1), w2(m.n2);
+		if (cudaMemcpy(w1.data(), m.b1, sizeof(word_t) * m.n1, cudaMemcpyDeviceToHost) != cudaSuccess ||
+		    cudaMemcpy(w2.data(), m.b2, sizeof(word_t) * m.n2, cudaMemcpyDeviceToHost) != cudaSuccess) {
+			g_terr = "basis download failed";
+			delete p;
+			return -1;
+		}
+		const size_t budget = (size_t)maxsm - 2048;
+		uint32_t capA = (uint32_t)(budget / ((size_t)p->W * 8));
+		uint32_t capB = (uint32_t)(budget / ((size_t)p->R * 8));
+		int ra = build_spin_plan(p, &p->dn, dn, w2, m.orbitals, m.nsite, capA, false, true, s);
+		int rb = ra == 0 ? build_spin_plan(p, &p->up, up, w1, m.orbitals, m.nsite, capB, true, false, s) : ra;
+		if (ra < 0 || rb < 0) { delete p; return -1; }
+		if (ra == 0 && rb == 0) {
+			p->v2 = 1;
+			p->smemA = (size_t)p->dn.max_block * p->W * 8;
+			p->smemB = (size_t)p->up.max_block * p->R * 8;
+			// blocks of down states that contain at least one local row
+			std::vector<uint32_t> rowlist(m.n2), blk_off(p->dn.nblocks + 1);
+			cudaMemcpy(rowlist.data(), p->dn.rowlist, sizeof(uint32_t) * m.n2, cudaMemcpyDeviceToHost);
+			cudaMemcpy(blk_off.data(), p->dn.blk_off, sizeof(uint32_t) * blk_off.size(), cudaMemcpyDeviceToHost);
+			for (int b = 0; b < p->dn.nblocks; b++) {
+				bool hit = false;
+				for (uint32_t i = blk_off[b]; i < blk_off[b + 1] && !hit; i++)
+					hit = rowlist[i] >= p->d0 && rowlist[i] < p->d0 + p->dcount;
+				if (hit) p->tilesA_host.push_back((uint32_t)b);
+			}
+			if (plan_upload(p, &p->tilesA, p->tilesA_host)) { delete p; return -1; }
+			p->ntilesA_blocks = (uint32_t)p->tilesA_host.size();
+			p->npanels = (uint32_t)((m.n1 + p->W - 1) / p->W);
+			cudaError_t e1 = cudaSuccess;
+			if (p->W == 8) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
+			if (p->W == 16) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
+			if (p->W == 32) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
+			cudaError_t e2 = p->R == 2
+			                     ? cudaFuncSetAttribute(k_sweep_up_blocks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB)
+			                     : cudaFuncSetAttribute(k_sweep_up_blocks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB);
+			if (e1 != cudaSuccess || e2 != cudaSuccess) { g_terr = "cudaFuncSetAttribute(smem) failed"; delete p; return -1; }
+		}
+	}
+	if (!p->v2) {
+		p->nrowchunks = (uint32_t)((p->dcount + PA_ROWS - 1) / PA_ROWS);
+		p->npanels_v1 = (uint32_t)((m.n1 + PA_COLS - 1) / PA_COLS);
+		p->up_smem_bytes = (size_t)m.n1 * sizeof(double);
+		p->up_in_smem = (p->up_smem_bytes + 1024 <= (size_t)maxsm) ? 1 : 0;
+		if (p->up_in_smem) {
+			cudaError_t e = cudaFuncSetAttribute(k_sweep_up_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->up_smem_bytes);
+			if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
+		}
+	}
 	// the last sweep owns the dot-product partial sums
 	if (p->has_twospin) p->dot_blocks = (int)((nloc + 255) / 256);
+	else if (p->v2) p->dot_blocks = (int)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
 	else if (p->up_in_smem) p->dot_blocks = (int)p->dcount;
 	else p->dot_blocks = (int)(((m.n1 + 255) / 256) * p->dcount);
 	*out = p;
 	return 0;
 }
 
-void lpp_tiled_destroy(TiledPlan* p) { delete p; }
+void lpp_tiled_destroy(TiledPlan* p)
+{
+	if (!p) return;
+	for (void* q : p->allocs) cudaFree(q);
+	delete p;
+}
 
 int lpp_tiled_dot_blocks(const TiledPlan* p) { return p->dot_blocks; }
 
@@ -228,17 +630,32 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
                    const SpmvArgs& a, cudaStream_t s)
 {
 	int launches = 0;
-	uint64_t nblkA = (uint64_t)p->npanels * p->nrowchunks;
-	k_sweep_down<<<(unsigned)nblkA, PA_COLS, 0, s>>>(m, dn, dt, a, p->d0, p->dcount, p->nrowchunks);
-	launches++;
 	const int dot_in_b = p->has_twospin ? 0 : 1;
-	if (p->up_in_smem) {
-		k_sweep_up_smem<<<(unsigned)p->dcount, PB_THREADS, p->up_smem_bytes, s>>>(m, up, a, p->d0, dot_in_b);
+	if (p->v2) {
+		const unsigned gridA = p->ntilesA_blocks * p->npanels;
+		if (p->W == 8)
+			k_sweep_down_blocks<8><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
+		else if (p->W == 16)
+			k_sweep_down_blocks<16><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
+		else
+			k_sweep_down_blocks<32><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
+		launches++;
+		const unsigned gridB = (unsigned)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
+		if (p->R == 2) k_sweep_up_blocks<2><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
+		else k_sweep_up_blocks<1><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
+		launches++;
 	} else {
-		uint32_t nbx = (uint32_t)((m.n1 + 255) / 256);
-		k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
+		uint64_t nblkA = (uint64_t)p->npanels_v1 * p->nrowchunks;
+		k_sweep_down<<<(unsigned)nblkA, PA_COLS, 0, s>>>(m, dn, dt, a, p->d0, p->dcount, p->nrowchunks);
+		launches++;
+		if (p->up_in_smem) {
+			k_sweep_up_smem<<<(unsigned)p->dcount, PB_THREADS, p->up_smem_bytes, s>>>(m, up, a, p->d0, dot_in_b);
+		} else {
+			uint32_t nbx = (uint32_t)((m.n1 + 255) / 256);
+			k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
+		}
+		launches++;
 	}
-	launches++;
 	if (p->has_twospin) {
 		k_sweep_twospin<<<(unsigned)((a.nloc + 255) / 256), 256, 0, s>>>(m, a);
 		launches++;
