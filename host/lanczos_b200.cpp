@@ -1,0 +1,224 @@
+// host/lanczos_b200.cpp -- minimal stand-alone driver over the C-ABI (include/lpp_b200.h).
+//
+// Mirrors what `lanczos -f input.inp` does on the hot path (src/lanczos.cpp:99-227 -> LanczosDriver1.h:47-66):
+// read the input file, build the geometry's connection matrix, construct the model sector, run the Lanczos ground
+// state, print "Energy=".  Only the subset of the PsimagLite InputNg format used by the configs is understood:
+//   TotalNumberOfSites= NumberOfTerms= GeometryKind=chain|ladder GeometryOptions=ConstantValues IsPeriodicX= LadderLeg=
+//   Connectors ... (one block per geometry direction/term, in file order)   Model=HubbardOneBand|FeAsBasedSc|Heisenberg
+//   hubbardU / potentialV / MagneticField / AnisotropyD vectors   Orbitals= FeAsMode=INT_PAPER33
+//   TargetElectronsUp= TargetElectronsDown= TargetSzPlusConst= HeisenbergTwiceS=1
+//   SolverOptions= (InternalProductCuda | InternalProductStored)  LanczosSteps= LanczosEps= LanczosMinSteps= Threads=(ignored)
+// Usage: lanczos_b200 -f input.inp [-p precision] [--parse-only]
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "../include/lpp_b200.h"
+
+struct Input {
+	std::map<std::string, std::string> scalars;               // "Label=" lines
+	std::map<std::string, std::vector<std::vector<double>>> vectors;  // "label n v..." blocks, in file order per label
+};
+
+static bool is_number(const std::string& s)
+{
+	char* end = nullptr;
+	std::strtod(s.c_str(), &end);
+	return end != s.c_str() && *end == 0;
+}
+
+static Input parse(const std::string& path)
+{
+	std::ifstream f(path.c_str());
+	if (!f) throw std::runtime_error("cannot open " + path);
+	std::vector<std::string> tok;
+	std::string line;
+	Input in;
+	while (std::getline(f, line)) {
+		size_t h = line.find('#');
+		if (h != std::string::npos) line = line.substr(0, h);
+		size_t eq = line.find('=');
+		if (eq != std::string::npos) {
+			std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+			k.erase(0, k.find_first_not_of(" \t"));
+			k.erase(k.find_last_not_of(" \t;") + 1);
+			v.erase(0, v.find_first_not_of(" \t"));
+			v.erase(v.find_last_not_of(" \t\r;") + 1);
+			in.scalars[k] = v;
+			continue;
+		}
+		std::istringstream ss(line);
+		std::string t;
+		while (ss >> t) tok.push_back(t);
+	}
+	// "label n v1 .. vn"  or matrix form "label r c v..." (Connectors 2 2 ...): a label followed by numbers
+	for (size_t i = 0; i < tok.size();) {
+		if (is_number(tok[i])) { i++; continue; }
+		std::string label = tok[i++];
+		std::vector<double> nums;
+		while (i < tok.size() && is_number(tok[i])) nums.push_back(std::atof(tok[i++].c_str()));
+		if (nums.empty()) continue;
+		std::vector<double> vals;
+		size_t n = (size_t)nums[0];
+		if (nums.size() == n + 1) vals.assign(nums.begin() + 1, nums.end());
+		else if (nums.size() >= 2 && nums.size() == (size_t)(nums[0] * nums[1]) + 2) vals.assign(nums.begin() + 2, nums.end());
+		else vals.assign(nums.begin() + 1, nums.end());
+		in.vectors[label].push_back(vals);
+	}
+	return in;
+}
+
+static int geti(const Input& in, const std::string& k, int def, bool required = false)
+{
+	auto it = in.scalars.find(k);
+	if (it == in.scalars.end()) {
+		if (required) throw std::runtime_error("missing " + k + "=");
+		return def;
+	}
+	return std::atoi(it->second.c_str());
+}
+static double getd(const Input& in, const std::string& k, double def)
+{
+	auto it = in.scalars.find(k);
+	return it == in.scalars.end() ? def : std::atof(it->second.c_str());
+}
+static std::string gets(const Input& in, const std::string& k, const std::string& def)
+{
+	auto it = in.scalars.find(k);
+	return it == in.scalars.end() ? def : it->second;
+}
+
+// connection matrix of term `term`: chain (one Connectors block per term) or ladder (two blocks per term: along x, along y).
+// With orbitals > 1 a Connectors block holds an orbitals x orbitals matrix (TestSuite/inputs/input100.inp:17-19).
+static std::vector<double> connection_matrix(const Input& in, int nsite, int orbitals, int term)
+{
+	const int nb = nsite * orbitals;
+	std::vector<double> m((size_t)nb * nb, 0.0);
+	std::string kind = gets(in, "GeometryKind", "chain");
+	bool periodic = geti(in, "IsPeriodicX", 0) != 0;
+	auto it = in.vectors.find("Connectors");
+	if (it == in.vectors.end()) throw std::runtime_error("missing Connectors");
+	const auto& blocks = it->second;
+	auto orbmat = [&](const std::vector<double>& v, int a, int b) {
+		if ((int)v.size() == orbitals * orbitals) return v[a * orbitals + b];
+		return a == b ? v[0] : 0.0;   // ConstantValues: one number
+	};
+	auto bond = [&](int i, int j, const std::vector<double>& v) {
+		for (int a = 0; a < orbitals; a++)
+			for (int b = 0; b < orbitals; b++) {
+				m[(size_t)(i * orbitals + a) * nb + j * orbitals + b] = orbmat(v, a, b);
+				m[(size_t)(j * orbitals + b) * nb + i * orbitals + a] = orbmat(v, a, b);
+			}
+	};
+	if (kind == "chain") {
+		if ((int)blocks.size() <= term) throw std::runtime_error("not enough Connectors blocks");
+		for (int i = 0; i + 1 < nsite; i++) bond(i, i + 1, blocks[term]);
+		if (periodic && nsite > 2) bond(0, nsite - 1, blocks[term]);
+	} else if (kind == "ladder") {
+		int leg = geti(in, "LadderLeg", 2);
+		int lx = nsite / leg;
+		if ((int)blocks.size() < 2 * (term + 1)) throw std::runtime_error("ladder needs two Connectors blocks per term");
+		for (int x = 0; x < lx; x++)
+			for (int y = 0; y < leg; y++) {
+				int s = y + leg * x;
+				if (x + 1 < lx) bond(s, s + leg, blocks[2 * term]);
+				else if (periodic && lx > 2) bond(s, y, blocks[2 * term]);
+				if (y + 1 < leg) bond(s, s + 1, blocks[2 * term + 1]);
+			}
+	} else {
+		throw std::runtime_error("GeometryKind " + kind + " is not supported by this driver");
+	}
+	return m;
+}
+
+int main(int argc, char** argv)
+{
+	std::string file;
+	int precision = 12;
+	bool parse_only = false;
+	for (int i = 1; i < argc; i++) {
+		if (!strcmp(argv[i], "-f") && i + 1 < argc) file = argv[++i];
+		else if (!strcmp(argv[i], "-p") && i + 1 < argc) precision = std::atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--parse-only")) parse_only = true;
+	}
+	if (file.empty()) {
+		std::cerr << "USAGE: " << argv[0] << " -f input.inp [-p precision] [--parse-only]\n";
+		return 1;
+	}
+	try {
+		Input in = parse(file);
+		std::string model = gets(in, "Model", "");
+		lpp_desc d;
+		memset(&d, 0, sizeof(d));
+		d.nsite = geti(in, "TotalNumberOfSites", 0, true);
+		d.orbitals = 1;
+		std::vector<double> U, V, D, jzz;
+		if (in.vectors.count("hubbardU")) U = in.vectors["hubbardU"][0];
+		if (in.vectors.count("potentialV")) V = in.vectors["potentialV"][0];
+		if (model == "HubbardOneBand") {
+			d.model = LPP_MODEL_HUBBARD;
+			d.nup = geti(in, "TargetElectronsUp", 0, true);
+			d.ndown = geti(in, "TargetElectronsDown", 0, true);
+		} else if (model == "FeAsBasedSc") {
+			d.model = LPP_MODEL_FEAS;
+			d.orbitals = geti(in, "Orbitals", 2, true);
+			if (gets(in, "FeAsMode", "INT_PAPER33") != "INT_PAPER33") throw std::runtime_error("only FeAsMode=INT_PAPER33 is on the path");
+			d.nup = geti(in, "TargetElectronsUp", 0, true);
+			d.ndown = geti(in, "TargetElectronsDown", 0, true);
+			D.assign(1, getd(in, "AnisotropyD", 0.0));
+		} else if (model == "Heisenberg") {
+			d.model = LPP_MODEL_HEISENBERG;
+			if (geti(in, "HeisenbergTwiceS", 1) != 1) throw std::runtime_error("only HeisenbergTwiceS=1 is on the path");
+			d.nup = geti(in, "TargetSzPlusConst", 0, true);
+			if (in.vectors.count("MagneticField")) V = in.vectors["MagneticField"][0];
+			if (in.vectors.count("AnisotropyD")) D = in.vectors["AnisotropyD"][0];
+			jzz = connection_matrix(in, d.nsite, 1, 1);
+		} else {
+			throw std::runtime_error("Model=" + model + " is not on the accelerated path");
+		}
+		std::vector<double> hop = connection_matrix(in, d.nsite, d.orbitals, 0);
+		d.feas_u3_all_pairs = 1;
+		d.hop = hop.data();
+		d.jzz = jzz.empty() ? nullptr : jzz.data();
+		d.U = U.empty() ? nullptr : U.data(); d.nU = (int)U.size();
+		d.V = V.empty() ? nullptr : V.data(); d.nV = (int)V.size();
+		d.D = D.empty() ? nullptr : D.data(); d.nD = (int)D.size();
+		d.device = 0; d.rank = 0; d.nranks = 1;
+		std::string opts = gets(in, "SolverOptions", "none");
+		lpp_solver_params p;
+		p.steps = geti(in, "LanczosSteps", 200);
+		p.minsteps = geti(in, "LanczosMinSteps", 4);
+		p.eps = getd(in, "LanczosEps", 1e-12);
+		p.kernel = opts.find("InternalProductStored") != std::string::npos ? LPP_KERNEL_STORED : LPP_KERNEL_AUTO;
+		p.reortho = 0;
+		p.seed = 1234;
+		if (parse_only) {
+			std::cout << "model=" << d.model << " nsite=" << d.nsite << " orbitals=" << d.orbitals << " nup=" << d.nup
+			          << " ndown=" << d.ndown << " nU=" << d.nU << " nV=" << d.nV << " kernel=" << p.kernel << " hop01=" << hop[1]
+			          << " steps=" << p.steps << "\n";
+			return 0;
+		}
+		lpp_handle* h = nullptr;
+		if (lpp_create(&d, &h) != 0) throw std::runtime_error(lpp_last_error());
+		uint64_t rows = 0;
+		lpp_rows(h, &rows);
+		double energy = 0;
+		int32_t ns = 0;
+		if (lpp_ground_state(h, &p, nullptr, 1, &energy, nullptr, nullptr, nullptr, &ns) != 0)
+			throw std::runtime_error(lpp_last_error());
+		std::cout.precision(precision);
+		std::cout << "#Hilbert=" << rows << " LanczosSteps=" << ns << "\n";
+		std::cout << "Energy=" << energy << "\n";   // LanczosDriver1.h:64-66
+		lpp_destroy(h);
+	} catch (std::exception& e) {
+		std::cerr << "lanczos_b200: " << e.what() << "\n";
+		return 2;
+	}
+	return 0;
+}

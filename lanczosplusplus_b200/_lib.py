@@ -52,6 +52,24 @@ def build(force=False, verbose=False):
     return LIB_PATH
 
 
+DRIVER_SRC = os.path.join(_HERE, "..", "host", "lanczos_b200.cpp")
+DRIVER_BIN = os.path.join(_HERE, "..", "host", "lanczos_b200")
+
+
+def build_driver(force=False):
+    """Compile the stand-alone C++ driver (host/lanczos_b200.cpp) against the in-tree shared library."""
+    build()
+    if not force and os.path.exists(DRIVER_BIN) and os.path.getmtime(DRIVER_BIN) >= max(
+            os.path.getmtime(DRIVER_SRC), os.path.getmtime(LIB_PATH)):
+        return DRIVER_BIN
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-o", DRIVER_BIN, DRIVER_SRC, "-L" + _HERE, "-llpp_b200",
+           "-Wl,-rpath,$ORIGIN/../lanczosplusplus_b200"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise LppError("g++ failed:\n" + r.stdout)
+    return DRIVER_BIN
+
+
 class Desc(C.Structure):
     _fields_ = [("model", C.c_int32), ("nsite", C.c_int32), ("orbitals", C.c_int32), ("nup", C.c_int32),
                 ("ndown", C.c_int32), ("feas_u3_all_pairs", C.c_int32),

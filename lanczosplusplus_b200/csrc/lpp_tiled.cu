@@ -11,6 +11,7 @@
 //   sweep C  x += alpha (two-spin terms) y         : FeAs U2/U3 only.
 // Hop tables are per spin species (O(N_spin * z) entries), built on device; the Hamiltonian itself is never stored.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include <vector>
@@ -30,6 +31,7 @@ const char* lpp_tiled_error() { return g_terr.c_str(); }
 #define TE_SIGN 0x80000000u
 #define TE_EXT 0x40000000u
 #define TE_IDX 0x00ffffffu
+#define TE_HOLE 0xffffffffu
 #define LPP_MAXMAG 16
 
 struct MagTable {
@@ -63,6 +65,16 @@ struct TiledPlan {
 	int has_twospin = 0;
 	int dot_blocks = 0;
 	std::vector<void*> allocs;
+	size_t sched_holes = 0, sched_real = 0;
+	int blocksA = 0;              // sweep A: 0 = streaming panels, 1 = shared-memory blocks (v2), 2 = pipelined blocks (v3)
+	int threadsA = 1024;
+	int pipeB = 1, NE = 24;       // sweep B: software-pipelined kernel with NE prefetched table slots
+	uint32_t* tabL = nullptr;     // lean (branch-free) up table, [k][n], widthL slots per state
+	int widthL = 0;
+	uint8_t* wcntL = nullptr;     // per 32 consecutive up states: table slots needed (multiple of 4)
+	int leanA = 1, leanB = 0;
+	size_t smemAL = 0, smemBL = 0;
+	size_t smemA3 = 0;
 	// v1 fallback
 	uint32_t nrowchunks = 0, npanels_v1 = 0;
 	int up_in_smem = 0;
@@ -173,8 +185,8 @@ __global__ void k_compress(HopTable t, MagTable mt, const uint32_t* __restrict__
 		if (pass == 0) next = pos;
 	}
 	for (int k = pos; k < t.width; k++) {
-		if (row_major) tab[s * (uint64_t)t.width + k] = 0;
-		else tab[(uint64_t)k * t.n + s] = 0;
+		if (row_major) tab[s * (uint64_t)t.width + k] = TE_HOLE;
+		else tab[(uint64_t)k * t.n + s] = TE_HOLE;
 	}
 	meta[s] = (uint32_t)cnt | ((uint32_t)next << 8);
 }
@@ -253,6 +265,127 @@ k_sweep_down_blocks(ModelDev m, SpinPlan dn, MagTable mt, DiagTables dt, SpmvArg
 }
 
 // =====================================================================================================
+// sweep A v3: same tile as v2, engineered against latency: cp.async staging of the block, row list / row metadata in
+// shared memory, and a software pipeline that prefetches the next row's table entries and x value while the current
+// row is being reduced.
+// =====================================================================================================
+struct RowCtx {
+	uint32_t d, meta, e0, e1, e2, e3;
+	double xold, dv2;
+	word_t k2;
+};
+
+template <int W, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_sweep_down_blocks3(ModelDev m, SpinPlan dn, MagTable mt, DiagTables dt, SpmvArgs a, uint64_t d0, uint64_t dcount,
+                     const uint32_t* __restrict__ tiles, uint32_t ntile_blocks, uint32_t max_block)
+{
+	extern __shared__ double ys[];                       // [block row][W] | rows_s[max_block] | meta_s[max_block]
+	uint32_t* rows_s = reinterpret_cast<uint32_t*>(ys + (size_t)max_block * W);
+	uint32_t* meta_s = rows_s + max_block;
+	constexpr int NSW = THREADS / W;                     // sub-warps (row slots) per CTA
+	const uint32_t panel = blockIdx.x / ntile_blocks;
+	const uint32_t blk = tiles[blockIdx.x % ntile_blocks];
+	const uint32_t boff = dn.blk_off[blk], bsize = dn.blk_off[blk + 1] - boff;
+	const int lane = threadIdx.x & 31;
+	const int sub = lane / W, col = lane % W;
+	const uint32_t sw = threadIdx.x / W;
+	const unsigned submask = (W == 32) ? 0xffffffffu : (((1u << W) - 1u) << (sub * W));
+	const uint64_t n1 = m.n1;
+	const uint64_t u = (uint64_t)panel * W + col;
+	const bool ucol = u < n1;
+	const uint64_t uc = ucol ? u : 0;
+	const double* __restrict__ y = a.y;
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+
+	for (uint32_t r = threadIdx.x; r < bsize; r += THREADS) {
+		const uint32_t d = dn.rowlist[boff + r];
+		rows_s[r] = d;
+		const bool local = d >= d0 && d < d0 + dcount;
+		meta_s[r] = local ? dn.meta[d] : 0xffffffffu;   // 0xffffffff: not an output row of this shard
+	}
+	for (uint32_t r = sw; r < bsize; r += NSW) {
+		const uint64_t d = dn.rowlist[boff + r];
+		if (ucol) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ys_s + (r * W + col) * 8u), "l"(y + d * n1 + u));
+		else ys[r * W + col] = 0.0;
+	}
+	asm volatile("cp.async.commit_group;");
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();
+
+	const word_t k1 = m.b1[uc];
+	const double dv1 = dt.dv1[uc];
+	const int width = dn.width;
+	const bool need_x = a.beta != 0.0;
+
+	auto load_row = [&](uint32_t r, RowCtx& c) {
+		c.d = rows_s[r];
+		c.meta = meta_s[r];
+		c.e0 = c.e1 = c.e2 = c.e3 = 0u;
+		c.xold = 0.0;
+		if (c.meta == 0xffffffffu) return;
+		const int cnt = (int)(c.meta & 0xffu);
+		const uint32_t* __restrict__ trow = dn.tab + (uint64_t)c.d * width;
+		if (col < cnt) c.e0 = trow[col];
+		if (col + W < cnt) c.e1 = trow[col + W];
+		if (col + 2 * W < cnt) c.e2 = trow[col + 2 * W];
+		if (col + 3 * W < cnt) c.e3 = trow[col + 3 * W];
+		c.k2 = m.b2[c.d];
+		c.dv2 = dt.dv2[c.d];
+		if (need_x && ucol) c.xold = a.x[((uint64_t)c.d - d0) * n1 + u];
+	};
+
+	RowCtx cur, nxt;
+	uint32_t r = sw;
+	if (r < bsize) load_row(r, cur);
+	for (; r < bsize; r += NSW) {
+		const uint32_t rn = r + NSW;
+		if (rn < bsize) load_row(rn, nxt);
+		if (cur.meta != 0xffffffffu) {
+			const int cnt = (int)(cur.meta & 0xffu), next = (int)((cur.meta >> 8) & 0xffu);
+#define TA_ENTRY(kk) __shfl_sync(submask, ((kk) < W ? cur.e0 : (kk) < 2 * W ? cur.e1 : (kk) < 3 * W ? cur.e2 : cur.e3), ((kk) % W) + sub * W)
+			double diag;
+			if (m.model == LPP_MODEL_HUBBARD && dt.uniformU) diag = dt.U0 * (double)lpp_popc(k1 & cur.k2) + dv1 + cur.dv2;
+			else diag = tiled_diag(m, dt, k1, cur.k2, uc, cur.d);
+			double acc = diag * ys[r * W + col];
+			double acc2 = 0.0;
+			int k = 0;
+			for (; k + 1 < next; k += 2) {               // hops leaving the block: coalesced W*8-byte reads (L2)
+				const uint32_t ea = TA_ENTRY(k);
+				const uint32_t eb = TA_ENTRY(k + 1);
+				const double va = y[(uint64_t)(ea & TE_IDX) * n1 + uc];
+				const double vb = y[(uint64_t)(eb & TE_IDX) * n1 + uc];
+				acc += te_amp(mt, ea) * va;
+				acc2 += te_amp(mt, eb) * vb;
+			}
+			if (k < next) {
+				const uint32_t ea = TA_ENTRY(k);
+				acc += te_amp(mt, ea) * y[(uint64_t)(ea & TE_IDX) * n1 + uc];
+				k++;
+			}
+			for (; k + 1 < cnt; k += 2) {                // hops inside the block: shared memory, conflict free
+				const uint32_t ea = TA_ENTRY(k);
+				const uint32_t eb = TA_ENTRY(k + 1);
+				acc += te_amp(mt, ea) * ys[(ea & TE_IDX) * W + col];
+				acc2 += te_amp(mt, eb) * ys[(eb & TE_IDX) * W + col];
+			}
+			if (k < cnt) {
+				const uint32_t ea = TA_ENTRY(k);
+				acc += te_amp(mt, ea) * ys[(ea & TE_IDX) * W + col];
+			}
+#undef TA_ENTRY
+			acc += acc2;
+			if (ucol) {
+				double xn = a.alpha * acc;
+				if (need_x) xn += a.beta * cur.xold;
+				a.x[((uint64_t)cur.d - d0) * n1 + u] = xn;
+			}
+		}
+		cur = nxt;
+	}
+}
+
+// =====================================================================================================
 // sweep B v2: R rows x one contiguous block of up states, rows interleaved in shared memory
 // =====================================================================================================
 template <int R>
@@ -275,37 +408,166 @@ k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0,
 		yrow[r] = y + (d0 + dl) * n1;
 		xrow[r] = a.x + dl * n1;
 	}
+	// stage the rows with cp.async (no register round trip, every element in flight at once)
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
 	for (uint32_t i = threadIdx.x; i < bsize; i += PB_THREADS) {
-		if (R == 2) {
-			double2 v;
-			v.x = yrow[0][boff + i];
-			v.y = live[1] ? yrow[1][boff + i] : 0.0;
-			reinterpret_cast<double2*>(ys)[i] = v;
-		} else {
-			ys[i] = yrow[0][boff + i];
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (live[r])
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ys_s + (i * R + r) * 8u), "l"(yrow[r] + boff + i));
+			else
+				ys[i * R + r] = 0.0;
 		}
 	}
+	asm volatile("cp.async.commit_group;");
+	asm volatile("cp.async.wait_group 0;");
 	__syncthreads();
 	double contrib = 0.0;
 	for (uint32_t i = threadIdx.x; i < bsize; i += PB_THREADS) {
 		const uint64_t u = boff + i;
 		const uint32_t meta = up.meta[u];
 		const int cnt = (int)(meta & 0xffu), next = (int)((meta >> 8) & 0xffu);
-		double acc[R];
+		const uint32_t* __restrict__ tcol = up.tab + u;
+		double acc[R], xold[R];
 #pragma unroll
-		for (int r = 0; r < R; r++) acc[r] = 0.0;
+		for (int r = 0; r < R; r++) {
+			acc[r] = 0.0;
+			xold[r] = live[r] ? xrow[r][u] : 0.0;        // issued early, consumed after the gathers
+		}
 		int k = 0;
 		for (; k < next; k++) {                          // hops leaving the block (only when the up basis is split)
-			const uint32_t e = up.tab[(uint64_t)k * n1 + u];
+			const uint32_t e = tcol[(uint64_t)k * n1];
 			const double amp = te_amp(mt, e);
 #pragma unroll
 			for (int r = 0; r < R; r++) acc[r] += amp * yrow[r][e & TE_IDX];
 		}
-#pragma unroll 4
-		for (; k < cnt; k++) {
-			const uint32_t e = up.tab[(uint64_t)k * n1 + u];
+		// hops inside the block: 4 table entries in flight, then 4 shared-memory gathers.  TE_HOLE entries are padding
+		// inserted by the bank-conflict-free slot scheduling (the lane sits the slot out).
+		for (; k < cnt; k += 4) {
+			uint32_t e[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) e[j] = (k + j < cnt) ? tcol[(uint64_t)(k + j) * n1] : TE_HOLE;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				if (e[j] == TE_HOLE) continue;
+				const double amp = te_amp(mt, e[j]);
+				if (R == 2) {
+					const double2 v = reinterpret_cast<const double2*>(ys)[e[j] & TE_IDX];
+					acc[0] += amp * v.x;
+					acc[1] += amp * v.y;
+				} else {
+					acc[0] += amp * ys[e[j] & TE_IDX];
+				}
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (!live[r]) continue;
+			double xn = xold[r] + a.alpha * acc[r];
+			xrow[r][u] = xn;
+			contrib += ys[i * R + r] * xn;
+		}
+	}
+	if (want_dot && a.dot_partials) {
+		double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+// =====================================================================================================
+// sweep B v4: same tile as v2, software pipelined against the L2 latency of the table: the NE table entries of the
+// thread's NEXT up state are loaded (unconditionally; the table is padded with TE_HOLE) while the current state's
+// gathers are reduced, so the shared-memory gathers of one state issue back to back.
+// =====================================================================================================
+#define PBP_THREADS 512
+template <int R, int NE>
+__global__ void __launch_bounds__(PBP_THREADS, 1)
+k_sweep_up_pipe(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0, uint64_t dcount, int want_dot)
+{
+	extern __shared__ double ys[];                       // [block position][R]
+	const uint32_t blk = blockIdx.x % up.nblocks;
+	const uint64_t dl0 = (uint64_t)(blockIdx.x / up.nblocks) * R;
+	const uint32_t boff = up.blk_off[blk], bsize = up.blk_off[blk + 1] - boff;
+	const uint64_t n1 = m.n1;
+	const int width = up.width;
+	const double* __restrict__ y = a.y;
+	const double* yrow[R];
+	double* xrow[R];
+	bool live[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		live[r] = dl0 + r < dcount;
+		const uint64_t dl = live[r] ? dl0 + r : dl0;
+		yrow[r] = y + (d0 + dl) * n1;
+		xrow[r] = a.x + dl * n1;
+	}
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+	for (uint32_t i = threadIdx.x; i < bsize; i += PBP_THREADS) {
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (live[r])
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ys_s + (i * R + r) * 8u), "l"(yrow[r] + boff + i));
+			else
+				ys[i * R + r] = 0.0;
+		}
+	}
+	asm volatile("cp.async.commit_group;");
+
+	uint32_t en[NE], mnext = 0;
+	double xn_old[R];
+	auto prefetch = [&](uint32_t ii) {
+		const uint64_t u = boff + ii;
+		const uint32_t* __restrict__ tcol = up.tab + u;
+#pragma unroll
+		for (int j = 0; j < NE; j++) en[j] = (j < width) ? tcol[(uint64_t)j * n1] : TE_HOLE;
+		mnext = up.meta[u];
+#pragma unroll
+		for (int r = 0; r < R; r++) xn_old[r] = live[r] ? xrow[r][u] : 0.0;
+	};
+	uint32_t i = threadIdx.x;
+	if (i < bsize) prefetch(i);                          // overlaps with the cp.async staging
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();
+
+	double contrib = 0.0;
+	for (; i < bsize; i += PBP_THREADS) {
+		uint32_t ec[NE];
+		double xold[R];
+#pragma unroll
+		for (int j = 0; j < NE; j++) ec[j] = en[j];
+#pragma unroll
+		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
+		const uint32_t meta = mnext;
+		const uint64_t u = boff + i;
+		if (i + PBP_THREADS < bsize) prefetch(i + PBP_THREADS);
+		double acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0;
+#pragma unroll
+		for (int j = 0; j < NE; j++) {
+			const uint32_t e = ec[j];
+			if (e == TE_HOLE) continue;
 			const double amp = te_amp(mt, e);
-			if (R == 2) {
+			if (e & TE_EXT) {
+#pragma unroll
+				for (int r = 0; r < R; r++) acc[r] += amp * yrow[r][e & TE_IDX];
+			} else if (R == 2) {
+				const double2 v = reinterpret_cast<const double2*>(ys)[e & TE_IDX];
+				acc[0] += amp * v.x;
+				acc[1] += amp * v.y;
+			} else {
+				acc[0] += amp * ys[e & TE_IDX];
+			}
+		}
+		const int cnt = (int)(meta & 0xffu);
+		for (int k = NE; k < cnt; k++) {                 // rare: states with more than NE table slots
+			const uint32_t e = up.tab[(uint64_t)k * n1 + u];
+			if (e == TE_HOLE) continue;
+			const double amp = te_amp(mt, e);
+			if (e & TE_EXT) {
+#pragma unroll
+				for (int r = 0; r < R; r++) acc[r] += amp * yrow[r][e & TE_IDX];
+			} else if (R == 2) {
 				const double2 v = reinterpret_cast<const double2*>(ys)[e & TE_IDX];
 				acc[0] += amp * v.x;
 				acc[1] += amp * v.y;
@@ -316,7 +578,7 @@ k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0,
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			if (!live[r]) continue;
-			double xn = xrow[r][u] + a.alpha * acc[r];
+			double xn = xold[r] + a.alpha * acc[r];
 			xrow[r][u] = xn;
 			contrib += ys[i * R + r] * xn;
 		}
@@ -324,6 +586,181 @@ k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0,
 	if (want_dot && a.dot_partials) {
 		double s = tiled_block_sum(contrib);
 		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+// =====================================================================================================
+// lean sweeps (round-1 profile: the sweeps above are instruction-issue bound, ~50 warp instructions per table slot).
+// sweep B lean: every thread executes exactly NE branch-free slots per up state.  A slot is a 4-byte word
+// [31] sign | [24..29] magnitude | [0..23] BYTE offset into the staged tile; padding and scheduling holes point at one of
+// G zero slots behind the tile, chosen on a bank group that is free in that slot, so they cost no conflict and no branch.
+// =====================================================================================================
+template <int R, int NE, bool UNI>
+__global__ void __launch_bounds__(PBP_THREADS, 1)
+k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __restrict__ wcnt, uint32_t boff, uint32_t bsize,
+                MagTable mt, SpmvArgs a, uint64_t d0, uint64_t dcount, int want_dot)
+{
+	extern __shared__ double ys[];                       // [block position][R] + G zero slots
+	constexpr int G = 16 / R;
+	const uint64_t dl0 = (uint64_t)blockIdx.x * R;
+	const uint64_t n1 = m.n1;
+	const double* yrow[R];
+	double* xrow[R];
+	bool live[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		live[r] = dl0 + r < dcount;
+		const uint64_t dl = live[r] ? dl0 + r : dl0;
+		yrow[r] = a.y + (d0 + dl) * n1;
+		xrow[r] = a.x + dl * n1;
+	}
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+	for (uint32_t i = threadIdx.x; i < bsize; i += PBP_THREADS) {
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (live[r])
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ys_s + (i * R + r) * 8u), "l"(yrow[r] + boff + i));
+			else
+				ys[i * R + r] = 0.0;
+		}
+	}
+	if (threadIdx.x < G * R) ys[(size_t)bsize * R + threadIdx.x] = 0.0;
+	asm volatile("cp.async.commit_group;");
+
+	uint32_t en[NE];
+	double xn_old[R];
+	int wnext = 0;                                       // slots used by the warp's 32 states (warp uniform, multiple of 4)
+	const uint64_t stride = n1;
+	auto prefetch = [&](uint32_t ii) {
+		const uint32_t* __restrict__ tcol = tabL + boff + ii;
+		wnext = (int)wcnt[(boff + ii) >> 5];
+#pragma unroll
+		for (int j = 0; j < NE; j += 4) {
+			if (j < wnext) {
+#pragma unroll
+				for (int q = 0; q < 4; q++) en[j + q] = tcol[(uint64_t)(j + q) * stride];
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < R; r++) xn_old[r] = live[r] ? xrow[r][boff + ii] : 0.0;
+	};
+	uint32_t i = threadIdx.x;
+	if (i < bsize) prefetch(i);                          // overlaps with the cp.async staging
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();
+
+	const double t0 = mt.mag[0];
+	double contrib = 0.0;
+	for (; i < bsize; i += PBP_THREADS) {
+		uint32_t ec[NE];
+		double xold[R];
+#pragma unroll
+		for (int j = 0; j < NE; j++) ec[j] = en[j];
+#pragma unroll
+		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
+		const int wcur = wnext;
+		if (i + PBP_THREADS < bsize) prefetch(i + PBP_THREADS);
+		double acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0;
+#pragma unroll
+		for (int j = 0; j < NE; j++) {
+			if ((j & ~3) >= wcur) continue;              // warp-uniform: whole 4-slot chunks beyond the warp's need
+			const uint32_t e = ec[j];
+			double amp;
+			if (UNI) amp = __hiloint2double(0x3ff00000 | (int)(e & TE_SIGN), 0);          // +-1.0, scaled by |t| once below
+			else {
+				const double mg = mt.mag[(e >> 24) & 63u];
+				amp = __hiloint2double(__double2hiint(mg) ^ (int)(e & TE_SIGN), __double2loint(mg));
+			}
+			const uint32_t addr = ys_s + (e & TE_IDX);
+			if (R == 2) {
+				double vx, vy;
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(addr));
+				acc[0] = fma(amp, vx, acc[0]);
+				acc[1] = fma(amp, vy, acc[1]);
+			} else {
+				double vx;
+				asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vx) : "r"(addr));
+				acc[0] = fma(amp, vx, acc[0]);
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (!live[r]) continue;
+			const double hv = UNI ? t0 * acc[r] : acc[r];
+			double xn = xold[r] + a.alpha * hv;
+			xrow[r][boff + i] = xn;
+			contrib += ys[i * R + r] * xn;
+		}
+	}
+	if (want_dot && a.dot_partials) {
+		double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+// sweep A lean: streaming panels as in k_sweep_down, but the CTA-uniform table entries of its rows are staged once in
+// shared memory as (byte offset of the source row, amplitude) pairs, so a hop costs a broadcast 16-byte shared load,
+// one 64-bit add, the coalesced global load and the FMA.
+#define PAL_COLS 256
+#define PAL_ROWS 16
+struct DownEntry {
+	unsigned long long off8;   // byte offset of row idx in y
+	double amp;
+};
+__global__ void __launch_bounds__(PAL_COLS) k_sweep_down_lean(ModelDev m, HopTable dn, DiagTables dt, SpmvArgs a, uint64_t d0,
+                                                            uint64_t dcount, uint32_t nrowchunks)
+{
+	extern __shared__ double ys[];
+	DownEntry* ent = reinterpret_cast<DownEntry*>(ys);                                  // [PAL_ROWS][width]
+	const uint32_t panel = blockIdx.x / nrowchunks, chunk = blockIdx.x % nrowchunks;
+	const uint64_t n1 = m.n1;
+	const int width = dn.width;
+	const uint64_t dl_first = (uint64_t)chunk * PAL_ROWS;
+	const int nrows = (int)min((uint64_t)PAL_ROWS, dcount - dl_first);
+	for (int q = threadIdx.x; q < nrows * width; q += PAL_COLS) {
+		const int r = q / width, k = q % width;
+		const uint64_t d = d0 + dl_first + r;
+		DownEntry e;
+		e.off8 = (unsigned long long)dn.idx[(uint64_t)k * dn.n + d] * n1 * 8ull;
+		e.amp = dn.val[(uint64_t)k * dn.n + d];                                         // padded entries carry amp = 0, idx = d
+		ent[r * width + k] = e;
+	}
+	__syncthreads();
+	const uint64_t u = (uint64_t)panel * PAL_COLS + threadIdx.x;
+	if (u >= n1) return;
+	const word_t k1 = m.b1[u];
+	const double dv1 = dt.dv1[u];
+	const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + u);
+	const bool need_x = a.beta != 0.0;
+#pragma unroll 1
+	for (int r = 0; r < nrows; r++) {
+		const uint64_t dl = dl_first + r, d = d0 + dl;
+		const int cd = (int)dn.cnt[d];
+		const uint64_t t = dl * n1 + u;
+		const double xold = need_x ? a.x[t] : 0.0;
+		double diag;
+		const word_t k2 = m.b2[d];
+		if (m.model == LPP_MODEL_HUBBARD && dt.uniformU) diag = dt.U0 * (double)lpp_popc(k1 & k2) + dv1 + dt.dv2[d];
+		else diag = tiled_diag(m, dt, k1, k2, u, d);
+		double acc = diag * *reinterpret_cast<const double*>(ycol + d * n1 * 8ull);
+		double acc2 = 0.0;
+		const DownEntry* __restrict__ er = ent + r * width;
+		int k = 0;
+#pragma unroll 2
+		for (; k + 1 < cd; k += 2) {
+			const DownEntry ea = er[k], eb = er[k + 1];
+			acc = fma(ea.amp, *reinterpret_cast<const double*>(ycol + ea.off8), acc);
+			acc2 = fma(eb.amp, *reinterpret_cast<const double*>(ycol + eb.off8), acc2);
+		}
+		if (k < cd) {
+			const DownEntry ea = er[k];
+			acc = fma(ea.amp, *reinterpret_cast<const double*>(ycol + ea.off8), acc);
+		}
+		double xn = a.alpha * (acc + acc2);
+		if (need_x) xn += a.beta * xold;
+		a.x[t] = xn;
 	}
 }
 
@@ -486,8 +923,127 @@ static void make_blocks(const std::vector<word_t>& words, int nbits_per_site, in
 	for (size_t b = 0; b < nb; b++) *max_block = std::max(*max_block, count[b]);
 }
 
+// Bank-conflict-free slot scheduling for the sweep-B gathers.  The G = 16/R lanes that the hardware serves together
+// (quarter-warp for 16-byte, half-warp for 8-byte shared-memory loads) handle G consecutive up states; at table slot k
+// they gather from G positions of the staged block.  Re-order every state's list (and pad with TE_HOLE) so that in each
+// slot the G targets fall into G different bank groups (position mod G).  Amplitudes travel with their entries, so the
+// result is the same sum in a different order.
+static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::vector<uint32_t>& blk_off, cudaStream_t s)
+{
+	const uint64_t n = sp->n;
+	const int width = sp->width;
+	std::vector<uint32_t> tab((size_t)std::max(width, 1) * n), meta(n);
+	TCK(cudaMemcpy(tab.data(), sp->tab, tab.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	TCK(cudaMemcpy(meta.data(), sp->meta, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+	std::vector<std::vector<uint32_t>> out(n);
+	int newwidth = 0;
+	for (size_t b = 0; b + 1 < blk_off.size(); b++) {
+		const uint32_t boff = blk_off[b], bsize = blk_off[b + 1] - boff;
+		for (uint32_t base = 0; base < bsize; base += G) {
+			const int nl = (int)std::min<uint32_t>(G, bsize - base);
+			std::vector<std::vector<uint32_t>> rem(nl);
+			for (int l = 0; l < nl; l++) {
+				const uint64_t u = boff + base + l;
+				const int cnt = meta[u] & 0xff, next = (meta[u] >> 8) & 0xff;
+				for (int k = next; k < cnt; k++) rem[l].push_back(tab[(size_t)k * n + u]);
+			}
+			std::vector<int> order(nl);
+			for (;;) {
+				bool any = false;
+				for (int l = 0; l < nl; l++) any = any || !rem[l].empty();
+				if (!any) break;
+				for (int l = 0; l < nl; l++) order[l] = l;
+				std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return rem[x].size() > rem[y].size(); });
+				uint32_t used = 0;
+				for (int oi = 0; oi < nl; oi++) {
+					const int l = order[oi];
+					if (rem[l].empty()) continue;
+					const uint64_t u = boff + base + l;
+					size_t pick = rem[l].size();
+					for (size_t j = 0; j < rem[l].size(); j++)
+						if (!(used & (1u << ((rem[l][j] & TE_IDX) % G)))) { pick = j; break; }
+					if (pick == rem[l].size()) { out[u].push_back(TE_HOLE); continue; }
+					used |= 1u << ((rem[l][pick] & TE_IDX) % G);
+					out[u].push_back(rem[l][pick]);
+					rem[l].erase(rem[l].begin() + pick);
+				}
+			}
+			for (int l = 0; l < nl; l++) {
+				const uint64_t u = boff + base + l;
+				const int next = (meta[u] >> 8) & 0xff;
+				newwidth = std::max(newwidth, next + (int)out[u].size());
+			}
+		}
+	}
+	if (newwidth > 255) { g_terr = "scheduled table too wide"; return 1; }
+	std::vector<uint32_t> ntab((size_t)std::max(newwidth, 1) * n, TE_HOLE), nmeta(n);
+	size_t holes = 0, real = 0;
+	for (uint64_t u = 0; u < n; u++) {
+		const int next = (meta[u] >> 8) & 0xff;
+		for (int k = 0; k < next; k++) ntab[(size_t)k * n + u] = tab[(size_t)k * n + u];
+		for (size_t j = 0; j < out[u].size(); j++) {
+			ntab[(size_t)(next + j) * n + u] = out[u][j];
+			if (out[u][j] == TE_HOLE) holes++; else real++;
+		}
+		nmeta[u] = (uint32_t)(next + out[u].size()) | ((uint32_t)next << 8);
+	}
+	p->sched_holes = holes;
+	p->sched_real = real;
+	// lean table for k_sweep_up_lean: branch-free, byte offsets, holes/padding on free bank groups of the zero slots.
+	// Only when no hop leaves its block (single-block up basis), which is the case whenever an up-segment fits.
+	bool has_ext = false;
+	for (uint64_t u = 0; u < n; u++) has_ext = has_ext || ((meta[u] >> 8) & 0xff) != 0;
+	if (!has_ext && blk_off.size() == 2) {
+		const int R = 16 / G;
+		const uint32_t bsize = blk_off[1] - blk_off[0];
+		const int WL = std::max(newwidth, 32);
+		std::vector<uint32_t> lean((size_t)WL * n);
+		for (uint32_t base = 0; base < bsize; base += G) {
+			const int nl = (int)std::min<uint32_t>(G, bsize - base);
+			for (int sidx = 0; sidx < WL; sidx++) {
+				uint32_t used = 0;
+				for (int l = 0; l < nl; l++) {
+					const auto& o = out[base + l];
+					if (sidx < (int)o.size() && o[sidx] != TE_HOLE) used |= 1u << ((o[sidx] & TE_IDX) % G);
+				}
+				for (int l = 0; l < nl; l++) {
+					const auto& o = out[base + l];
+					uint32_t e;
+					if (sidx < (int)o.size() && o[sidx] != TE_HOLE) {
+						e = ((o[sidx] & TE_IDX) * (uint32_t)(8 * R)) | (o[sidx] & (TE_SIGN | 0x3f000000u));
+					} else {
+						int g = 0;
+						while (used & (1u << g)) g++;      // a free bank group always exists: at most nl-1 <= G-1 are taken
+						used |= 1u << g;
+						const uint32_t zslot = bsize + (uint32_t)(((g - (int)(bsize % G)) % G + G) % G);
+						e = zslot * (uint32_t)(8 * R);
+					}
+					lean[(size_t)sidx * n + base + l] = e;
+				}
+			}
+		}
+		std::vector<uint8_t> wc((bsize + 31) / 32, 0);
+		for (uint32_t uu = 0; uu < bsize; uu++) {
+			int c = (int)out[uu].size();
+			while (c > 0 && out[uu][c - 1] == TE_HOLE) c--;
+			c = (c + 3) & ~3;
+			wc[uu >> 5] = (uint8_t)std::max<int>(wc[uu >> 5], c);
+		}
+		if (plan_upload(p, &p->tabL, lean)) return -1;
+		if (plan_upload(p, &p->wcntL, wc)) return -1;
+		p->widthL = WL;
+	}
+	uint32_t* dtab = nullptr;
+	if (plan_upload(p, &dtab, ntab)) return -1;
+	TCK(cudaMemcpyAsync(sp->meta, nmeta.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+	TCK(cudaStreamSynchronize(s));
+	sp->tab = dtab;
+	sp->width = newwidth;
+	return 0;
+}
+
 static int build_spin_plan(TiledPlan* p, SpinPlan* sp, const HopTable& t, const std::vector<word_t>& words, int bits_per_site,
-                           int nsite, uint32_t cap, bool need_contiguous, bool row_major, cudaStream_t s)
+                           int nsite, uint32_t cap, bool need_contiguous, bool row_major, int sched_group, cudaStream_t s)
 {
 	std::vector<uint32_t> rowlist, blk_off, local, blk_of;
 	uint32_t mx = 0;
@@ -520,6 +1076,7 @@ static int build_spin_plan(TiledPlan* p, SpinPlan* sp, const HopTable& t, const 
 	TCK(cudaStreamSynchronize(s));
 	TCK(cudaGetLastError());
 	if (hbad) { g_terr = "hop amplitude not in the magnitude table"; return 1; }
+	if (sched_group > 0 && !row_major) return schedule_conflict_free(p, sp, sched_group, blk_off, s);
 	return 0;
 }
 
@@ -557,6 +1114,19 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 	const char* envr = getenv("LPP_TILED_R");
 	p->R = envr ? atoi(envr) : 2;
 	if (p->R != 1 && p->R != 2) p->R = 2;
+	const char* envs = getenv("LPP_TILED_SCHED");
+	const bool sched = !(envs && envs[0] == '0');
+	const char* enva = getenv("LPP_TILED_A");
+	p->blocksA = enva ? atoi(enva) : 0;
+	const char* envb = getenv("LPP_TILED_B");
+	p->pipeB = envb ? atoi(envb) : 1;
+	const char* envn = getenv("LPP_TILED_NE");
+	p->NE = envn ? atoi(envn) : 24;
+	if (p->NE != 16 && p->NE != 24 && p->NE != 32) p->NE = 24;
+	const char* envt = getenv("LPP_TILED_TA");
+	p->threadsA = (envt && atoi(envt) == 512) ? 512 : 1024;
+	const char* envk = getenv("LPP_TILED_SMEMA_KB");
+	const size_t smemA_budget = envk ? (size_t)atoi(envk) * 1024 : (size_t)maxsm - 2048;
 	if (try_v2) {
 		std::vector<word_t> w1(m.n1), w2(m.n2);
 		if (cudaMemcpy(w1.data(), m.b1, sizeof(word_t) * m.n1, cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -566,15 +1136,16 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 			return -1;
 		}
 		const size_t budget = (size_t)maxsm - 2048;
-		uint32_t capA = (uint32_t)(budget / ((size_t)p->W * 8));
+		uint32_t capA = (uint32_t)(std::min(budget, smemA_budget) / ((size_t)p->W * 8 + 8));
 		uint32_t capB = (uint32_t)(budget / ((size_t)p->R * 8));
-		int ra = build_spin_plan(p, &p->dn, dn, w2, m.orbitals, m.nsite, capA, false, true, s);
-		int rb = ra == 0 ? build_spin_plan(p, &p->up, up, w1, m.orbitals, m.nsite, capB, true, false, s) : ra;
+		int ra = build_spin_plan(p, &p->dn, dn, w2, m.orbitals, m.nsite, capA, false, true, 0, s);
+		int rb = ra == 0 ? build_spin_plan(p, &p->up, up, w1, m.orbitals, m.nsite, capB, true, false, sched ? 16 / p->R : 0, s) : ra;
 		if (ra < 0 || rb < 0) { delete p; return -1; }
 		if (ra == 0 && rb == 0) {
 			p->v2 = 1;
 			p->smemA = (size_t)p->dn.max_block * p->W * 8;
 			p->smemB = (size_t)p->up.max_block * p->R * 8;
+			p->smemA3 = p->smemA + (size_t)p->dn.max_block * 8;
 			// blocks of down states that contain at least one local row
 			std::vector<uint32_t> rowlist(m.n2), blk_off(p->dn.nblocks + 1);
 			cudaMemcpy(rowlist.data(), p->dn.rowlist, sizeof(uint32_t) * m.n2, cudaMemcpyDeviceToHost);
@@ -595,21 +1166,52 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 			cudaError_t e2 = p->R == 2
 			                     ? cudaFuncSetAttribute(k_sweep_up_blocks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB)
 			                     : cudaFuncSetAttribute(k_sweep_up_blocks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB);
-			if (e1 != cudaSuccess || e2 != cudaSuccess) { g_terr = "cudaFuncSetAttribute(smem) failed"; delete p; return -1; }
+			cudaError_t e3 = cudaSuccess;
+#define SETB(R_, N_) if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_sweep_up_pipe<R_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB)
+			SETB(1, 16); SETB(1, 24); SETB(1, 32); SETB(2, 16); SETB(2, 24); SETB(2, 32);
+#undef SETB
+#define SETA3(W_, T_, B_) if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_sweep_down_blocks3<W_, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA3)
+			SETA3(8, 1024, 1); SETA3(16, 1024, 1); SETA3(32, 1024, 1); SETA3(8, 512, 2); SETA3(16, 512, 2); SETA3(32, 512, 2);
+#undef SETA3
+			if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { g_terr = "cudaFuncSetAttribute(smem) failed"; delete p; return -1; }
 		}
 	}
-	if (!p->v2) {
+	{
 		p->nrowchunks = (uint32_t)((p->dcount + PA_ROWS - 1) / PA_ROWS);
 		p->npanels_v1 = (uint32_t)((m.n1 + PA_COLS - 1) / PA_COLS);
 		p->up_smem_bytes = (size_t)m.n1 * sizeof(double);
 		p->up_in_smem = (p->up_smem_bytes + 1024 <= (size_t)maxsm) ? 1 : 0;
-		if (p->up_in_smem) {
+		if (p->up_in_smem && !p->v2) {
 			cudaError_t e = cudaFuncSetAttribute(k_sweep_up_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->up_smem_bytes);
 			if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
 		}
 	}
+	{
+		const char* envl = getenv("LPP_TILED_LEAN");      // bit 0: lean sweep A, bit 1: lean sweep B (default both)
+		const int lean = envl ? atoi(envl) : 3;
+		p->leanA = (lean & 1) && (p->blocksA == 0);
+		p->smemAL = (size_t)PAL_ROWS * std::max(dn.width, 1) * sizeof(DownEntry);
+		p->leanB = (lean & 2) && p->v2 && p->tabL != nullptr && p->widthL <= 32 && p->up.nblocks == 1;
+		if (p->leanB) {
+			p->smemBL = ((size_t)m.n1 + 16 / p->R) * p->R * 8;
+			if (p->smemBL + 1024 > (size_t)maxsm) p->leanB = 0;
+		}
+		cudaError_t e = cudaSuccess;
+		if (p->leanA && p->smemAL > 48 * 1024) e = cudaFuncSetAttribute(k_sweep_down_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
+#define SETL(R_, U_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_lean<R_, 32, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBL)
+		if (p->leanB) { SETL(1, true); SETL(1, false); SETL(2, true); SETL(2, false); }
+#undef SETL
+		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
+	}
+	if (getenv("LPP_VERBOSE"))
+		fprintf(stderr, "[lpp tiled] leanA=%d leanB=%d widthL=%d\n", p->leanA, p->leanB, p->widthL);
+	if (getenv("LPP_VERBOSE"))
+		fprintf(stderr, "[lpp tiled] v2=%d blocksA=%d TA=%d W=%d R=%d pipeB=%d NE=%d dn: blocks=%d max=%u width=%d | up: blocks=%d max=%u width=%d sched real=%zu holes=%zu\n",
+		        p->v2, p->blocksA, p->threadsA, p->W, p->R, p->pipeB, p->NE, p->dn.nblocks, p->dn.max_block, p->dn.width, p->up.nblocks, p->up.max_block,
+		        p->up.width, p->sched_real, p->sched_holes);
 	// the last sweep owns the dot-product partial sums
 	if (p->has_twospin) p->dot_blocks = (int)((nloc + 255) / 256);
+	else if (p->v2 && p->leanB) p->dot_blocks = (int)((p->dcount + p->R - 1) / p->R);
 	else if (p->v2) p->dot_blocks = (int)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
 	else if (p->up_in_smem) p->dot_blocks = (int)p->dcount;
 	else p->dot_blocks = (int)(((m.n1 + 255) / 256) * p->dcount);
@@ -631,7 +1233,16 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 {
 	int launches = 0;
 	const int dot_in_b = p->has_twospin ? 0 : 1;
-	if (p->v2) {
+	if (p->v2 && p->blocksA == 2) {
+		const unsigned gridA = p->ntilesA_blocks * p->npanels;
+#define RUNA3(W_, T_, B_) k_sweep_down_blocks3<W_, T_, B_><<<gridA, T_, p->smemA3, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks, p->dn.max_block)
+		if (p->threadsA == 512) {
+			if (p->W == 8) RUNA3(8, 512, 2); else if (p->W == 16) RUNA3(16, 512, 2); else RUNA3(32, 512, 2);
+		} else {
+			if (p->W == 8) RUNA3(8, 1024, 1); else if (p->W == 16) RUNA3(16, 1024, 1); else RUNA3(32, 1024, 1);
+		}
+#undef RUNA3
+	} else if (p->v2 && p->blocksA == 1) {
 		const unsigned gridA = p->ntilesA_blocks * p->npanels;
 		if (p->W == 8)
 			k_sweep_down_blocks<8><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
@@ -639,23 +1250,38 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 			k_sweep_down_blocks<16><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
 		else
 			k_sweep_down_blocks<32><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
-		launches++;
-		const unsigned gridB = (unsigned)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
-		if (p->R == 2) k_sweep_up_blocks<2><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
-		else k_sweep_up_blocks<1><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
-		launches++;
+	} else if (p->leanA) {
+		const uint32_t nchunks = (uint32_t)((p->dcount + PAL_ROWS - 1) / PAL_ROWS);
+		const uint32_t npan = (uint32_t)((m.n1 + PAL_COLS - 1) / PAL_COLS);
+		k_sweep_down_lean<<<npan * nchunks, PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, p->d0, p->dcount, nchunks);
 	} else {
 		uint64_t nblkA = (uint64_t)p->npanels_v1 * p->nrowchunks;
 		k_sweep_down<<<(unsigned)nblkA, PA_COLS, 0, s>>>(m, dn, dt, a, p->d0, p->dcount, p->nrowchunks);
-		launches++;
-		if (p->up_in_smem) {
-			k_sweep_up_smem<<<(unsigned)p->dcount, PB_THREADS, p->up_smem_bytes, s>>>(m, up, a, p->d0, dot_in_b);
-		} else {
-			uint32_t nbx = (uint32_t)((m.n1 + 255) / 256);
-			k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
-		}
-		launches++;
 	}
+	launches++;
+	if (p->v2 && p->leanB) {
+		const unsigned gridL = (unsigned)((p->dcount + p->R - 1) / p->R);
+		const uint32_t bsz = (uint32_t)m.n1;
+#define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, a, p->d0, p->dcount, dot_in_b)
+		if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
+		else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+#undef RUNL
+	} else if (p->v2) {
+		const unsigned gridB = (unsigned)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
+#define RUNB(R_, N_) k_sweep_up_pipe<R_, N_><<<gridB, PBP_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b)
+		if (p->pipeB) {
+			if (p->R == 2) { if (p->NE == 16) RUNB(2, 16); else if (p->NE == 24) RUNB(2, 24); else RUNB(2, 32); }
+			else { if (p->NE == 16) RUNB(1, 16); else if (p->NE == 24) RUNB(1, 24); else RUNB(1, 32); }
+		} else if (p->R == 2) k_sweep_up_blocks<2><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
+		else k_sweep_up_blocks<1><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
+#undef RUNB
+	} else if (p->up_in_smem) {
+		k_sweep_up_smem<<<(unsigned)p->dcount, PB_THREADS, p->up_smem_bytes, s>>>(m, up, a, p->d0, dot_in_b);
+	} else {
+		uint32_t nbx = (uint32_t)((m.n1 + 255) / 256);
+		k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
+	}
+	launches++;
 	if (p->has_twospin) {
 		k_sweep_twospin<<<(unsigned)((a.nloc + 255) / 256), 256, 0, s>>>(m, a);
 		launches++;
