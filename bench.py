@@ -179,9 +179,8 @@ def main():
                                   hop=case.get("hop"), jzz=case.get("jzz"), U=case.get("U"), V=case.get("V"),
                                   D=case.get("D"), device=local, rank=rank, nranks=world, kernel=args.kernel)
     if world > 1:
-        ids = [lpp.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        eng.comm_init(ids[0])
+        from lanczosplusplus_b200 import distributed as lppdist
+        lppdist.attach(eng, dist)   # NCCL id broadcast + CUDA IPC handles of the column shards (peer-memory exchange)
     rows = eng.rows()
     _, nloc = eng.local_rows()
 
@@ -238,7 +237,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": iter_ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "rows": rows, "kernel": args.kernel, "l2": "vectors (1.3 GB) exceed L2; no flush",
-                       "sharding": "rows split over the spin-down index; x halo by NCCL broadcast-gather" if world > 1 else "none"},
+                       "sharding": ("two-layout: up sweep on row shards, down sweep on column shards, re-layout by peer-memory kernels "
+                                    "over NVLink (CUDA IPC); NCCL for the scalar all-reduces") if world > 1 else "none"},
             "spmv_ms": spmv_ms, "spmv_gbs": BYTES_PER_ROW_SPMV * rows / (spmv_ms * 1e-3) / 1e9,
             "iter_gbs": BYTES_PER_ROW_ITER * rows / (iter_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -153,6 +153,14 @@ int lpp_tridiag_eig(int32_t n, const double* a, const double* b, double* eigs, d
 int lpp_comm_unique_id(uint8_t id[128]);
 int lpp_comm_init(lpp_handle* h, const uint8_t id[128]);
 
+/* Peer-memory exchange for the two-layout sharding (Hubbard-type product bases, nranks > 1): every rank exports the CUDA IPC
+ * handles of its column-shard buffers (128 bytes), the launcher all-gathers them, every rank imports the nranks*128 bytes.
+ * After that the row<->column re-layout of each mat-vec is done by the engine's own kernels with stores/loads on the
+ * peers' memory over NVLink; NCCL only carries the scalar all-reduces.  lpp_p2p_export returns LPP_ERR_STATE when the
+ * sharding does not apply (the engine then uses the NCCL paths). */
+int lpp_p2p_export(lpp_handle* h, int32_t kernel, uint8_t handles[128]);
+int lpp_p2p_import(lpp_handle* h, const uint8_t* all_handles);
+
 /* contiguous near-equal split of n items over nranks (the row-sharding rule used for the slow index) */
 int lpp_shard_range(uint64_t n, int32_t rank, int32_t nranks, uint64_t* first, uint64_t* count);
 

@@ -310,7 +310,11 @@ LPP_HD void lpp_feas_twospin(const ModelDev& m, word_t k1, word_t k2, int all_pa
 {
 	const int no = m.orbitals, nsite = m.nsite;
 	const double u2 = 0.5 * m.U[2], u3 = m.U[3];
+	// two orbitals: a term exists only on sites holding exactly one up and exactly one down electron
+	word_t cand = ~(word_t)0;
+	if (no == 2) cand = (k1 ^ (k1 >> 1)) & (k2 ^ (k2 >> 1));
 	for (int i = 0; i < nsite; i++) {
+		if (no == 2 && !((cand >> (2 * i)) & 1)) continue;
 		for (int orb1 = 0; orb1 < no; orb1++) {
 			for (int orb2 = 0; orb2 < no; orb2++) {
 				if (orb1 == orb2) continue;

@@ -47,6 +47,8 @@ struct NcclApi {
 	int (*CommDestroy)(ncclComm_t) = nullptr;
 	int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
@@ -67,6 +69,8 @@ static int nccl_load()
 	SYM(CommDestroy, "ncclCommDestroy");
 	SYM(AllReduce, "ncclAllReduce");
 	SYM(Broadcast, "ncclBroadcast");
+	SYM(Send, "ncclSend");
+	SYM(Recv, "ncclRecv");
 	SYM(GroupStart, "ncclGroupStart");
 	SYM(GroupEnd, "ncclGroupEnd");
 	SYM(GetErrorString, "ncclGetErrorString");
@@ -95,6 +99,8 @@ struct lpp_handle {
 	HopTable up{}, dn{};
 	DiagTables dt{};
 	TiledPlan* tiled = nullptr;
+	HeisBond* heis_bonds = nullptr;
+	int heis_nbonds = 0, heis_field = 0;
 	// CRS
 	bool crs_ready = false;
 	int64_t* rowptr = nullptr;
@@ -113,6 +119,23 @@ struct lpp_handle {
 	double* scal_host = nullptr;
 	// comm
 	ncclComm_t comm = nullptr;
+	// two-layout sharding (product bases without two-spin terms): the up sweep runs on the ROW shard, the down sweep on the
+	// COLUMN shard, linked by two all-to-all transposes per mat-vec (SURVEY §8e alternative A)
+	int two_layout = -1;          // -1 undecided, 0 no, 1 yes
+	ColSplit cols{};
+	std::vector<uint64_t> dstart; // down-index range of every rank (nranks+1)
+	uint64_t ucol0 = 0, ncols = 0;
+	double* ycol = nullptr;
+	double* xcol = nullptr;
+	double* sendbuf = nullptr;
+	double* recvbuf = nullptr;
+	double* partials2 = nullptr;
+	int partials2_cap = 0;
+	int p2p = 0;                  // 1: peers' column shards are mapped (CUDA IPC): exchange by our own kernels over NVLink
+	PeerPtrs peer_ycol{}, peer_xcol{};
+	std::vector<void*> ipc_opened;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_pack = nullptr, ev_ycol = nullptr, ev_xcol = nullptr, ev_recv = nullptr, ev_scal = nullptr;
 	// stats
 	int64_t launches = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -191,12 +214,15 @@ extern "C" int lpp_destroy(lpp_handle* h)
 {
 	if (!h) return 0;
 	cudaSetDevice(h->device);
+	for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
 	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 	if (h->tiled) lpp_tiled_destroy(h->tiled);
 	for (void* p : h->allocs) cudaFree(p);
 	if (h->scal_host) cudaFreeHost(h->scal_host);
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);
+	for (cudaEvent_t e : {h->ev_pack, h->ev_ycol, h->ev_xcol, h->ev_recv, h->ev_scal}) if (e) cudaEventDestroy(e);
+	if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return 0;
@@ -457,7 +483,8 @@ extern "C" int lpp_crs_export(const lpp_handle* h, int64_t* rowptr, int64_t* col
 // ------------------------------------------------------------------ SpMV dispatch
 static int resolve_kernel(const lpp_handle* h, int kernel)
 {
-	if (kernel == LPP_KERNEL_AUTO) return (h->md.model == LPP_MODEL_HEISENBERG) ? LPP_KERNEL_GENERIC : LPP_KERNEL_TILED;
+	if (kernel == LPP_KERNEL_AUTO) return (h->md.model == LPP_MODEL_HEISENBERG) ? LPP_KERNEL_TABLE : LPP_KERNEL_TILED;
+	if (h->md.model == LPP_MODEL_HEISENBERG && kernel == LPP_KERNEL_TILED) return LPP_KERNEL_TABLE;
 	return kernel;
 }
 
@@ -468,6 +495,16 @@ static int ensure_partials(lpp_handle* h, int n)
 	h->partials = nullptr;
 	CKR(dev_alloc(h, &h->partials, (size_t)n));
 	h->partials_cap = n;
+	return 0;
+}
+
+static int ensure_tiled(lpp_handle* h)
+{
+	CKR(ensure_tables(h));
+	if (!h->tiled) {
+		int rc = lpp_tiled_create(h->md, h->hop.data(), h->up, h->dn, h->row0, h->nloc, h->stream, &h->tiled);
+		if (rc != 0) return fail(LPP_ERR_CUDA, std::string("tiled plan: ") + lpp_tiled_error());
+	}
 	return 0;
 }
 
@@ -485,6 +522,24 @@ static int do_spmv(lpp_handle* h, int kernel, double alpha, double beta, double*
 		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
 		lpp_launch_spmv_generic(h->md, a, h->stream);
 		h->launches += 1;
+	} else if (kernel == LPP_KERNEL_TABLE && h->md.model == LPP_MODEL_HEISENBERG) {
+		if (!h->heis_bonds) {
+			std::vector<HeisBond> bl;
+			const int n = h->md.nsite;
+			for (int p = 0; p < n; p++)
+				for (int q = p + 1; q < n; q++) {
+					HeisBond b{p, q, h->hop[(size_t)p * n + q], h->hop[(size_t)q * n + p], h->jzz[(size_t)p * n + q]};
+					if (b.jpm_pq != 0 || b.jpm_qp != 0 || b.jzz != 0) bl.push_back(b);
+				}
+			h->heis_nbonds = (int)bl.size();
+			CKR(dev_upload(h, &h->heis_bonds, bl.data(), bl.size()));
+			h->heis_field = 0;
+			for (int i = 0; i < n; i++) if (h->V[i] != 0 || h->D[i] != 0) h->heis_field = 1;
+		}
+		nb = lpp_spmv_generic_blocks(h->nloc);
+		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
+		lpp_launch_spmv_heis(h->md, h->heis_bonds, h->heis_nbonds, h->heis_field, a, h->stream);
+		h->launches += 1;
 	} else if (kernel == LPP_KERNEL_TABLE) {
 		CKR(ensure_tables(h));
 		nb = lpp_spmv_table_blocks(h->md, h->nloc);
@@ -492,11 +547,7 @@ static int do_spmv(lpp_handle* h, int kernel, double alpha, double beta, double*
 		lpp_launch_spmv_table(h->md, h->up, h->dn, h->dt, a, h->stream);
 		h->launches += 1;
 	} else if (kernel == LPP_KERNEL_TILED) {
-		CKR(ensure_tables(h));
-		if (!h->tiled) {
-			int rc = lpp_tiled_create(h->md, h->hop.data(), h->up, h->dn, h->row0, h->nloc, h->stream, &h->tiled);
-			if (rc != 0) return fail(LPP_ERR_CUDA, std::string("tiled plan: ") + lpp_tiled_error());
-		}
+		CKR(ensure_tiled(h));
 		nb = lpp_tiled_dot_blocks(h->tiled);
 		if (want_dot) { CKR(ensure_partials(h, nb)); a.dot_partials = h->partials; }
 		int nl = lpp_tiled_spmv(h->tiled, h->md, h->up, h->dn, h->dt, a, h->stream);
@@ -681,11 +732,15 @@ extern "C" int lpp_cf_eval(int32_t n, const double* a, const double* b, double e
 }
 
 // ------------------------------------------------------------------ Krylov loop
-static int ensure_vectors(lpp_handle* h)
+static int ensure_tiled(lpp_handle* h);
+static int ensure_two_layout(lpp_handle* h, int kernel);
+
+static int ensure_vectors(lpp_handle* h, int kernel)
 {
 	if (!h->vx) CKR(dev_alloc(h, &h->vx, h->nloc));
 	if (!h->vy) CKR(dev_alloc(h, &h->vy, h->nloc));
-	if (h->desc.nranks > 1 && !h->yfull) CKR(dev_alloc(h, &h->yfull, h->rows));
+	CKR(ensure_two_layout(h, kernel));
+	if (h->desc.nranks > 1 && h->two_layout != 1 && !h->yfull) CKR(dev_alloc(h, &h->yfull, h->rows));
 	CKR(ensure_partials(h, lpp_vec_blocks(h->nloc)));
 	return 0;
 }
@@ -695,13 +750,165 @@ static int reduce_scalar(lpp_handle* h, int npartials, double* out)
 {
 	lpp_launch_finalize_sum(h->partials, npartials, h->scal_dev, h->stream);
 	h->launches += 1;
+	cudaStream_t cs = h->stream;
 	if (h->desc.nranks > 1) {
 		if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
-		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+		if (h->comm_stream && !h->p2p) {   // every NCCL call of this handle goes through one stream
+			cs = h->comm_stream;
+			CK(cudaEventRecord(h->ev_scal, h->stream));
+			CK(cudaStreamWaitEvent(cs, h->ev_scal, 0));
+		}
+		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 1, kNcclFloat64, kNcclSum, h->comm, cs));
 	}
-	CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, sizeof(double), cudaMemcpyDeviceToHost, cs));
+	CK(cudaStreamSynchronize(cs));
 	*out = h->scal_host[0];
+	return 0;
+}
+
+// ------------------------------------------------------------------ two-layout sharded SpMV
+static int ensure_two_layout(lpp_handle* h, int kernel)
+{
+	if (h->two_layout >= 0) return 0;
+	h->two_layout = 0;
+	const char* env = getenv("LPP_TWO_LAYOUT");
+	if (h->desc.nranks == 1 || h->desc.nranks > LPP_MAX_RANKS || (env && env[0] == '0')) return 0;
+	if (h->md.model != LPP_MODEL_HUBBARD) return 0;          // FeAs two-spin terms need arbitrary remote elements
+	if (resolve_kernel(h, kernel) != LPP_KERNEL_TILED) return 0;
+	CKR(ensure_tiled(h));
+	if (!lpp_tiled_two_layout_ok(h->tiled)) return 0;
+	const int G = h->desc.nranks, me = h->desc.rank;
+	const uint64_t n1 = h->md.n1, n2 = h->md.n2;
+	h->cols.nranks = G;
+	h->cols.me = me;
+	h->dstart.assign(G + 1, 0);
+	for (int r = 0; r < G; r++) {
+		uint64_t f, c;
+		shard_range(n1 / 2, r, G, &f, &c);                 // split pairs of columns: even shard widths allow 16-byte accesses
+		h->cols.cs[r] = 2 * f;
+		h->cols.cs[r + 1] = (r == G - 1) ? n1 : 2 * (f + c);
+		shard_range(n2, r, G, &f, &c);
+		h->dstart[r] = f;
+		h->dstart[r + 1] = f + c;
+	}
+	h->ucol0 = h->cols.cs[me];
+	h->ncols = h->cols.cs[me + 1] - h->cols.cs[me];
+	CKR(dev_alloc(h, &h->ycol, n2 * h->ncols));
+	CKR(dev_alloc(h, &h->xcol, n2 * h->ncols));
+	h->partials2_cap = lpp_tiled_down_cols_blocks(h->md, h->ncols);
+	CKR(dev_alloc(h, &h->partials2, (size_t)h->partials2_cap));
+	CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_ycol, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_xcol, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_recv, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&h->ev_scal, cudaEventDisableTiming));
+	h->two_layout = 1;
+	return 0;
+}
+
+// x = beta x + alpha H y on the ROW shard (x, y: local rows).  Flow (S = compute stream, C = comm stream):
+//   S pack y -> per-peer column blocks | C all-to-all (y: ROW -> COLUMN layout)  ||  S up sweep on the ROW shard
+//   S down sweep + diagonal on the COLUMN shard | C all-to-all (x: COLUMN -> ROW) | S x_row += received blocks
+// The Lanczos dot <y, x> is the sum of the two sweeps' partial sums (it is layout independent).
+static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, const double* y, bool want_dot, double* dot_out)
+{
+	if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
+	cudaStream_t S = h->stream, C = h->comm_stream;
+	const int G = h->desc.nranks, me = h->desc.rank;
+	const uint64_t n1 = h->md.n1, nrows = h->nloc / n1, d0loc = h->row0 / n1, ncme = h->ncols;
+	if (h->p2p) {
+		// Peer-memory path, one stream.  The two tiny all-reduces are also the cross-GPU barriers:
+		//   pack (remote stores into every rank's ycol) | up sweep (local) | all-reduce #1: everybody's pack has landed
+		//   down sweep on ycol -> xcol | all-reduce #2 (the Lanczos dot): everybody's xcol is final | unpack (remote loads)
+		// The next pack / down sweep cannot overwrite a buffer a peer still reads: each is issued after an all-reduce
+		// that the peer only enters once it has finished reading (stream order).
+		C = S;
+		lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, S);
+		const int nbB = lpp_tiled_up_rows_blocks(h->tiled, nrows);
+		CKR(ensure_partials(h, std::max(nbB, lpp_vec_blocks(h->nloc))));
+		SpmvArgs ab;
+		ab.alpha = alpha; ab.beta = beta; ab.x = x; ab.y = y; ab.row0 = 0; ab.nloc = h->nloc;
+		ab.dot_partials = want_dot ? h->partials : nullptr;
+		if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nrows, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+		CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
+		SpmvArgs aa;
+		aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
+		aa.dot_partials = want_dot ? h->partials2 : nullptr;
+		if (lpp_tiled_sweep_down_cols(h->tiled, h->md, h->dn, h->dt, aa, h->ucol0, ncme, S) < 0)
+			return fail(LPP_ERR_CUDA, lpp_tiled_error());
+		if (want_dot) {
+			lpp_launch_finalize_sum(h->partials, nbB, h->scal_dev, S);
+			lpp_launch_finalize_sum(h->partials2, h->partials2_cap, h->scal_dev + 1, S);
+		}
+		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 2, kNcclFloat64, kNcclSum, h->comm, S));
+		if (want_dot) CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, S));
+		lpp_launch_unpack_add_p2p(x, h->peer_xcol, nrows, n1, h->cols, d0loc, S);
+		h->launches += want_dot ? 6 : 4;
+		if (want_dot) {
+			CK(cudaStreamSynchronize(S));
+			*dot_out = h->scal_host[0] + h->scal_host[1];
+		}
+		CK(cudaGetLastError());
+		return 0;
+	}
+	if (!h->sendbuf) CKR(dev_alloc(h, &h->sendbuf, h->nloc));
+	if (!h->recvbuf) CKR(dev_alloc(h, &h->recvbuf, h->nloc));
+	lpp_launch_pack_cols(y, h->sendbuf, h->ycol, nrows, n1, h->cols, d0loc, S);
+	CK(cudaEventRecord(h->ev_pack, S));
+	CK(cudaStreamWaitEvent(C, h->ev_pack, 0));
+	CKN(g_nccl.GroupStart());
+	for (int q = 0; q < G; q++) {
+		if (q == me) continue;
+		const uint64_t ncq = h->cols.cs[q + 1] - h->cols.cs[q], ndq = h->dstart[q + 1] - h->dstart[q];
+		CKN(g_nccl.Send(h->sendbuf + nrows * h->cols.cs[q], nrows * ncq, kNcclFloat64, q, h->comm, C));
+		CKN(g_nccl.Recv(h->ycol + h->dstart[q] * ncme, ndq * ncme, kNcclFloat64, q, h->comm, C));
+	}
+	CKN(g_nccl.GroupEnd());
+	CK(cudaEventRecord(h->ev_ycol, C));
+	const int nbB = lpp_tiled_up_rows_blocks(h->tiled, nrows);
+	CKR(ensure_partials(h, std::max(nbB, lpp_vec_blocks(h->nloc))));
+	SpmvArgs ab;
+	ab.alpha = alpha; ab.beta = beta; ab.x = x; ab.y = y; ab.row0 = 0; ab.nloc = h->nloc;
+	ab.dot_partials = want_dot ? h->partials : nullptr;
+	if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nrows, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+	CK(cudaStreamWaitEvent(S, h->ev_ycol, 0));
+	SpmvArgs aa;
+	aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
+	aa.dot_partials = want_dot ? h->partials2 : nullptr;
+	if (lpp_tiled_sweep_down_cols(h->tiled, h->md, h->dn, h->dt, aa, h->ucol0, ncme, S) < 0)
+		return fail(LPP_ERR_CUDA, lpp_tiled_error());
+	CK(cudaEventRecord(h->ev_xcol, S));
+	h->launches += 3;
+	if (want_dot) {
+		lpp_launch_finalize_sum(h->partials, nbB, h->scal_dev, S);
+		lpp_launch_finalize_sum(h->partials2, h->partials2_cap, h->scal_dev + 1, S);
+		CK(cudaEventRecord(h->ev_scal, S));
+		h->launches += 2;
+	}
+	CK(cudaStreamWaitEvent(C, h->ev_xcol, 0));
+	CKN(g_nccl.GroupStart());
+	for (int q = 0; q < G; q++) {
+		if (q == me) continue;
+		const uint64_t ncq = h->cols.cs[q + 1] - h->cols.cs[q], ndq = h->dstart[q + 1] - h->dstart[q];
+		CKN(g_nccl.Send(h->xcol + h->dstart[q] * ncme, ndq * ncme, kNcclFloat64, q, h->comm, C));
+		CKN(g_nccl.Recv(h->recvbuf + nrows * h->cols.cs[q], nrows * ncq, kNcclFloat64, q, h->comm, C));
+	}
+	CKN(g_nccl.GroupEnd());
+	CK(cudaEventRecord(h->ev_recv, C));
+	if (want_dot) {
+		CK(cudaStreamWaitEvent(C, h->ev_scal, 0));
+		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 2, kNcclFloat64, kNcclSum, h->comm, C));
+		CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, C));
+	}
+	CK(cudaStreamWaitEvent(S, h->ev_recv, 0));
+	lpp_launch_unpack_add(x, h->recvbuf, h->xcol, nrows, n1, h->cols, d0loc, S);
+	h->launches += 2;
+	if (want_dot) {
+		CK(cudaStreamSynchronize(C));
+		*dot_out = h->scal_host[0] + h->scal_host[1];
+	}
+	CK(cudaGetLastError());
 	return 0;
 }
 
@@ -746,12 +953,16 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	for (; j < steps; j++) {
 		if (tm && j == tm->from) { CK(cudaEventRecord(h->ev0, h->stream)); tm->launches_at_from = h->launches; }
 		if (zcoef) { lpp_launch_axpy(z, y, zcoef[j] / nj, n, h->stream); h->launches += 1; }
-		const double* src = nullptr;
-		CKR(gather_full(h, y, &src));
-		int nparts = 0;
-		CKR(do_spmv(h, p->kernel, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, src, true, &nparts));
 		double dot = 0;
-		CKR(reduce_scalar(h, nparts, &dot));
+		if (h->two_layout == 1) {
+			CKR(spmv_two_layout(h, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, y, true, &dot));
+		} else {
+			const double* src = nullptr;
+			CKR(gather_full(h, y, &src));
+			int nparts = 0;
+			CKR(do_spmv(h, p->kernel, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, src, true, &nparts));
+			CKR(reduce_scalar(h, nparts, &dot));
+		}
 		double aj = dot / nj;
 		lpp_launch_axpy_norm(x, y, aj / nj, n, h->partials, h->stream);
 		h->launches += 1;
@@ -777,7 +988,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 
 static int load_init(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int use_modified)
 {
-	CKR(ensure_vectors(h));
+	CKR(ensure_vectors(h, p->kernel));
 	if (init_host) {
 		CK(cudaMemcpyAsync(h->vy, init_host + h->row0, sizeof(double) * h->nloc, cudaMemcpyHostToDevice, h->stream));
 	} else if (use_modified) {
@@ -910,23 +1121,68 @@ extern "C" int lpp_comm_init(lpp_handle* h, const uint8_t id[128])
 	return 0;
 }
 
+// peer-memory exchange: export the handles of this rank's column-shard buffers / map everybody's
+extern "C" int lpp_p2p_export(lpp_handle* h, int32_t kernel, uint8_t handles[128])
+{
+	if (!h || !handles) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	CKR(ensure_two_layout(h, kernel));
+	if (h->two_layout != 1) return fail(LPP_ERR_STATE, "two-layout sharding does not apply to this handle");
+	cudaIpcMemHandle_t a, b;
+	CK(cudaIpcGetMemHandle(&a, h->ycol));
+	CK(cudaIpcGetMemHandle(&b, h->xcol));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+	memcpy(handles, &a, 64);
+	memcpy(handles + 64, &b, 64);
+	return 0;
+}
+
+extern "C" int lpp_p2p_import(lpp_handle* h, const uint8_t* all_handles)
+{
+	if (!h || !all_handles) return fail(LPP_ERR_ARG, "null argument");
+	if (h->two_layout != 1) return fail(LPP_ERR_STATE, "lpp_p2p_export must succeed first");
+	CK(cudaSetDevice(h->device));
+	for (int q = 0; q < h->desc.nranks; q++) {
+		if (q == h->desc.rank) {
+			h->peer_ycol.p[q] = h->ycol;
+			h->peer_xcol.p[q] = h->xcol;
+			continue;
+		}
+		cudaIpcMemHandle_t a, b;
+		memcpy(&a, all_handles + (size_t)q * 128, 64);
+		memcpy(&b, all_handles + (size_t)q * 128 + 64, 64);
+		void* pa = nullptr;
+		void* pb = nullptr;
+		CK(cudaIpcOpenMemHandle(&pa, a, cudaIpcMemLazyEnablePeerAccess));
+		CK(cudaIpcOpenMemHandle(&pb, b, cudaIpcMemLazyEnablePeerAccess));
+		h->ipc_opened.push_back(pa);
+		h->ipc_opened.push_back(pb);
+		h->peer_ycol.p[q] = (double*)pa;
+		h->peer_xcol.p[q] = (double*)pb;
+	}
+	h->p2p = 1;
+	return 0;
+}
+
 // ------------------------------------------------------------------ measurement hooks
 extern "C" int lpp_bench_spmv(lpp_handle* h, int32_t kernel, int32_t iters, int32_t warmup, lpp_timing* t)
 {
 	if (!h || !t || iters < 1) return fail(LPP_ERR_ARG, "bad argument");
 	CK(cudaSetDevice(h->device));
-	CKR(ensure_vectors(h));
-	lpp_solver_params p{};
-	p.seed = 42;
+	CKR(ensure_vectors(h, kernel));
 	lpp_launch_fill_random(h->vy, h->row0, h->nloc, 42, h->stream);
 	CK(cudaMemsetAsync(h->vx, 0, sizeof(double) * h->nloc, h->stream));
 	const double* src = nullptr;
-	CKR(gather_full(h, h->vy, &src));
-	for (int i = 0; i < warmup; i++) CKR(do_spmv(h, kernel, 1.0, 1.0, h->vx, src, false, nullptr));
+	if (h->two_layout != 1) CKR(gather_full(h, h->vy, &src));
+	auto one = [&]() -> int {
+		if (h->two_layout == 1) return spmv_two_layout(h, 1.0, 1.0, h->vx, h->vy, false, nullptr);
+		return do_spmv(h, kernel, 1.0, 1.0, h->vx, src, false, nullptr);
+	};
+	for (int i = 0; i < warmup; i++) CKR(one());
 	CK(cudaStreamSynchronize(h->stream));
 	int64_t l0 = h->launches;
 	CK(cudaEventRecord(h->ev0, h->stream));
-	for (int i = 0; i < iters; i++) CKR(do_spmv(h, kernel, 1.0, 1.0, h->vx, src, false, nullptr));
+	for (int i = 0; i < iters; i++) CKR(one());
 	CK(cudaEventRecord(h->ev1, h->stream));
 	CK(cudaEventSynchronize(h->ev1));
 	float ms = 0;

@@ -194,6 +194,54 @@ __global__ void __launch_bounds__(LPP_TPB) k_spmv_generic(ModelDev m, SpmvArgs a
 	}
 }
 
+// K4 fast path: Heisenberg S=1/2 with the couplings flattened into a bond list (p<q, jpm(p,q), jpm(q,p), jzz(p,q)).
+// Same terms as Heisenberg.h:242-307: diagonal sum_{p<q} jzz m_p m_q (+ field, + D m^2), off-diagonal 1/2 jpm(i,j) with
+// i the down site and j the up site; the target state is ranked with the split colex tables (2 look-ups).
+__global__ void __launch_bounds__(LPP_TPB) k_spmv_heis(ModelDev m, const HeisBond* __restrict__ bonds, int nbonds, int has_field,
+                                                      SpmvArgs a)
+{
+	uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x;
+	double contrib = 0.0;
+	if (t < a.nloc) {
+		const uint64_t r = a.row0 + t;
+		const word_t w = m.b1[r];
+		const double* __restrict__ y = a.y;
+		double diag = 0.0, acc = 0.0, acc2 = 0.0;
+		if (has_field) {
+			for (int i = 0; i < m.nsite; i++) {
+				const double mi = (double)((w >> i) & 1) - 0.5;
+				diag += m.V[i] * mi + m.D[i] * (mi * mi);
+			}
+		}
+		for (int b = 0; b < nbonds; b++) {
+			const HeisBond bd = bonds[b];
+			const int bp = (int)((w >> bd.p) & 1), bq = (int)((w >> bd.q) & 1);
+			diag += (bp == bq) ? 0.25 * bd.jzz : -0.25 * bd.jzz;
+			if (bp != bq) {
+				const double amp = 0.5 * (bp ? bd.jpm_qp : bd.jpm_pq);
+				if (amp != 0.0) {
+					const uint64_t c = lpp_rank_onespin(m, 0, w ^ (lpp_bit(bd.p) | lpp_bit(bd.q)));
+					if (b & 1) acc2 += amp * y[c]; else acc += amp * y[c];
+				}
+			}
+		}
+		const double yr = y[r];
+		double xn = a.alpha * (diag * yr + acc + acc2);
+		if (a.beta != 0.0) xn += a.beta * a.x[t];
+		a.x[t] = xn;
+		contrib = yr * xn;
+	}
+	if (a.dot_partials) {
+		double s = lpp_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+void lpp_launch_spmv_heis(const ModelDev& m, const HeisBond* bonds, int nbonds, int has_field, const SpmvArgs& a, cudaStream_t s)
+{
+	k_spmv_heis<<<lpp_spmv_generic_blocks(a.nloc), LPP_TPB, 0, s>>>(m, bonds, nbonds, has_field, a);
+}
+
 int lpp_spmv_generic_blocks(uint64_t nloc) { return (int)((nloc + LPP_TPB - 1) / LPP_TPB); }
 void lpp_launch_spmv_generic(const ModelDev& m, const SpmvArgs& a, cudaStream_t s)
 {
@@ -504,4 +552,101 @@ void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int s
 {
 	k_apply_op<<<(unsigned)((dst_nloc + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(src, dst, op, site, spin, factor, srcv, z,
 	                                                                            dst_row0, dst_nloc);
+}
+
+// ------------------------------------------------------------------ two-layout exchange helpers (multi-GPU)
+// ROW shard (nrows x n1, local down range) <-> COLUMN shards: peer q owns columns [cs[q], cs[q+1]).
+// Buffers hold one block per peer, block q = row-major nrows x ncols_q at element offset nrows*cs[q].
+__device__ __forceinline__ int lpp_col_owner(const ColSplit& c, uint64_t u)
+{
+	int q = 0;
+	while (q + 1 < c.nranks && u >= c.cs[q + 1]) q++;
+	return q;
+}
+
+// y_row -> sendbuf blocks; the rank's own block goes straight into its column shard ycol (rows d0loc.., pitch ncols_me)
+__global__ void __launch_bounds__(LPP_TPB) k_pack_cols(const double* __restrict__ src, double* __restrict__ sendbuf,
+                                                      double* __restrict__ ycol, uint64_t nrows, uint64_t n1, ColSplit c,
+                                                      uint64_t d0loc)
+{
+	const uint64_t total = nrows * n1;
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < total; i += (uint64_t)gridDim.x * LPP_TPB) {
+		const uint64_t r = i / n1, u = i - r * n1;
+		const int q = lpp_col_owner(c, u);
+		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
+		const double v = src[i];
+		if (q == c.me) ycol[(d0loc + r) * nc + cu] = v;
+		else sendbuf[nrows * c.cs[q] + r * nc + cu] = v;
+	}
+}
+
+// x_row += blocks received from the column shards (own block read from xcol)
+__global__ void __launch_bounds__(LPP_TPB) k_unpack_add(double* __restrict__ x, const double* __restrict__ recvbuf,
+                                                       const double* __restrict__ xcol, uint64_t nrows, uint64_t n1, ColSplit c,
+                                                       uint64_t d0loc)
+{
+	const uint64_t total = nrows * n1;
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < total; i += (uint64_t)gridDim.x * LPP_TPB) {
+		const uint64_t r = i / n1, u = i - r * n1;
+		const int q = lpp_col_owner(c, u);
+		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
+		const double v = (q == c.me) ? xcol[(d0loc + r) * nc + cu] : recvbuf[nrows * c.cs[q] + r * nc + cu];
+		x[i] += v;
+	}
+}
+
+// Peer-memory variants (NVLink, CUDA IPC mappings): the pack kernel stores each element straight into the owning rank's
+// column shard, the unpack kernel loads the column results from the owning rank -- transfer and re-layout are one kernel,
+// no staging buffers and no library collective on the data path.
+// one block row per matrix row (no integer division), each thread walks columns with stride blockDim
+__global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restrict__ src, PeerPtrs ycols, uint64_t nrows,
+                                                          uint64_t n1, ColSplit c, uint64_t d0loc)
+{
+	const uint64_t r = blockIdx.y;
+	const double* __restrict__ srow = src + r * n1;
+	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+		const int q = lpp_col_owner(c, u);
+		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
+		ycols.p[q][(d0loc + r) * nc + cu] = srow[u];
+	}
+}
+
+__global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__ x, PeerPtrs xcols, uint64_t nrows, uint64_t n1,
+                                                           ColSplit c, uint64_t d0loc)
+{
+	const uint64_t r = blockIdx.y;
+	double* __restrict__ xrow = x + r * n1;
+	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+		const int q = lpp_col_owner(c, u);
+		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
+		xrow[u] += xcols.p[q][(d0loc + r) * nc + cu];
+	}
+}
+
+static dim3 lpp_rowwise_grid(uint64_t nrows, uint64_t n1)
+{
+	unsigned gx = (unsigned)((n1 + (uint64_t)LPP_TPB * 4 - 1) / ((uint64_t)LPP_TPB * 4));
+	return dim3(gx ? gx : 1, (unsigned)nrows, 1);
+}
+
+void lpp_launch_pack_cols_p2p(const double* src, const PeerPtrs& ycols, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                              uint64_t d0loc, cudaStream_t s)
+{
+	k_pack_cols_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(src, ycols, nrows, n1, c, d0loc);
+}
+void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc,
+                               cudaStream_t s)
+{
+	k_unpack_add_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(x, xcols, nrows, n1, c, d0loc);
+}
+
+void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                          uint64_t d0loc, cudaStream_t s)
+{
+	k_pack_cols<<<lpp_vec_blocks(nrows * n1 * 2), LPP_TPB, 0, s>>>(src, sendbuf, ycol, nrows, n1, c, d0loc);
+}
+void lpp_launch_unpack_add(double* x, const double* recvbuf, const double* xcol, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                           uint64_t d0loc, cudaStream_t s)
+{
+	k_unpack_add<<<lpp_vec_blocks(nrows * n1 * 2), LPP_TPB, 0, s>>>(x, recvbuf, xcol, nrows, n1, c, d0loc);
 }

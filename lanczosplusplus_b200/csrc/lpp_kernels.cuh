@@ -38,6 +38,11 @@ void lpp_launch_hop_count(const ModelDev& m, int spin, uint64_t n, uint32_t* cnt
 void lpp_launch_hop_fill(const ModelDev& m, int spin, HopTable t, cudaStream_t s);
 void lpp_launch_spin_diag(const ModelDev& m, int spin, uint64_t n, double* dv, cudaStream_t s);
 
+struct HeisBond {
+	int p, q;
+	double jpm_pq, jpm_qp, jzz;
+};
+void lpp_launch_spmv_heis(const ModelDev& m, const HeisBond* bonds, int nbonds, int has_field, const SpmvArgs& a, cudaStream_t s);
 int lpp_spmv_generic_blocks(uint64_t nloc);
 void lpp_launch_spmv_generic(const ModelDev& m, const SpmvArgs& a, cudaStream_t s);
 int lpp_spmv_table_blocks(const ModelDev& m, uint64_t nloc);
@@ -67,6 +72,24 @@ void lpp_launch_finalize_sum(const double* partials, int n, double* out, cudaStr
 // operator application (Engine.h:416-458), gather form on the destination basis
 void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, double factor,
                          const double* srcv, double* z, uint64_t dst_row0, uint64_t dst_nloc, cudaStream_t s);
+
+// two-layout exchange helpers (multi-GPU)
+#define LPP_MAX_RANKS 16
+struct ColSplit {
+	uint64_t cs[LPP_MAX_RANKS + 1];   // column range of peer q: [cs[q], cs[q+1])
+	int nranks, me;
+};
+struct PeerPtrs {
+	double* p[LPP_MAX_RANKS];
+};
+void lpp_launch_pack_cols_p2p(const double* src, const PeerPtrs& ycols, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                              uint64_t d0loc, cudaStream_t s);
+void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc,
+                               cudaStream_t s);
+void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                          uint64_t d0loc, cudaStream_t s);
+void lpp_launch_unpack_add(double* x, const double* recvbuf, const double* xcol, uint64_t nrows, uint64_t n1, const ColSplit& c,
+                           uint64_t d0loc, cudaStream_t s);
 
 // tiled two-sweep kernels (lpp_tiled.cu)
 struct TiledPlan;

@@ -629,20 +629,14 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 
 	uint32_t en[NE];
 	double xn_old[R];
-	int wnext = 0;                                       // slots used by the warp's 32 states (warp uniform, multiple of 4)
+	const bool need_x = a.beta != 0.0;
 	const uint64_t stride = n1;
 	auto prefetch = [&](uint32_t ii) {
 		const uint32_t* __restrict__ tcol = tabL + boff + ii;
-		wnext = (int)wcnt[(boff + ii) >> 5];
 #pragma unroll
-		for (int j = 0; j < NE; j += 4) {
-			if (j < wnext) {
+		for (int j = 0; j < NE; j++) en[j] = tcol[(uint64_t)j * stride];
 #pragma unroll
-				for (int q = 0; q < 4; q++) en[j + q] = tcol[(uint64_t)(j + q) * stride];
-			}
-		}
-#pragma unroll
-		for (int r = 0; r < R; r++) xn_old[r] = live[r] ? xrow[r][boff + ii] : 0.0;
+		for (int r = 0; r < R; r++) xn_old[r] = (live[r] && need_x) ? xrow[r][boff + ii] : 0.0;
 	};
 	uint32_t i = threadIdx.x;
 	if (i < bsize) prefetch(i);                          // overlaps with the cp.async staging
@@ -658,14 +652,12 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 		for (int j = 0; j < NE; j++) ec[j] = en[j];
 #pragma unroll
 		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
-		const int wcur = wnext;
 		if (i + PBP_THREADS < bsize) prefetch(i + PBP_THREADS);
 		double acc[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = 0.0;
 #pragma unroll
 		for (int j = 0; j < NE; j++) {
-			if ((j & ~3) >= wcur) continue;              // warp-uniform: whole 4-slot chunks beyond the warp's need
 			const uint32_t e = ec[j];
 			double amp;
 			if (UNI) amp = __hiloint2double(0x3ff00000 | (int)(e & TE_SIGN), 0);          // +-1.0, scaled by |t| once below
@@ -689,7 +681,7 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 		for (int r = 0; r < R; r++) {
 			if (!live[r]) continue;
 			const double hv = UNI ? t0 * acc[r] : acc[r];
-			double xn = xold[r] + a.alpha * hv;
+			double xn = a.beta * xold[r] + a.alpha * hv;
 			xrow[r][boff + i] = xn;
 			contrib += ys[i * R + r] * xn;
 		}
@@ -705,17 +697,23 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 // one 64-bit add, the coalesced global load and the FMA.
 #define PAL_COLS 256
 #define PAL_ROWS 16
+struct ColView {
+	uint64_t pitch, ncols, u0;
+};
 struct DownEntry {
 	unsigned long long off8;   // byte offset of row idx in y
 	double amp;
 };
-__global__ void __launch_bounds__(PAL_COLS) k_sweep_down_lean(ModelDev m, HopTable dn, DiagTables dt, SpmvArgs a, uint64_t d0,
-                                                            uint64_t dcount, uint32_t nrowchunks)
+// ColView: the kernel sees an (nrows x ncols) row-major matrix with row pitch `pitch`; column c is up state u0 + c.
+// Single GPU: pitch = ncols = Nup, u0 = 0.  Two-layout multi-GPU: the rank's column shard, all Ndn rows.
+template <int VEC>
+__global__ void __launch_bounds__(PAL_COLS, (VEC == 2) ? 3 : 4) k_sweep_down_lean(ModelDev m, HopTable dn, DiagTables dt, SpmvArgs a, uint64_t d0,
+                                                               uint64_t dcount, uint32_t nrowchunks, ColView cv)
 {
 	extern __shared__ double ys[];
 	DownEntry* ent = reinterpret_cast<DownEntry*>(ys);                                  // [PAL_ROWS][width]
 	const uint32_t panel = blockIdx.x / nrowchunks, chunk = blockIdx.x % nrowchunks;
-	const uint64_t n1 = m.n1;
+	const uint64_t pitch = cv.pitch;
 	const int width = dn.width;
 	const uint64_t dl_first = (uint64_t)chunk * PAL_ROWS;
 	const int nrows = (int)min((uint64_t)PAL_ROWS, dcount - dl_first);
@@ -723,46 +721,111 @@ __global__ void __launch_bounds__(PAL_COLS) k_sweep_down_lean(ModelDev m, HopTab
 		const int r = q / width, k = q % width;
 		const uint64_t d = d0 + dl_first + r;
 		DownEntry e;
-		e.off8 = (unsigned long long)dn.idx[(uint64_t)k * dn.n + d] * n1 * 8ull;
+		e.off8 = (unsigned long long)dn.idx[(uint64_t)k * dn.n + d] * pitch * 8ull;
 		e.amp = dn.val[(uint64_t)k * dn.n + d];                                         // padded entries carry amp = 0, idx = d
 		ent[r * width + k] = e;
 	}
 	__syncthreads();
-	const uint64_t u = (uint64_t)panel * PAL_COLS + threadIdx.x;
-	if (u >= n1) return;
-	const word_t k1 = m.b1[u];
-	const double dv1 = dt.dv1[u];
-	const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + u);
-	const bool need_x = a.beta != 0.0;
+	// VEC adjacent columns per thread (VEC = 2: 16-byte accesses; needs an even pitch and an even column count)
+	const uint64_t c = ((uint64_t)panel * PAL_COLS + threadIdx.x) * VEC;
+	double contrib = 0.0;
+	if (c < cv.ncols) {
+		word_t k1[VEC];
+		double dv1[VEC];
+#pragma unroll
+		for (int v = 0; v < VEC; v++) {
+			k1[v] = m.b1[cv.u0 + c + v];
+			dv1[v] = dt.dv1[cv.u0 + c + v];
+		}
+		const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + c);
+		const bool need_x = a.beta != 0.0;
+		constexpr int NB = (VEC == 2) ? 4 : 8;            // independent row reads in flight per thread
 #pragma unroll 1
-	for (int r = 0; r < nrows; r++) {
-		const uint64_t dl = dl_first + r, d = d0 + dl;
-		const int cd = (int)dn.cnt[d];
-		const uint64_t t = dl * n1 + u;
-		const double xold = need_x ? a.x[t] : 0.0;
-		double diag;
-		const word_t k2 = m.b2[d];
-		if (m.model == LPP_MODEL_HUBBARD && dt.uniformU) diag = dt.U0 * (double)lpp_popc(k1 & k2) + dv1 + dt.dv2[d];
-		else diag = tiled_diag(m, dt, k1, k2, u, d);
-		double acc = diag * *reinterpret_cast<const double*>(ycol + d * n1 * 8ull);
-		double acc2 = 0.0;
-		const DownEntry* __restrict__ er = ent + r * width;
-		int k = 0;
-#pragma unroll 2
-		for (; k + 1 < cd; k += 2) {
-			const DownEntry ea = er[k], eb = er[k + 1];
-			acc = fma(ea.amp, *reinterpret_cast<const double*>(ycol + ea.off8), acc);
-			acc2 = fma(eb.amp, *reinterpret_cast<const double*>(ycol + eb.off8), acc2);
+		for (int r = 0; r < nrows; r++) {
+			const uint64_t dl = dl_first + r, d = d0 + dl;
+			const int cd = (int)dn.cnt[d];
+			const uint64_t t = dl * pitch + c;
+			double xold[VEC], yr[VEC], acc[VEC], acc2[VEC];
+			if (VEC == 2) {
+				const double2 yv = *reinterpret_cast<const double2*>(ycol + d * pitch * 8ull);
+				yr[0] = yv.x; yr[VEC - 1] = yv.y;
+				if (need_x) {
+					const double2 xv = *reinterpret_cast<const double2*>(a.x + t);
+					xold[0] = xv.x; xold[VEC - 1] = xv.y;
+				}
+			} else {
+				yr[0] = *reinterpret_cast<const double*>(ycol + d * pitch * 8ull);
+				if (need_x) xold[0] = a.x[t];
+			}
+			const word_t k2 = m.b2[d];
+			const double dv2 = dt.dv2[d];
+#pragma unroll
+			for (int v = 0; v < VEC; v++) {
+				double diag;
+				if (m.model == LPP_MODEL_HUBBARD && dt.uniformU) diag = dt.U0 * (double)lpp_popc(k1[v] & k2) + dv1[v] + dv2;
+				else diag = tiled_diag(m, dt, k1[v], k2, cv.u0 + c + v, d);
+				acc[v] = diag * yr[v];
+				acc2[v] = 0.0;
+			}
+			const DownEntry* __restrict__ er = ent + r * width;
+			// entries past cnt are padding (amp = 0, source row = d itself), so whole batches can be issued blindly
+			const int cdr = min((cd + NB - 1) / NB * NB, width);
+			int k = 0;
+			for (; k + NB <= cdr; k += NB) {
+				DownEntry e[NB];
+#pragma unroll
+				for (int j = 0; j < NB; j++) e[j] = er[k + j];
+				if (VEC == 2) {
+					double2 v[NB];
+#pragma unroll
+					for (int j = 0; j < NB; j++) v[j] = *reinterpret_cast<const double2*>(ycol + e[j].off8);
+#pragma unroll
+					for (int j = 0; j < NB; j += 2) {
+						acc[0] = fma(e[j].amp, v[j].x, acc[0]);
+						acc[VEC - 1] = fma(e[j].amp, v[j].y, acc[VEC - 1]);
+						acc2[0] = fma(e[j + 1].amp, v[j + 1].x, acc2[0]);
+						acc2[VEC - 1] = fma(e[j + 1].amp, v[j + 1].y, acc2[VEC - 1]);
+					}
+				} else {
+					double v[NB];
+#pragma unroll
+					for (int j = 0; j < NB; j++) v[j] = *reinterpret_cast<const double*>(ycol + e[j].off8);
+#pragma unroll
+					for (int j = 0; j < NB; j += 2) {
+						acc[0] = fma(e[j].amp, v[j], acc[0]);
+						acc2[0] = fma(e[j + 1].amp, v[j + 1], acc2[0]);
+					}
+				}
+			}
+			for (; k < cd; k++) {
+				const DownEntry ea = er[k];
+				if (VEC == 2) {
+					const double2 v = *reinterpret_cast<const double2*>(ycol + ea.off8);
+					acc[0] = fma(ea.amp, v.x, acc[0]);
+					acc[VEC - 1] = fma(ea.amp, v.y, acc[VEC - 1]);
+				} else {
+					acc[0] = fma(ea.amp, *reinterpret_cast<const double*>(ycol + ea.off8), acc[0]);
+				}
+			}
+			double xn[VEC];
+#pragma unroll
+			for (int v = 0; v < VEC; v++) {
+				xn[v] = a.alpha * (acc[v] + acc2[v]);
+				if (need_x) xn[v] += a.beta * xold[v];
+				contrib += yr[v] * xn[v];
+			}
+			if (VEC == 2) *reinterpret_cast<double2*>(a.x + t) = make_double2(xn[0], xn[VEC - 1]);
+			else a.x[t] = xn[0];
 		}
-		if (k < cd) {
-			const DownEntry ea = er[k];
-			acc = fma(ea.amp, *reinterpret_cast<const double*>(ycol + ea.off8), acc);
-		}
-		double xn = a.alpha * (acc + acc2);
-		if (need_x) xn += a.beta * xold;
-		a.x[t] = xn;
+	}
+	if (a.dot_partials) {
+		double sum = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = sum;
 	}
 }
+
+static inline int down_lean_vec(const ColView& cv) { return (cv.pitch % 2 == 0 && cv.ncols % 2 == 0) ? 2 : 1; }
+static inline uint32_t down_lean_panels(const ColView& cv) { return (uint32_t)((cv.ncols + (uint64_t)PAL_COLS * down_lean_vec(cv) - 1) / ((uint64_t)PAL_COLS * down_lean_vec(cv))); }
 
 // =====================================================================================================
 // v1 sweeps (fallbacks: too many distinct amplitudes, or one-spin bases that cannot be blocked)
@@ -1197,7 +1260,10 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 			if (p->smemBL + 1024 > (size_t)maxsm) p->leanB = 0;
 		}
 		cudaError_t e = cudaSuccess;
-		if (p->leanA && p->smemAL > 48 * 1024) e = cudaFuncSetAttribute(k_sweep_down_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
+		if (p->leanA && p->smemAL > 48 * 1024) {
+			e = cudaFuncSetAttribute(k_sweep_down_lean<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
+			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_down_lean<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
+		}
 #define SETL(R_, U_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_lean<R_, 32, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBL)
 		if (p->leanB) { SETL(1, true); SETL(1, false); SETL(2, true); SETL(2, false); }
 #undef SETL
@@ -1252,8 +1318,12 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 			k_sweep_down_blocks<32><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
 	} else if (p->leanA) {
 		const uint32_t nchunks = (uint32_t)((p->dcount + PAL_ROWS - 1) / PAL_ROWS);
-		const uint32_t npan = (uint32_t)((m.n1 + PAL_COLS - 1) / PAL_COLS);
-		k_sweep_down_lean<<<npan * nchunks, PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, p->d0, p->dcount, nchunks);
+		SpmvArgs aa = a;
+		aa.dot_partials = nullptr;
+		ColView cv{m.n1, m.n1, 0};
+		const uint32_t npan = down_lean_panels(cv);
+		if (down_lean_vec(cv) == 2) k_sweep_down_lean<2><<<npan * nchunks, PAL_COLS, p->smemAL, s>>>(m, dn, dt, aa, p->d0, p->dcount, nchunks, cv);
+		else k_sweep_down_lean<1><<<npan * nchunks, PAL_COLS, p->smemAL, s>>>(m, dn, dt, aa, p->d0, p->dcount, nchunks, cv);
 	} else {
 		uint64_t nblkA = (uint64_t)p->npanels_v1 * p->nrowchunks;
 		k_sweep_down<<<(unsigned)nblkA, PA_COLS, 0, s>>>(m, dn, dt, a, p->d0, p->dcount, p->nrowchunks);
@@ -1262,7 +1332,9 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 	if (p->v2 && p->leanB) {
 		const unsigned gridL = (unsigned)((p->dcount + p->R - 1) / p->R);
 		const uint32_t bsz = (uint32_t)m.n1;
-#define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, a, p->d0, p->dcount, dot_in_b)
+		SpmvArgs ab = a;
+		ab.beta = 1.0;                                  // sweep A already applied beta
+#define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
 		if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
 		else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
 #undef RUNL
@@ -1289,4 +1361,47 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); return -1; }
 	return launches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// two-layout multi-GPU entry points: the up sweep runs on the rank's ROW shard (all up states, local down range),
+// the down sweep (+ diagonal) on the rank's COLUMN shard (all down states, local up range).
+// ---------------------------------------------------------------------------------------------------------------
+int lpp_tiled_two_layout_ok(const TiledPlan* p) { return (p->v2 && p->leanB && !p->has_twospin) ? 1 : 0; }
+
+int lpp_tiled_up_rows_blocks(const TiledPlan* p, uint64_t nrows) { return (int)((nrows + p->R - 1) / p->R); }
+
+// x = beta x + alpha (T_up (x) 1) y on `nrows` local rows; x, y are the local row blocks (row r at r*Nup)
+int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, uint64_t nrows, cudaStream_t s)
+{
+	const unsigned gridL = (unsigned)lpp_tiled_up_rows_blocks(p, nrows);
+	const uint32_t bsz = (uint32_t)m.n1;
+	const int want_dot = a.dot_partials ? 1 : 0;
+#define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, a, 0, nrows, want_dot)
+	if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
+	else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+#undef RUNL
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); return -1; }
+	return 1;
+}
+
+int lpp_tiled_down_cols_blocks(const ModelDev& m, uint64_t ncols)
+{
+	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
+	ColView cv{ncols, ncols, 0};
+	return (int)(down_lean_panels(cv) * nchunks);
+}
+
+// xcol = beta xcol + alpha (D + 1 (x) T_dn) ycol on the column shard [u0, u0+ncols), all Ndn rows, pitch = ncols
+int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& dn, const DiagTables& dt, const SpmvArgs& a,
+                              uint64_t u0, uint64_t ncols, cudaStream_t s)
+{
+	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
+	ColView cv{ncols, ncols, u0};
+	if (down_lean_vec(cv) == 2) k_sweep_down_lean<2><<<lpp_tiled_down_cols_blocks(m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
+	else k_sweep_down_lean<1><<<lpp_tiled_down_cols_blocks(m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); return -1; }
+	return 1;
 }

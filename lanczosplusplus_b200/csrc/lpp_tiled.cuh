@@ -10,3 +10,11 @@ int lpp_tiled_dot_blocks(const TiledPlan* p);
 // returns the number of kernels launched, or <0 on error
 int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const HopTable& dn, const DiagTables& dt,
                    const SpmvArgs& a, cudaStream_t s);
+
+// two-layout multi-GPU (see lpp_tiled.cu)
+int lpp_tiled_two_layout_ok(const TiledPlan* p);
+int lpp_tiled_up_rows_blocks(const TiledPlan* p, uint64_t nrows);
+int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, uint64_t nrows, cudaStream_t s);
+int lpp_tiled_down_cols_blocks(const ModelDev& m, uint64_t ncols);
+int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& dn, const DiagTables& dt, const SpmvArgs& a,
+                              uint64_t u0, uint64_t ncols, cudaStream_t s);

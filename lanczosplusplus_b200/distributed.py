@@ -2,6 +2,7 @@
 the engine owns.  torch.distributed is used only to move the 128-byte NCCL unique id and to take max-over-ranks timings.
 """
 import ctypes as C
+import os
 
 from . import _lib
 from ._lib import check
@@ -31,4 +32,10 @@ def attach(engine, dist):
     """Give a row-sharded InternalProductCuda its NCCL communicator."""
     from .engine import comm_unique_id
     engine.comm_init(broadcast_unique_id(dist, comm_unique_id))
+    if os.environ.get("LPP_P2P", "1") != "0":
+        mine = engine.p2p_export()
+        parts = [None] * dist.get_world_size()
+        dist.all_gather_object(parts, mine)
+        if all(p is not None for p in parts):
+            engine.p2p_import(b"".join(parts))
     return engine

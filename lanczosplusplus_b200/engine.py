@@ -148,6 +148,19 @@ class InternalProductCuda:
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         check(_lib.lib().lpp_comm_init(self.h, buf))
 
+    def p2p_export(self, kernel=None):
+        """128 bytes of CUDA IPC handles of this rank's column-shard buffers, or None when two-layout sharding does not apply."""
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.lib().lpp_p2p_export(self.h, self.kernel if kernel is None else kernel, buf)
+        if rc == -3:
+            return None
+        check(rc)
+        return bytes(buf)
+
+    def p2p_import(self, all_handles):
+        buf = (C.c_uint8 * len(all_handles)).from_buffer_copy(all_handles)
+        check(_lib.lib().lpp_p2p_import(self.h, buf))
+
     # --- measurement hooks
     def bench_spmv(self, iters, warmup, kernel=None):
         t = Timing()

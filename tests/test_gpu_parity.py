@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 def kernels_for(lpp, case):
     if case["model"] == cases.HEISENBERG:
-        return [lpp.KERNEL_GENERIC, lpp.KERNEL_STORED, lpp.KERNEL_AUTO]
+        return [lpp.KERNEL_GENERIC, lpp.KERNEL_TABLE, lpp.KERNEL_STORED, lpp.KERNEL_AUTO]
     return [lpp.KERNEL_GENERIC, lpp.KERNEL_TABLE, lpp.KERNEL_TILED, lpp.KERNEL_STORED, lpp.KERNEL_AUTO]
 
 
