@@ -11,8 +11,8 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "liblpp_b200.so")
-SOURCES = ["lpp_kernels.cu", "lpp_tiled.cu", "lpp_engine.cu"]
-HEADERS = ["lpp_device.cuh", "lpp_kernels.cuh", "lpp_tiled.cuh", "lpp_setup.h"]
+SOURCES = ["lpp_kernels.cu", "lpp_tiled.cu", "lpp_dtile.cu", "lpp_engine.cu"]
+HEADERS = ["lpp_device.cuh", "lpp_kernels.cuh", "lpp_tiled.cuh", "lpp_dtile.cuh", "lpp_sweep_common.cuh", "lpp_setup.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
 
@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into lanczosplusplus_b200/liblpp_b200.so."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+    extra = os.environ.get("LPP_NVCC_EXTRA", "").split()     # tuning experiments only (e.g. -DDT_THREADS=768)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     if verbose:
         print(" ".join(cmd))
     env = dict(os.environ)

@@ -502,7 +502,7 @@ static int ensure_tiled(lpp_handle* h)
 {
 	CKR(ensure_tables(h));
 	if (!h->tiled) {
-		int rc = lpp_tiled_create(h->md, h->hop.data(), h->up, h->dn, h->row0, h->nloc, h->stream, &h->tiled);
+		int rc = lpp_tiled_create(h->md, h->hop.data(), h->up, h->dn, h->dt, h->row0, h->nloc, h->stream, &h->tiled);
 		if (rc != 0) return fail(LPP_ERR_CUDA, std::string("tiled plan: ") + lpp_tiled_error());
 	}
 	return 0;
@@ -795,7 +795,7 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 	h->ncols = h->cols.cs[me + 1] - h->cols.cs[me];
 	CKR(dev_alloc(h, &h->ycol, n2 * h->ncols));
 	CKR(dev_alloc(h, &h->xcol, n2 * h->ncols));
-	h->partials2_cap = lpp_tiled_down_cols_blocks(h->md, h->ncols);
+	h->partials2_cap = lpp_tiled_down_cols_blocks(h->tiled, h->md, h->ncols);
 	CKR(dev_alloc(h, &h->partials2, (size_t)h->partials2_cap));
 	CK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
 	CK(cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming));

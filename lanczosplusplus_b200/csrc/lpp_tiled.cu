@@ -14,8 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "lpp_tiled.cuh"
+#include "lpp_sweep_common.cuh"
+#include "lpp_dtile.cuh"
 
 static thread_local std::string g_terr;
 const char* lpp_tiled_error() { return g_terr.c_str(); }
@@ -32,12 +35,6 @@ const char* lpp_tiled_error() { return g_terr.c_str(); }
 #define TE_EXT 0x40000000u
 #define TE_IDX 0x00ffffffu
 #define TE_HOLE 0xffffffffu
-#define LPP_MAXMAG 16
-
-struct MagTable {
-	double mag[LPP_MAXMAG];
-	int nmag;
-};
 
 struct SpinPlan {
 	uint32_t* tab = nullptr;      // down: row-major [s][width]; up: column-major [k][n]
@@ -71,8 +68,15 @@ struct TiledPlan {
 	int pipeB = 1, NE = 24;       // sweep B: software-pipelined kernel with NE prefetched table slots
 	uint32_t* tabL = nullptr;     // lean (branch-free) up table, [k][n], widthL slots per state
 	int widthL = 0;
-	uint8_t* wcntL = nullptr;     // per 32 consecutive up states: table slots needed (multiple of 4)
+	uint8_t* wcntL = nullptr;     // per 32 consecutive up states: table slots needed (even)
+	void* tabP = nullptr;         // packed up table [chunk][group of 4 slots][lane] (k_sweep_up_packed)
+	uint32_t* choffP = nullptr;   // first group of every chunk
+	uint8_t* wcnt4P = nullptr;    // slots per chunk, multiple of 4
+	int packedE16 = 0, packedB = 0;
+	size_t smemBP = 0;
+	double packed_mean_slots = 0;
 	int leanA = 1, leanB = 0;
+	DownTilePlan* dtile = nullptr;   // shared-memory tile kernel for sweep A (lpp_dtile.cu, opt-in); nullptr: streaming kernel
 	size_t smemAL = 0, smemBL = 0;
 	size_t smemA3 = 0;
 	// v1 fallback
@@ -85,69 +89,6 @@ struct TiledPlan {
 #define PA_ROWS 8
 #define PB_THREADS 1024
 #define TA_THREADS 1024
-
-__device__ __forceinline__ double tiled_warp_sum(double v)
-{
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-	return v;
-}
-__device__ __forceinline__ double tiled_block_sum(double v)
-{
-	__shared__ double red[32];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	v = tiled_warp_sum(v);
-	if (lane == 0) red[wid] = v;
-	__syncthreads();
-	const int nw = (blockDim.x + 31) >> 5;
-	v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
-	if (wid == 0) v = tiled_warp_sum(v);
-	__syncthreads();
-	return v;
-}
-
-__device__ __forceinline__ double tiled_feas_diag(const ModelDev& m, word_t k1, word_t k2)
-{
-	const int no = m.orbitals;
-	double s = m.U[0] * (double)lpp_popc(k1 & k2);
-	word_t m0 = 0;
-	for (int i = 0; i < m.nsite; i++) m0 |= lpp_bit(i * no);
-	for (int a = 0; a < no; a++) {
-		word_t A1 = (k1 >> a) & m0, A2 = (k2 >> a) & m0;
-		for (int b = a + 1; b < no; b++) {
-			word_t B1 = (k1 >> b) & m0, B2 = (k2 >> b) & m0;
-			int uu = lpp_popc(A1 & B1), ud = lpp_popc(A1 & B2), du = lpp_popc(A2 & B1), dd = lpp_popc(A2 & B2);
-			s += m.U[1] * (double)(uu + ud + du + dd);
-			s += m.U[4] * 0.25 * (double)(uu - ud - du + dd);
-			s += m.U[5] * (double)(uu + dd);
-		}
-	}
-	if (m.D[0] != 0.0) {
-		for (int i = 0; i < m.nsite; i++) {
-			word_t sm = lpp_below(no) << (i * no);
-			double sz = 0.5 * (double)(lpp_popc(k1 & sm) - lpp_popc(k2 & sm));
-			s += m.D[0] * sz * sz;
-		}
-	}
-	return s;
-}
-
-__device__ __forceinline__ double tiled_diag(const ModelDev& m, const DiagTables& dt, word_t k1, word_t k2, uint64_t i1,
-                                             uint64_t i2)
-{
-	double s;
-	if (m.model == LPP_MODEL_HUBBARD) {
-		if (dt.uniformU) s = dt.U0 * (double)lpp_popc(k1 & k2);
-		else {
-			s = 0;
-			word_t b = k1 & k2;
-			while (b) { s += m.U[lpp_ctz(b)]; b &= b - 1; }
-		}
-	} else {
-		s = tiled_feas_diag(m, k1, k2);
-	}
-	return s + dt.dv1[i1] + dt.dv2[i2];
-}
 
 __device__ __forceinline__ double te_amp(const MagTable& mt, uint32_t e)
 {
@@ -595,6 +536,33 @@ k_sweep_up_pipe(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0, u
 // [31] sign | [24..29] magnitude | [0..23] BYTE offset into the staged tile; padding and scheduling holes point at one of
 // G zero slots behind the tile, chosen on a bank group that is free in that slot, so they cost no conflict and no branch.
 // =====================================================================================================
+// N branch-free gathers of one up state: ec[j] = [31] sign | [24..29] magnitude | [0..23] byte offset into the staged tile
+template <int R, int N, int NE, bool UNI>
+__device__ __forceinline__ void up_lean_gather(const uint32_t (&ec)[NE], const MagTable& mt, uint32_t ys_s, double (&acc)[R])
+{
+#pragma unroll
+	for (int j = 0; j < N; j++) {
+		const uint32_t e = ec[j];
+		double amp;
+		if (UNI) amp = __hiloint2double(0x3ff00000 | (int)(e & TE_SIGN), 0);          // +-1.0, scaled by |t| once by the caller
+		else {
+			const double mg = mt.mag[(e >> 24) & 63u];
+			amp = __hiloint2double(__double2hiint(mg) ^ (int)(e & TE_SIGN), __double2loint(mg));
+		}
+		const uint32_t addr = ys_s + (e & TE_IDX);
+		if (R == 2) {
+			double vx, vy;
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(addr));
+			acc[0] = fma(amp, vx, acc[0]);
+			acc[1] = fma(amp, vy, acc[1]);
+		} else {
+			double vx;
+			asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vx) : "r"(addr));
+			acc[0] = fma(amp, vx, acc[0]);
+		}
+	}
+}
+
 template <int R, int NE, bool UNI>
 __global__ void __launch_bounds__(PBP_THREADS, 1)
 k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __restrict__ wcnt, uint32_t boff, uint32_t bsize,
@@ -631,10 +599,16 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 	double xn_old[R];
 	const bool need_x = a.beta != 0.0;
 	const uint64_t stride = n1;
+	// wcnt: slots the 32 consecutive states of a warp need (even, warp-uniform); only those are fetched and executed
 	auto prefetch = [&](uint32_t ii) {
 		const uint32_t* __restrict__ tcol = tabL + boff + ii;
+		const int pc = (int)wcnt[ii >> 5];
 #pragma unroll
-		for (int j = 0; j < NE; j++) en[j] = tcol[(uint64_t)j * stride];
+		for (int j = 0; j < NE; j += 2)
+			if (j < pc) {
+				en[j] = tcol[(uint64_t)j * stride];
+				en[j + 1] = tcol[(uint64_t)(j + 1) * stride];
+			}
 #pragma unroll
 		for (int r = 0; r < R; r++) xn_old[r] = (live[r] && need_x) ? xrow[r][boff + ii] : 0.0;
 	};
@@ -648,6 +622,7 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 	for (; i < bsize; i += PBP_THREADS) {
 		uint32_t ec[NE];
 		double xold[R];
+		const int cnt = (int)wcnt[i >> 5];
 #pragma unroll
 		for (int j = 0; j < NE; j++) ec[j] = en[j];
 #pragma unroll
@@ -656,26 +631,15 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 		double acc[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = 0.0;
-#pragma unroll
-		for (int j = 0; j < NE; j++) {
-			const uint32_t e = ec[j];
-			double amp;
-			if (UNI) amp = __hiloint2double(0x3ff00000 | (int)(e & TE_SIGN), 0);          // +-1.0, scaled by |t| once below
-			else {
-				const double mg = mt.mag[(e >> 24) & 63u];
-				amp = __hiloint2double(__double2hiint(mg) ^ (int)(e & TE_SIGN), __double2loint(mg));
-			}
-			const uint32_t addr = ys_s + (e & TE_IDX);
-			if (R == 2) {
-				double vx, vy;
-				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(addr));
-				acc[0] = fma(amp, vx, acc[0]);
-				acc[1] = fma(amp, vy, acc[1]);
-			} else {
-				double vx;
-				asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vx) : "r"(addr));
-				acc[0] = fma(amp, vx, acc[0]);
-			}
+		// branch-free runs of N independent gathers; N = the warp's slot count (states with fewer hops read zero slots)
+		switch (cnt) {
+#define LPP_UP_CASE(N_) case N_: up_lean_gather<R, N_, NE, UNI>(ec, mt, ys_s, acc); break;
+			LPP_UP_CASE(2) LPP_UP_CASE(4) LPP_UP_CASE(6) LPP_UP_CASE(8) LPP_UP_CASE(10) LPP_UP_CASE(12) LPP_UP_CASE(14)
+			LPP_UP_CASE(16) LPP_UP_CASE(18) LPP_UP_CASE(20) LPP_UP_CASE(22) LPP_UP_CASE(24) LPP_UP_CASE(26) LPP_UP_CASE(28)
+			LPP_UP_CASE(30)
+#undef LPP_UP_CASE
+		case 0: break;
+		default: up_lean_gather<R, NE, NE, UNI>(ec, mt, ys_s, acc); break;
 		}
 #pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -692,14 +656,162 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 	}
 }
 
+#ifndef UPP_THREADS
+#define UPP_THREADS 512
+#endif
+// sweep B packed: the lean kernel with (1) a per-warp slot count (a warp's 32 consecutive states execute only the slots
+// they need, rounded to 4: 24 on average instead of 32 on the 4x4 lattice) and (2) the table stored per warp chunk as
+// [chunk][group of 4 slots][lane], so the 4 entries of a group are one coalesced 8-byte (E16: 2-byte entries
+// [15] sign | [13:0] tile position, single hop magnitude) or 16-byte (4-byte lean entries) load per lane.
+template <int R, bool UNI, bool E16, int N4>
+__device__ __forceinline__ void up_packed_gather(const typename std::conditional<E16, uint2, uint4>::type (&ec)[8], const MagTable& mt,
+                                                 uint32_t ys_s, double (&acc)[R])
+{
+#pragma unroll
+	for (int g = 0; g < N4; g++) {
+		uint32_t off[4], sg[4], mi[4];
+		if constexpr (E16) {
+			const uint32_t w0 = ec[g].x, w1 = ec[g].y;
+			off[0] = (w0 & 0x3fffu) * (8u * R); sg[0] = w0 << 16;
+			off[1] = ((w0 >> 16) & 0x3fffu) * (8u * R); sg[1] = w0;
+			off[2] = (w1 & 0x3fffu) * (8u * R); sg[2] = w1 << 16;
+			off[3] = ((w1 >> 16) & 0x3fffu) * (8u * R); sg[3] = w1;
+			mi[0] = mi[1] = mi[2] = mi[3] = 0;
+		} else {
+			const uint32_t w[4] = {ec[g].x, ec[g].y, ec[g].z, ec[g].w};
+#pragma unroll
+			for (int i = 0; i < 4; i++) { off[i] = w[i] & TE_IDX; sg[i] = w[i]; mi[i] = (w[i] >> 24) & 63u; }
+		}
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			double amp;
+			if (UNI) amp = __hiloint2double((int)(0x3ff00000u | (sg[i] & TE_SIGN)), 0);   // +-1.0, scaled by |t| once by the caller
+			else {
+				const double mg = mt.mag[mi[i]];
+				amp = __hiloint2double(__double2hiint(mg) ^ (int)(sg[i] & TE_SIGN), __double2loint(mg));
+			}
+			const uint32_t addr = ys_s + off[i];
+			if (R == 2) {
+				double vx, vy;
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(addr));
+				acc[0] = fma(amp, vx, acc[0]);
+				acc[1] = fma(amp, vy, acc[1]);
+			} else {
+				double vx;
+				asm volatile("ld.shared.f64 %0, [%1];" : "=d"(vx) : "r"(addr));
+				acc[0] = fma(amp, vx, acc[0]);
+			}
+		}
+	}
+}
+
+template <int R, bool UNI, bool E16>
+__global__ void __launch_bounds__(UPP_THREADS, 1)
+k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __restrict__ choff, const uint8_t* __restrict__ wcnt4,
+                  uint32_t bsize, MagTable mt, SpmvArgs a, uint64_t d0, uint64_t dcount, int want_dot)
+{
+	using VT = typename std::conditional<E16, uint2, uint4>::type;
+	extern __shared__ double ys[];                       // [position][R] + G zero slots
+	constexpr int G = 16 / R;
+	const uint64_t dl0 = (uint64_t)blockIdx.x * R;
+	const uint64_t n1 = m.n1;
+	const double* yrow[R];
+	double* xrow[R];
+	bool live[R];
+#pragma unroll
+	for (int r = 0; r < R; r++) {
+		live[r] = dl0 + r < dcount;
+		const uint64_t dl = live[r] ? dl0 + r : dl0;
+		yrow[r] = a.y + (d0 + dl) * n1;
+		xrow[r] = a.x + dl * n1;
+	}
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+	for (uint32_t i = threadIdx.x; i < bsize; i += UPP_THREADS) {
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (live[r])
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ys_s + (i * R + r) * 8u), "l"(yrow[r] + i));
+			else
+				ys[i * R + r] = 0.0;
+		}
+	}
+	if (threadIdx.x < G * R) ys[(size_t)bsize * R + threadIdx.x] = 0.0;
+	asm volatile("cp.async.commit_group;");
+	// chunk directory (first group and slot count of every 32-state chunk) in shared memory behind the tile: the table
+	// prefetch of the next state must not wait for a dependent global load
+	const uint32_t nch = (bsize + 31) >> 5;
+	uint32_t* s_choff = reinterpret_cast<uint32_t*>(ys + (size_t)bsize * R + G * R);
+	uint8_t* s_wcnt = reinterpret_cast<uint8_t*>(s_choff + nch);
+	for (uint32_t c = threadIdx.x; c < nch; c += UPP_THREADS) {
+		s_choff[c] = choff[c];
+		s_wcnt[c] = wcnt4[c];
+	}
+	__syncthreads();
+
+	VT en[8];
+	double xn_old[R];
+	const bool need_x = a.beta != 0.0;
+	const uint32_t lane = threadIdx.x & 31;
+	auto prefetch = [&](uint32_t ii) {
+		const uint32_t c = ii >> 5;
+		const int pc = (int)s_wcnt[c];
+		const VT* __restrict__ base = reinterpret_cast<const VT*>(tabP) + (size_t)s_choff[c] * 32 + lane;
+#pragma unroll
+		for (int g = 0; g < 8; g++)
+			if (4 * g < pc) en[g] = __ldg(base + g * 32);
+#pragma unroll
+		for (int r = 0; r < R; r++) xn_old[r] = (live[r] && need_x) ? xrow[r][ii] : 0.0;
+	};
+	uint32_t i = threadIdx.x;
+	if (i < bsize) prefetch(i);                          // overlaps with the cp.async staging
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();
+
+	const double t0 = mt.mag[0];
+	double contrib = 0.0;
+	for (; i < bsize; i += UPP_THREADS) {
+		VT ec[8];
+		double xold[R];
+		const int cnt = (int)s_wcnt[i >> 5];
+#pragma unroll
+		for (int g = 0; g < 8; g++) ec[g] = en[g];
+#pragma unroll
+		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
+		if (i + UPP_THREADS < bsize) prefetch(i + UPP_THREADS);
+		double acc[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) acc[r] = 0.0;
+		switch (cnt >> 2) {                                // warp-uniform: branch-free runs of 4*N independent gathers
+		case 0: break;
+		case 1: up_packed_gather<R, UNI, E16, 1>(ec, mt, ys_s, acc); break;
+		case 2: up_packed_gather<R, UNI, E16, 2>(ec, mt, ys_s, acc); break;
+		case 3: up_packed_gather<R, UNI, E16, 3>(ec, mt, ys_s, acc); break;
+		case 4: up_packed_gather<R, UNI, E16, 4>(ec, mt, ys_s, acc); break;
+		case 5: up_packed_gather<R, UNI, E16, 5>(ec, mt, ys_s, acc); break;
+		case 6: up_packed_gather<R, UNI, E16, 6>(ec, mt, ys_s, acc); break;
+		case 7: up_packed_gather<R, UNI, E16, 7>(ec, mt, ys_s, acc); break;
+		default: up_packed_gather<R, UNI, E16, 8>(ec, mt, ys_s, acc); break;
+		}
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			if (!live[r]) continue;
+			const double hv = UNI ? t0 * acc[r] : acc[r];
+			double xn = a.beta * xold[r] + a.alpha * hv;
+			xrow[r][i] = xn;
+			contrib += ys[i * R + r] * xn;
+		}
+	}
+	if (want_dot && a.dot_partials) {
+		double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
 // sweep A lean: streaming panels as in k_sweep_down, but the CTA-uniform table entries of its rows are staged once in
 // shared memory as (byte offset of the source row, amplitude) pairs, so a hop costs a broadcast 16-byte shared load,
 // one 64-bit add, the coalesced global load and the FMA.
 #define PAL_COLS 256
 #define PAL_ROWS 16
-struct ColView {
-	uint64_t pitch, ncols, u0;
-};
 struct DownEntry {
 	unsigned long long off8;   // byte offset of row idx in y
 	double amp;
@@ -1089,12 +1201,44 @@ static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::
 		for (uint32_t uu = 0; uu < bsize; uu++) {
 			int c = (int)out[uu].size();
 			while (c > 0 && out[uu][c - 1] == TE_HOLE) c--;
-			c = (c + 3) & ~3;
+			c = (c + 1) & ~1;
 			wc[uu >> 5] = (uint8_t)std::max<int>(wc[uu >> 5], c);
 		}
 		if (plan_upload(p, &p->tabL, lean)) return -1;
 		if (plan_upload(p, &p->wcntL, wc)) return -1;
 		p->widthL = WL;
+		// packed layout for k_sweep_up_packed: [chunk][group of 4 slots][lane]
+		if (WL <= 32) {
+			const uint32_t nch = (bsize + 31) / 32;
+			std::vector<uint8_t> wc4(nch);
+			std::vector<uint32_t> choff(nch + 1, 0);
+			for (uint32_t c = 0; c < nch; c++) {
+				wc4[c] = (uint8_t)((wc[c] + 3) & ~3);
+				choff[c + 1] = choff[c] + wc4[c] / 4;
+			}
+			const bool e16 = p->mt.nmag == 1 && (size_t)bsize + G < (1u << 14);
+			const uint32_t hole0 = bsize * (uint32_t)(8 * R);      // zero slot 0 (states past the end of the last chunk)
+			std::vector<uint32_t> pk32;
+			std::vector<uint16_t> pk16;
+			if (e16) pk16.resize((size_t)choff[nch] * 32 * 4);
+			else pk32.resize((size_t)choff[nch] * 32 * 4);
+			for (uint32_t c = 0; c < nch; c++)
+				for (uint32_t g = 0; g < (uint32_t)wc4[c] / 4; g++)
+					for (uint32_t l = 0; l < 32; l++)
+						for (uint32_t k = 0; k < 4; k++) {
+							const uint32_t u = c * 32 + l, sidx = 4 * g + k;
+							const uint32_t e = (u < bsize) ? lean[(size_t)sidx * n + u] : hole0;
+							const size_t at = (((size_t)choff[c] + g) * 32 + l) * 4 + k;
+							if (e16) pk16[at] = (uint16_t)(((e & TE_IDX) / (uint32_t)(8 * R)) | ((e & TE_SIGN) ? 0x8000u : 0u));
+							else pk32[at] = e;
+						}
+			if (e16) { uint16_t* d = nullptr; if (plan_upload(p, &d, pk16)) return -1; p->tabP = d; }
+			else { uint32_t* d = nullptr; if (plan_upload(p, &d, pk32)) return -1; p->tabP = d; }
+			if (plan_upload(p, &p->choffP, choff)) return -1;
+			if (plan_upload(p, &p->wcnt4P, wc4)) return -1;
+			p->packedE16 = e16 ? 1 : 0;
+			p->packed_mean_slots = 4.0 * choff[nch] / std::max<uint32_t>(nch, 1);
+		}
 	}
 	uint32_t* dtab = nullptr;
 	if (plan_upload(p, &dtab, ntab)) return -1;
@@ -1143,7 +1287,8 @@ static int build_spin_plan(TiledPlan* p, SpinPlan* sp, const HopTable& t, const 
 	return 0;
 }
 
-int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& up, const HopTable& dn, uint64_t row0,
+int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& up, const HopTable& dn, const DiagTables& dt,
+                     uint64_t row0,
                      uint64_t nloc, cudaStream_t s, TiledPlan** out)
 {
 	if (m.model == LPP_MODEL_HEISENBERG) { g_terr = "tiled path is for product bases"; return -1; }
@@ -1267,10 +1412,23 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 #define SETL(R_, U_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_lean<R_, 32, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBL)
 		if (p->leanB) { SETL(1, true); SETL(1, false); SETL(2, true); SETL(2, false); }
 #undef SETL
+		const char* envp = getenv("LPP_TILED_PACKED");
+		p->packedB = p->leanB && p->tabP != nullptr && !(envp && envp[0] == '0');
+		p->smemBP = p->smemBL + ((size_t)(m.n1 + 31) / 32) * 5 + 16;
+		if (p->smemBP + 1024 > (size_t)maxsm) p->packedB = 0;
+#define SETP(R_, U_, E_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_packed<R_, U_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBP)
+		if (p->packedB) { SETP(1, true, true); SETP(1, true, false); SETP(1, false, false); SETP(2, true, true); SETP(2, true, false); SETP(2, false, false); }
+#undef SETP
 		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
 	}
+	if (mags_ok) {
+		int rd = lpp_dtile_create(m, dn, dt.dv2, p->mt, s, &p->dtile);
+		if (rd < 0) { g_terr = std::string("down tile plan: ") + lpp_dtile_error(); delete p; return -1; }
+		if (rd > 0 && getenv("LPP_VERBOSE")) fprintf(stderr, "[lpp tiled] down tile kernel not used: %s\n", lpp_dtile_error());
+	}
 	if (getenv("LPP_VERBOSE"))
-		fprintf(stderr, "[lpp tiled] leanA=%d leanB=%d widthL=%d\n", p->leanA, p->leanB, p->widthL);
+		fprintf(stderr, "[lpp tiled] leanA=%d leanB=%d widthL=%d dtile=%d packedB=%d e16=%d mean slots/warp=%.2f\n", p->leanA, p->leanB, p->widthL,
+		        p->dtile ? 1 : 0, p->packedB, p->packedE16, p->packed_mean_slots);
 	if (getenv("LPP_VERBOSE"))
 		fprintf(stderr, "[lpp tiled] v2=%d blocksA=%d TA=%d W=%d R=%d pipeB=%d NE=%d dn: blocks=%d max=%u width=%d | up: blocks=%d max=%u width=%d sched real=%zu holes=%zu\n",
 		        p->v2, p->blocksA, p->threadsA, p->W, p->R, p->pipeB, p->NE, p->dn.nblocks, p->dn.max_block, p->dn.width, p->up.nblocks, p->up.max_block,
@@ -1289,6 +1447,7 @@ void lpp_tiled_destroy(TiledPlan* p)
 {
 	if (!p) return;
 	for (void* q : p->allocs) cudaFree(q);
+	lpp_dtile_destroy(p->dtile);
 	delete p;
 }
 
@@ -1299,7 +1458,12 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 {
 	int launches = 0;
 	const int dot_in_b = p->has_twospin ? 0 : 1;
-	if (p->v2 && p->blocksA == 2) {
+	const ColView cvfull{m.n1, m.n1, 0};
+	if (p->dtile && p->blocksA == 0 && lpp_dtile_accepts(p->dtile, cvfull)) {
+		SpmvArgs aa = a;
+		aa.dot_partials = nullptr;
+		if (lpp_dtile_sweep(p->dtile, m, dt, aa, p->d0, p->dcount, cvfull, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
+	} else if (p->v2 && p->blocksA == 2) {
 		const unsigned gridA = p->ntilesA_blocks * p->npanels;
 #define RUNA3(W_, T_, B_) k_sweep_down_blocks3<W_, T_, B_><<<gridA, T_, p->smemA3, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks, p->dn.max_block)
 		if (p->threadsA == 512) {
@@ -1335,8 +1499,13 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 		SpmvArgs ab = a;
 		ab.beta = 1.0;                                  // sweep A already applied beta
 #define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
-		if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
+#define RUNP(R_, U_, E_) k_sweep_up_packed<R_, U_, E_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
+		if (p->packedB) {
+			if (p->R == 2) { if (p->packedE16) RUNP(2, true, true); else if (p->mt.nmag == 1) RUNP(2, true, false); else RUNP(2, false, false); }
+			else { if (p->packedE16) RUNP(1, true, true); else if (p->mt.nmag == 1) RUNP(1, true, false); else RUNP(1, false, false); }
+		} else if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
 		else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+#undef RUNP
 #undef RUNL
 	} else if (p->v2) {
 		const unsigned gridB = (unsigned)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
@@ -1378,16 +1547,23 @@ int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, 
 	const uint32_t bsz = (uint32_t)m.n1;
 	const int want_dot = a.dot_partials ? 1 : 0;
 #define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, a, 0, nrows, want_dot)
-	if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
+#define RUNP(R_, U_, E_) k_sweep_up_packed<R_, U_, E_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, a, 0, nrows, want_dot)
+	if (p->packedB) {
+		if (p->R == 2) { if (p->packedE16) RUNP(2, true, true); else if (p->mt.nmag == 1) RUNP(2, true, false); else RUNP(2, false, false); }
+		else { if (p->packedE16) RUNP(1, true, true); else if (p->mt.nmag == 1) RUNP(1, true, false); else RUNP(1, false, false); }
+	} else if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
 	else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+#undef RUNP
 #undef RUNL
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); return -1; }
 	return 1;
 }
 
-int lpp_tiled_down_cols_blocks(const ModelDev& m, uint64_t ncols)
+int lpp_tiled_down_cols_blocks(const TiledPlan* p, const ModelDev& m, uint64_t ncols)
 {
+	const ColView cvt{ncols, ncols, 0};
+	if (p->dtile && lpp_dtile_accepts(p->dtile, cvt)) return lpp_dtile_grid(p->dtile, cvt);
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, 0};
 	return (int)(down_lean_panels(cv) * nchunks);
@@ -1399,8 +1575,12 @@ int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& d
 {
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, u0};
-	if (down_lean_vec(cv) == 2) k_sweep_down_lean<2><<<lpp_tiled_down_cols_blocks(m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
-	else k_sweep_down_lean<1><<<lpp_tiled_down_cols_blocks(m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
+	if (p->dtile && lpp_dtile_accepts(p->dtile, cv)) {
+		if (lpp_dtile_sweep(p->dtile, m, dt, a, 0, m.n2, cv, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
+		return 1;
+	}
+	if (down_lean_vec(cv) == 2) k_sweep_down_lean<2><<<lpp_tiled_down_cols_blocks(p, m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
+	else k_sweep_down_lean<1><<<lpp_tiled_down_cols_blocks(p, m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); return -1; }
 	return 1;

@@ -190,3 +190,33 @@ def test_full_size_properties_c3(lpp):
     en, _, a, b = solver.computeOneState(None, want_vector=False)
     assert abs(en - eref) <= 1e-8 * abs(eref)
     e.close()
+
+
+@pytest.mark.parametrize("cap", ["3", "16", "200"])
+def test_down_tile_kernel_with_small_blocks(lpp, oracle, cap, monkeypatch):
+    """The shared-memory tile kernel of the down sweep (lpp_dtile.cu) with the block size capped, so that small bases are
+    split into several blocks and hops leave their block (the external-operand path), against the oracle."""
+    monkeypatch.setenv("LPP_DTILE", "1")
+    monkeypatch.setenv("LPP_DTILE_CAP", cap)
+    for name in ("c1_hub8", "hub6_pbc_V", "hub_3x3", "feas4", "feas_2x2"):
+        case = cases.SMALL_CASES[name]
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        e = cases.make_engine(lpp, case)
+        y = geo.splitmix64_vector(o.rows(), 42)
+        x0 = geo.splitmix64_vector(o.rows(), 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+        assert relerr(x, xref) <= 1e-13, (name, cap)
+        e.close()
+    case = cases.hubbard_chain(12, 6, 6, periodic=True)                    # dim 853776, 924 down states
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    e = cases.make_engine(lpp, case)
+    y = geo.splitmix64_vector(o.rows(), 42)
+    xref = np.zeros(o.rows())
+    o.matvec(xref, y, faithful=False)
+    x = np.zeros(o.rows())
+    e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+    assert relerr(x, xref) <= 1e-13, cap
+    e.close()
