@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -95,6 +95,16 @@ def measured_peak():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic(workload, world):
+    """DRAM bytes (read + write) per SpMV from the committed `ncu --set full` capture of the two sweep kernels
+    (profiles/traffic_r01.json, written from profiles/prof_sweeps_r01_final_raw.csv); None when no capture applies."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if workload != "c3" or world != 1 or not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    return float(t["spmv_traffic_bytes"]), t["kernels"]
 
 
 def cpu_sample(case, budget_rows, faithful, steps, warmup):
@@ -233,6 +243,7 @@ def main():
     peak, peak_src = measured_peak()
     spmv_bytes = BYTES_PER_ROW_SPMV * rows / world           # per GPU, per launch of the SpMV
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    traffic, traffic_kernels = measured_traffic(args.workload, world)
     line = {"metric": METRIC, "value": iter_ms * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": iter_ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -242,8 +253,12 @@ def main():
             "spmv_ms": spmv_ms, "spmv_gbs": BYTES_PER_ROW_SPMV * rows / (spmv_ms * 1e-3) / 1e9,
             "iter_gbs": BYTES_PER_ROW_ITER * rows / (iter_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "x += H y (all sweeps of one SpMV), 24 B/row algorithmic, per GPU"},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "x += H y = k_sweep_down_lean + k_sweep_up_packed (one launch each), 24 B/row algorithmic, "
+                                   "per GPU; duration = CUDA events around both launches on the engine's stream",
+                         "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram read+write of both sweeps)"
+                                           if traffic else None,
+                         "ncu_kernels": traffic_kernels},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": nloc * 8.0 / len(a), "d2h_bytes_per_step": 16},
             "energy": energy}

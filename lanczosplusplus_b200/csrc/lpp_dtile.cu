@@ -573,3 +573,237 @@ int lpp_dtile_sweep(DownTilePlan* p, const ModelDev& m, const DiagTables& dt, co
 	if (e != cudaSuccess) { g_derr = cudaGetErrorString(e); return -1; }
 	return 1;
 }
+
+// =====================================================================================================
+// k_sweep_down_rows: the down sweep without a staged tile (see lpp_dtile.cuh)
+// =====================================================================================================
+#ifndef DR_THREADS
+#define DR_THREADS 768
+#endif
+#define DR_WARPS (DR_THREADS / 32)
+#define DR_MAXHOPS 32
+#define DR_REC 272             // bytes per record of 4 consecutive rows: 16-byte header + 4 x 32 two-byte entries
+#ifndef DR_SPLIT
+#define DR_SPLIT 8             // row ranges per column group (grid = column groups x DR_SPLIT)
+#endif
+
+struct DownRowsPlan {
+	const uint4* rec = nullptr;   // record q covers down states 4q .. 4q+3: header bytes {cnt0, cnt1, cnt2, cnt3, max, ...},
+	                              // then entries[4][32]: [15] sign | [13:0] source down state
+	uint32_t nquads = 0;
+	uint64_t n2 = 0;
+	MagTable mt;
+	std::vector<void*> allocs;
+};
+
+__device__ __forceinline__ double2 dr_ldg16_if(const void* ptr, bool pred)
+{
+	double2 v;
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\tmov.f64 %1, 0d0000000000000000;\n\t"
+	             "@p ld.global.v2.f64 {%0, %1}, [%2];\n\t}"
+	             : "=d"(v.x), "=d"(v.y) : "l"(ptr), "r"((uint32_t)pred));
+	return v;
+}
+
+__global__ void __launch_bounds__(DR_THREADS, 1)
+k_sweep_down_rows(ModelDev m, const uint4* __restrict__ rec, uint32_t nquads, double t0, DiagTables dt, SpmvArgs a, uint64_t d0,
+                  uint64_t dcount, ColView cv)
+{
+	extern __shared__ __align__(16) unsigned char dr_smem[];   // [warp][2 stages][DR_REC]
+	const uint32_t g = blockIdx.x / DR_SPLIT, sp = blockIdx.x % DR_SPLIT;
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l8 = lane & 7, grp = lane >> 3;
+	const uint64_t c = (uint64_t)g * 16 + 2 * l8;
+	const bool colok = c < cv.ncols;
+	const uint32_t pitch8 = (uint32_t)(cv.pitch * 8ull);
+	const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + (colok ? c : 0));
+	char* __restrict__ xcol = reinterpret_cast<char*>(a.x + (colok ? c : 0));
+	// this CTA's quads: an equal share of the quad list, walked in rounds of DR_WARPS consecutive quads
+	const uint32_t per = (nquads + DR_SPLIT - 1) / DR_SPLIT;
+	const uint32_t qa = sp * per, qb = min(nquads, qa + per);
+	const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dr_smem) + warp * (2 * DR_REC);
+	word_t k1[2] = {0, 0};
+	double dv1[2] = {0.0, 0.0};
+	if (colok) {
+#pragma unroll
+		for (int v = 0; v < 2; v++) {
+			k1[v] = m.b1[cv.u0 + c + v];
+			dv1[v] = dt.dv1[cv.u0 + c + v];
+		}
+	}
+	const bool need_x = a.beta != 0.0;
+	const bool fastdiag = (m.model == LPP_MODEL_HUBBARD) && dt.uniformU;
+	const uint32_t d0w = (uint32_t)d0, dcw = (uint32_t)dcount, n2w = (uint32_t)m.n2;
+	double contrib = 0.0;
+
+	auto fetch = [&](uint32_t q, uint32_t stage) {
+		if (q < qb && lane < DR_REC / 16) dt_cp16(ring + stage * DR_REC + lane * 16, rec + (size_t)q * (DR_REC / 16) + lane);
+		asm volatile("cp.async.commit_group;");
+	};
+	uint32_t q = qa + warp;
+	fetch(q, 0);
+	fetch(q + DR_WARPS, 1);
+	uint32_t stage = 0;
+	for (; q < qb; q += DR_WARPS, stage ^= 1) {
+		asm volatile("cp.async.wait_group 1;");
+		__syncwarp();
+		const uint32_t rb = ring + stage * DR_REC;
+		const uint2 hd = dt_lds8u(rb);
+		const int padnet = (int)(int8_t)((hd.x >> (8 * grp)) & 0xffu);      // ('+' pads) - ('-' pads) of my row
+		const uint32_t pg = hd.y & 0xffu, ng = (hd.y >> 8) & 0xffu;          // groups of 4 slots: '+' groups, all groups
+		const uint32_t d = 4 * q + grp;
+		const uint32_t dl = d - d0w;
+		const bool act = colok && d < n2w && dl < dcw;
+		const uint64_t xoff = (uint64_t)(act ? dl : 0u) * pitch8;
+		const double2 ys = __ldg(reinterpret_cast<const double2*>(ycol + (uint64_t)(d < n2w ? d : 0u) * pitch8));
+		double2 xo = make_double2(0.0, 0.0);
+		if (act && need_x) xo = __ldcs(reinterpret_cast<const double2*>(xcol + xoff));
+		word_t k2 = 0;
+		double dv2 = 0.0;
+		if (act) { k2 = m.b2[d]; dv2 = dt.dv2[d]; }
+		// every slot is an unconditional 16-byte load (padding slots point at the row itself and are subtracted below);
+		// the sign is warp-uniform per group of 4 slots: '+' groups first, then '-' groups
+		double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+#pragma unroll
+		for (int bt = 0; bt < DR_MAXHOPS / 8; bt++)
+			if (8 * bt < (int)(4 * ng)) {                       // warp-uniform
+				const uint4 e4 = dt_lds16u(rb + 16 + grp * (DR_MAXHOPS * 2) + bt * 16);
+				const uint32_t w[4] = {e4.x, e4.y, e4.z, e4.w};
+				double2 v[8];
+#pragma unroll
+				for (int i = 0; i < 8; i++) {
+					const uint32_t e = (i & 1) ? (w[i >> 1] >> 16) : (w[i >> 1] & 0xffffu);
+					v[i] = __ldg(reinterpret_cast<const double2*>(ycol + (uint64_t)e * pitch8));
+				}
+				const double sa = (2 * bt < (int)pg) ? t0 : -t0;      // slots 8bt .. 8bt+3
+				const double sb = (2 * bt + 1 < (int)pg) ? t0 : ((2 * bt + 1 < (int)ng) ? -t0 : 0.0);
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					double (&pp)[2] = (i & 1) ? acc1 : acc0;
+					pp[0] = fma(sa, v[i].x, pp[0]);
+					pp[1] = fma(sa, v[i].y, pp[1]);
+				}
+#pragma unroll
+				for (int i = 4; i < 8; i++) {
+					double (&pp)[2] = (i & 1) ? acc1 : acc0;
+					pp[0] = fma(sb, v[i].x, pp[0]);
+					pp[1] = fma(sb, v[i].y, pp[1]);
+				}
+			}
+		const double corr = -t0 * (double)padnet;
+		__syncwarp();
+		fetch(q + 2 * DR_WARPS, stage);
+		if (act) {
+			double xn[2];
+			const double yv[2] = {ys.x, ys.y};
+			const double xov[2] = {xo.x, xo.y};
+#pragma unroll
+			for (int v = 0; v < 2; v++) {
+				const double dg = fastdiag ? dt.U0 * (double)lpp_popc(k1[v] & k2) + dv1[v] + dv2
+				                           : tiled_diag(m, dt, k1[v], k2, cv.u0 + c + v, d);
+				xn[v] = a.alpha * fma(dg + corr, yv[v], acc0[v] + acc1[v]);
+				if (need_x) xn[v] = fma(a.beta, xov[v], xn[v]);
+				contrib = fma(yv[v], xn[v], contrib);
+			}
+			__stcs(reinterpret_cast<double2*>(xcol + xoff), make_double2(xn[0], xn[1]));
+		}
+	}
+	asm volatile("cp.async.wait_group 0;");
+	if (a.dot_partials) {
+		const double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = s;
+	}
+}
+
+int lpp_drows_create(const ModelDev& m, const HopTable& dn, const MagTable& mt, cudaStream_t s, DownRowsPlan** out)
+{
+	*out = nullptr;
+	// Opt-in (LPP_DROWS=1): measured 2.3 ms per sweep on the 4x4 lattice against 2.1 ms for the streaming kernel.  It does
+	// what it was built for (L1 hit rate 55 %, L2->SM traffic 18 GB instead of 26.9 GB) but gathers served by L1 hits and L2
+	// together top out near 45 B/clk/SM, so the sweep stays latency bound (profiles/README.md, "row-walking kernel").
+	const char* env = getenv("LPP_DROWS");
+	if (!(env && env[0] == '1')) { g_derr = "not enabled (set LPP_DROWS=1)"; return 1; }
+	if (m.model == LPP_MODEL_HEISENBERG) { g_derr = "one-spin basis"; return 1; }
+	if (mt.nmag != 1) { g_derr = "more than one hop magnitude"; return 1; }
+	const uint64_t n = dn.n;
+	if (n > (1u << 14)) { g_derr = "down basis too large for 14-bit entries"; return 1; }
+	if (dn.width > DR_MAXHOPS) { g_derr = "too many hops per state"; return 1; }
+	DCK(cudaStreamSynchronize(s));
+	const int width = dn.width;
+	std::vector<uint32_t> idx((size_t)std::max(width, 1) * n), cnt(n);
+	std::vector<double> val((size_t)std::max(width, 1) * n);
+	DCK(cudaMemcpy(cnt.data(), dn.cnt, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+	if (width > 0) {
+		DCK(cudaMemcpy(idx.data(), dn.idx, sizeof(uint32_t) * idx.size(), cudaMemcpyDeviceToHost));
+		DCK(cudaMemcpy(val.data(), dn.val, sizeof(double) * val.size(), cudaMemcpyDeviceToHost));
+	}
+	DownRowsPlan* p = new DownRowsPlan();
+	p->mt = mt;
+	p->n2 = n;
+	p->nquads = (uint32_t)((n + 3) / 4);
+	std::vector<uint8_t> rec((size_t)p->nquads * DR_REC, 0);
+	unsigned long long nslots_total = 0;
+	for (uint32_t q = 0; q < p->nquads; q++) {
+		uint8_t* R = rec.data() + (size_t)q * DR_REC;
+		uint16_t* E = reinterpret_cast<uint16_t*>(R + 16);
+		std::vector<uint16_t> plus[4], minus[4];
+		uint32_t mp = 0, mm = 0;
+		for (int r = 0; r < 4; r++) {
+			const uint64_t d = 4ull * q + r;
+			if (d >= n) continue;
+			for (uint32_t k = 0; k < cnt[d]; k++) {
+				const double v = val[(size_t)k * n + d];
+				if (v == 0.0) continue;
+				if (fabs(v) != mt.mag[0]) { g_derr = "hop amplitude not in the magnitude table"; delete p; return 1; }
+				(v < 0 ? minus[r] : plus[r]).push_back((uint16_t)idx[(size_t)k * n + d]);
+			}
+			mp = std::max<uint32_t>(mp, (uint32_t)plus[r].size());
+			mm = std::max<uint32_t>(mm, (uint32_t)minus[r].size());
+		}
+		const uint32_t pg = (mp + 3) / 4, mg = (mm + 3) / 4;     // groups of 4 slots
+		if (4 * (pg + mg) > DR_MAXHOPS) { g_derr = "too many hop slots per quad"; delete p; return 1; }
+		for (int r = 0; r < 4; r++) {
+			const uint64_t d = std::min<uint64_t>(4ull * q + r, n - 1);   // padding slots: the row itself (always a valid address)
+			for (uint32_t j = 0; j < 4 * (pg + mg); j++) E[r * DR_MAXHOPS + j] = (uint16_t)d;
+			for (size_t j = 0; j < plus[r].size(); j++) E[r * DR_MAXHOPS + j] = plus[r][j];
+			for (size_t j = 0; j < minus[r].size(); j++) E[r * DR_MAXHOPS + 4 * pg + j] = minus[r][j];
+			const int padp = (int)(4 * pg - plus[r].size()), padm = (int)(4 * mg - minus[r].size());
+			R[r] = (uint8_t)(int8_t)(padp - padm);
+		}
+		R[4] = (uint8_t)pg;
+		R[5] = (uint8_t)(pg + mg);
+		nslots_total += 4ull * (pg + mg);
+	}
+	if (getenv("LPP_VERBOSE")) fprintf(stderr, "[lpp drows] quads=%u mean slots per row %.2f\n", p->nquads, (double)nslots_total / std::max<uint32_t>(p->nquads, 1));
+	void* dptr = nullptr;
+	DCK(cudaMalloc(&dptr, rec.size()));
+	p->allocs.push_back(dptr);
+	DCK(cudaMemcpy(dptr, rec.data(), rec.size(), cudaMemcpyHostToDevice));
+	p->rec = reinterpret_cast<const uint4*>(dptr);
+	*out = p;
+	return 0;
+}
+
+void lpp_drows_destroy(DownRowsPlan* p)
+{
+	if (!p) return;
+	for (void* q : p->allocs) cudaFree(q);
+	delete p;
+}
+
+int lpp_drows_accepts(const DownRowsPlan* p, const ColView& cv)
+{
+	return (p && cv.pitch % 2 == 0 && cv.ncols % 2 == 0 && cv.ncols > 0 && cv.pitch * 8ull < (1ull << 32)) ? 1 : 0;
+}
+
+int lpp_drows_grid(const DownRowsPlan* p, const ColView& cv) { return (int)(((cv.ncols + 15) / 16) * DR_SPLIT); }
+
+int lpp_drows_sweep(DownRowsPlan* p, const ModelDev& m, const DiagTables& dt, const SpmvArgs& a, uint64_t d0, uint64_t dcount,
+                    const ColView& cv, cudaStream_t s)
+{
+	if (!lpp_drows_accepts(p, cv)) { g_derr = "column view needs an even pitch and an even column count"; return -1; }
+	const size_t smem = (size_t)DR_WARPS * 2 * DR_REC;
+	k_sweep_down_rows<<<(unsigned)lpp_drows_grid(p, cv), DR_THREADS, smem, s>>>(m, p->rec, p->nquads, p->mt.mag[0], dt, a, d0, dcount, cv);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) { g_derr = cudaGetErrorString(e); return -1; }
+	return 1;
+}

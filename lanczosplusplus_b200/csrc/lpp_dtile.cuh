@@ -19,3 +19,15 @@ int lpp_dtile_grid(const DownTilePlan* p, const ColView& cv);
 int lpp_dtile_sweep(DownTilePlan* p, const ModelDev& m, const DiagTables& dt, const SpmvArgs& a, uint64_t d0, uint64_t dcount,
                     const ColView& cv, cudaStream_t s);
 void lpp_dtile_describe(const DownTilePlan* p, char* buf, size_t n);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-walking variant of the down sweep (k_sweep_down_rows): no staged tile; a CTA of 24 warps walks consecutive down
+// states for one group of 16 columns, a quarter-warp per row, and gathers straight from global memory, so that the
+// hop sources shared by neighbouring rows (colex neighbours differ in the low sites) are L1 hits instead of L2 reads.
+struct DownRowsPlan;
+int lpp_drows_create(const ModelDev& m, const HopTable& dn, const MagTable& mt, cudaStream_t s, DownRowsPlan** out);
+void lpp_drows_destroy(DownRowsPlan* p);
+int lpp_drows_accepts(const DownRowsPlan* p, const ColView& cv);
+int lpp_drows_grid(const DownRowsPlan* p, const ColView& cv);
+int lpp_drows_sweep(DownRowsPlan* p, const ModelDev& m, const DiagTables& dt, const SpmvArgs& a, uint64_t d0, uint64_t dcount,
+                    const ColView& cv, cudaStream_t s);

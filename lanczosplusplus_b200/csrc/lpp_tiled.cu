@@ -76,6 +76,7 @@ struct TiledPlan {
 	size_t smemBP = 0;
 	double packed_mean_slots = 0;
 	int leanA = 1, leanB = 0;
+	DownRowsPlan* drows = nullptr;   // row-walking sweep A (k_sweep_down_rows, lpp_dtile.cu); nullptr: streaming kernel
 	DownTilePlan* dtile = nullptr;   // shared-memory tile kernel for sweep A (lpp_dtile.cu, opt-in); nullptr: streaming kernel
 	size_t smemAL = 0, smemBL = 0;
 	size_t smemA3 = 0;
@@ -1425,6 +1426,9 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		int rd = lpp_dtile_create(m, dn, dt.dv2, p->mt, s, &p->dtile);
 		if (rd < 0) { g_terr = std::string("down tile plan: ") + lpp_dtile_error(); delete p; return -1; }
 		if (rd > 0 && getenv("LPP_VERBOSE")) fprintf(stderr, "[lpp tiled] down tile kernel not used: %s\n", lpp_dtile_error());
+		rd = lpp_drows_create(m, dn, p->mt, s, &p->drows);
+		if (rd < 0) { g_terr = std::string("down rows plan: ") + lpp_dtile_error(); delete p; return -1; }
+		if (rd > 0 && getenv("LPP_VERBOSE")) fprintf(stderr, "[lpp tiled] row-walking down kernel not used: %s\n", lpp_dtile_error());
 	}
 	if (getenv("LPP_VERBOSE"))
 		fprintf(stderr, "[lpp tiled] leanA=%d leanB=%d widthL=%d dtile=%d packedB=%d e16=%d mean slots/warp=%.2f\n", p->leanA, p->leanB, p->widthL,
@@ -1448,6 +1452,7 @@ void lpp_tiled_destroy(TiledPlan* p)
 	if (!p) return;
 	for (void* q : p->allocs) cudaFree(q);
 	lpp_dtile_destroy(p->dtile);
+	lpp_drows_destroy(p->drows);
 	delete p;
 }
 
@@ -1459,7 +1464,11 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 	int launches = 0;
 	const int dot_in_b = p->has_twospin ? 0 : 1;
 	const ColView cvfull{m.n1, m.n1, 0};
-	if (p->dtile && p->blocksA == 0 && lpp_dtile_accepts(p->dtile, cvfull)) {
+	if (p->drows && !p->dtile && p->blocksA == 0 && lpp_drows_accepts(p->drows, cvfull)) {
+		SpmvArgs aa = a;
+		aa.dot_partials = nullptr;
+		if (lpp_drows_sweep(p->drows, m, dt, aa, p->d0, p->dcount, cvfull, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
+	} else if (p->dtile && p->blocksA == 0 && lpp_dtile_accepts(p->dtile, cvfull)) {
 		SpmvArgs aa = a;
 		aa.dot_partials = nullptr;
 		if (lpp_dtile_sweep(p->dtile, m, dt, aa, p->d0, p->dcount, cvfull, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
@@ -1563,6 +1572,7 @@ int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, 
 int lpp_tiled_down_cols_blocks(const TiledPlan* p, const ModelDev& m, uint64_t ncols)
 {
 	const ColView cvt{ncols, ncols, 0};
+	if (p->drows && !p->dtile && lpp_drows_accepts(p->drows, cvt)) return lpp_drows_grid(p->drows, cvt);
 	if (p->dtile && lpp_dtile_accepts(p->dtile, cvt)) return lpp_dtile_grid(p->dtile, cvt);
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, 0};
@@ -1575,6 +1585,10 @@ int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& d
 {
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, u0};
+	if (p->drows && !p->dtile && lpp_drows_accepts(p->drows, cv)) {
+		if (lpp_drows_sweep(p->drows, m, dt, a, 0, m.n2, cv, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
+		return 1;
+	}
 	if (p->dtile && lpp_dtile_accepts(p->dtile, cv)) {
 		if (lpp_dtile_sweep(p->dtile, m, dt, a, 0, m.n2, cv, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
 		return 1;

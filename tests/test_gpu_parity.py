@@ -220,3 +220,45 @@ def test_down_tile_kernel_with_small_blocks(lpp, oracle, cap, monkeypatch):
     e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
     assert relerr(x, xref) <= 1e-13, cap
     e.close()
+
+
+def test_row_walking_down_kernel(lpp, oracle, monkeypatch):
+    """k_sweep_down_rows (opt-in, lpp_dtile.cu): unconditional gathers with sign-split slot groups and self-padding."""
+    monkeypatch.setenv("LPP_DROWS", "1")
+    for case in (cases.SMALL_CASES["c1_hub8"], cases.SMALL_CASES["hub6_pbc_V"], cases.hubbard_square(4, 3, 6, 6),
+                 cases.hubbard_chain(12, 6, 5, periodic=True)):
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        e = cases.make_engine(lpp, case)
+        y = geo.splitmix64_vector(o.rows(), 42)
+        x0 = geo.splitmix64_vector(o.rows(), 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+        assert relerr(x, xref) <= 1e-13
+        e.close()
+
+
+def test_large_up_basis_c5_structure(lpp, oracle):
+    """Config-5 structure at a size one GPU and the oracle handle quickly: 18-site open chain, 9 up electrons (48 620 up
+    states: an up segment no longer fits in shared memory, so the blocked up-sweep path runs), 2 down; dim 7 438 860."""
+    case = cases.hubbard_chain(18, 9, 2)
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    e = cases.make_engine(lpp, case)
+    assert e.rows() == o.rows() == 48620 * 153
+    y = geo.splitmix64_vector(o.rows(), 42)
+    x0 = geo.splitmix64_vector(o.rows(), 7)
+    xref = x0.copy()
+    o.matvec(xref, y, faithful=False)
+    for k in (lpp.KERNEL_TABLE, lpp.KERNEL_TILED):
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, xref) <= 1e-13, k
+    # U = 0: ground state energy = sum of the lowest single-particle levels of each species
+    e.close()
+    levels = np.sort(np.linalg.eigvalsh(geo.chain(18, -1.0, False)))
+    eref = levels[:9].sum() + levels[:2].sum()
+    e = cases.make_engine(lpp, cases.hubbard_chain(18, 9, 2, U=0.0))
+    en, _, a, b = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=300, eps=1e-12)).computeOneState(None, want_vector=False)
+    assert abs(en - eref) <= 1e-9 * abs(eref)
+    e.close()
