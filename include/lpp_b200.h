@@ -152,6 +152,10 @@ int lpp_tridiag_eig(int32_t n, const double* a, const double* b, double* eigs, d
  * lpp_comm_unique_id, broadcasts the 128 bytes, and every rank calls lpp_comm_init. */
 int lpp_comm_unique_id(uint8_t id[128]);
 int lpp_comm_init(lpp_handle* h, const uint8_t id[128]);
+/* A new-sector handle created for the continued-fraction path (Engine.h:165-187 creates the (nup-1, ndown) basis while the
+ * ground-state handle is alive) borrows the communicator of the handle it was derived from: same ranks, same device.  The
+ * borrowed communicator is not destroyed with `h`; `parent` must outlive it and must be idle while `h` runs. */
+int lpp_comm_share(lpp_handle* h, const lpp_handle* parent);
 
 /* Peer-memory exchange for the two-layout sharding (Hubbard-type product bases, nranks > 1): every rank exports the CUDA IPC
  * handles of its column-shard buffers (128 bytes), the launcher all-gathers them, every rank imports the nranks*128 bytes.

@@ -119,6 +119,7 @@ SYMBOLS = {
     "lpp_tridiag_eig": (C.c_int, [C.c_int32, _VP, _VP, _VP, _VP]),
     "lpp_comm_unique_id": (C.c_int, [_VP]),
     "lpp_comm_init": (C.c_int, [_VP, _VP]),
+    "lpp_comm_share": (C.c_int, [_VP, _VP]),
     "lpp_p2p_export": (C.c_int, [_VP, C.c_int32, _VP]),
     "lpp_p2p_import": (C.c_int, [_VP, _VP]),
     "lpp_bench_spmv": (C.c_int, [_VP, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Timing)]),

@@ -119,6 +119,7 @@ struct lpp_handle {
 	double* scal_host = nullptr;
 	// comm
 	ncclComm_t comm = nullptr;
+	bool comm_borrowed = false;    // lpp_comm_share: the communicator belongs to another handle
 	// two-layout sharding (product bases without two-spin terms): the up sweep runs on the ROW shard, the down sweep on the
 	// COLUMN shard, linked by two all-to-all transposes per mat-vec (SURVEY §8e alternative A)
 	int two_layout = -1;          // -1 undecided, 0 no, 1 yes
@@ -215,7 +216,7 @@ extern "C" int lpp_destroy(lpp_handle* h)
 	if (!h) return 0;
 	cudaSetDevice(h->device);
 	for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
-	if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+	if (h->comm && !h->comm_borrowed && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 	if (h->tiled) lpp_tiled_destroy(h->tiled);
 	for (void* p : h->allocs) cudaFree(p);
 	if (h->scal_host) cudaFreeHost(h->scal_host);
@@ -811,7 +812,8 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 //   S pack y -> per-peer column blocks | C all-to-all (y: ROW -> COLUMN layout)  ||  S up sweep on the ROW shard
 //   S down sweep + diagonal on the COLUMN shard | C all-to-all (x: COLUMN -> ROW) | S x_row += received blocks
 // The Lanczos dot <y, x> is the sum of the two sweeps' partial sums (it is layout independent).
-static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, const double* y, bool want_dot, double* dot_out)
+static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, const double* y, bool want_dot, double* dot_out,
+                           bool defer_unpack = false)
 {
 	if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
 	cudaStream_t S = h->stream, C = h->comm_stream;
@@ -823,14 +825,19 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		//   down sweep on ycol -> xcol | all-reduce #2 (the Lanczos dot): everybody's xcol is final | unpack (remote loads)
 		// The next pack / down sweep cannot overwrite a buffer a peer still reads: each is issued after an all-reduce
 		// that the peer only enters once it has finished reading (stream order).
+		// The pack (NVLink stores, no shared memory) runs on the second stream next to the up sweep (L1/shared bound).
 		C = S;
-		lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, S);
+		CK(cudaEventRecord(h->ev_pack, S));
+		CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
+		lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, h->comm_stream);
+		CK(cudaEventRecord(h->ev_ycol, h->comm_stream));
 		const int nbB = lpp_tiled_up_rows_blocks(h->tiled, nrows);
 		CKR(ensure_partials(h, std::max(nbB, lpp_vec_blocks(h->nloc))));
 		SpmvArgs ab;
 		ab.alpha = alpha; ab.beta = beta; ab.x = x; ab.y = y; ab.row0 = 0; ab.nloc = h->nloc;
 		ab.dot_partials = want_dot ? h->partials : nullptr;
 		if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nrows, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+		CK(cudaStreamWaitEvent(S, h->ev_ycol, 0));
 		CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
 		SpmvArgs aa;
 		aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
@@ -843,8 +850,9 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		}
 		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 2, kNcclFloat64, kNcclSum, h->comm, S));
 		if (want_dot) CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, S));
-		lpp_launch_unpack_add_p2p(x, h->peer_xcol, nrows, n1, h->cols, d0loc, S);
-		h->launches += want_dot ? 6 : 4;
+		// defer_unpack: the caller folds the re-layout of the column-shard result into its next pass over x
+		if (!defer_unpack) lpp_launch_unpack_add_p2p(x, h->peer_xcol, nrows, n1, h->cols, d0loc, S);
+		h->launches += (want_dot ? 6 : 4) - (defer_unpack ? 1 : 0);
 		if (want_dot) {
 			CK(cudaStreamSynchronize(S));
 			*dot_out = h->scal_host[0] + h->scal_host[1];
@@ -954,8 +962,9 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 		if (tm && j == tm->from) { CK(cudaEventRecord(h->ev0, h->stream)); tm->launches_at_from = h->launches; }
 		if (zcoef) { lpp_launch_axpy(z, y, zcoef[j] / nj, n, h->stream); h->launches += 1; }
 		double dot = 0;
+		const bool fuse_unpack = h->two_layout == 1 && h->p2p;
 		if (h->two_layout == 1) {
-			CKR(spmv_two_layout(h, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, y, true, &dot));
+			CKR(spmv_two_layout(h, 1.0 / nj, j == 0 ? 0.0 : -(bprev / nprev), x, y, true, &dot, fuse_unpack));
 		} else {
 			const double* src = nullptr;
 			CKR(gather_full(h, y, &src));
@@ -964,10 +973,18 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 			CKR(reduce_scalar(h, nparts, &dot));
 		}
 		double aj = dot / nj;
-		lpp_launch_axpy_norm(x, y, aj / nj, n, h->partials, h->stream);
+		int npb = np;
+		if (fuse_unpack) {
+			const uint64_t n1 = h->md.n1, nrows = h->nloc / n1;
+			npb = lpp_unpack_axpy_norm_blocks(nrows, n1);
+			CKR(ensure_partials(h, npb));
+			lpp_launch_unpack_axpy_norm_p2p(x, y, aj / nj, h->peer_xcol, nrows, n1, h->cols, h->row0 / n1, h->partials, h->stream);
+		} else {
+			lpp_launch_axpy_norm(x, y, aj / nj, n, h->partials, h->stream);
+		}
 		h->launches += 1;
 		double b2 = 0;
-		CKR(reduce_scalar(h, np, &b2));
+		CKR(reduce_scalar(h, npb, &b2));
 		double bj = sqrt(b2);
 		a[j] = aj;
 		b[j] = bj;
@@ -1118,6 +1135,18 @@ extern "C" int lpp_comm_init(lpp_handle* h, const uint8_t id[128])
 	ncclUniqueId u;
 	memcpy(u.internal, id, 128);
 	CKN(g_nccl.CommInitRank(&h->comm, h->desc.nranks, u, h->desc.rank));
+	return 0;
+}
+
+extern "C" int lpp_comm_share(lpp_handle* h, const lpp_handle* parent)
+{
+	if (!h || !parent) return fail(LPP_ERR_ARG, "null argument");
+	if (!parent->comm) return fail(LPP_ERR_STATE, "parent handle has no communicator");
+	if (h->desc.nranks != parent->desc.nranks || h->desc.rank != parent->desc.rank || h->device != parent->device)
+		return fail(LPP_ERR_ARG, "handles must share ranks and device");
+	if (h->comm && !h->comm_borrowed) return fail(LPP_ERR_STATE, "handle already owns a communicator");
+	h->comm = parent->comm;
+	h->comm_borrowed = true;
 	return 0;
 }
 

@@ -623,6 +623,27 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__
 	}
 }
 
+// x <- x + (peers' column-shard results) - coef * y ;  partials <- block sums of x_new^2.
+// The re-layout of the down-sweep result and the Lanczos "x -= a y, b^2 = |x|^2" sweep in one pass over the row shard.
+__global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __restrict__ x, const double* __restrict__ y, double coef,
+                                                                 PeerPtrs xcols, uint64_t nrows, uint64_t n1, ColSplit c,
+                                                                 uint64_t d0loc, double* __restrict__ partials)
+{
+	const uint64_t r = blockIdx.y;
+	double* __restrict__ xrow = x + r * n1;
+	const double* __restrict__ yrow = y + r * n1;
+	double s = 0.0;
+	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+		const int q = lpp_col_owner(c, u);
+		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
+		const double v = xrow[u] + xcols.p[q][(d0loc + r) * nc + cu] - coef * yrow[u];
+		xrow[u] = v;
+		s += v * v;
+	}
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
 static dim3 lpp_rowwise_grid(uint64_t nrows, uint64_t n1)
 {
 	unsigned gx = (unsigned)((n1 + (uint64_t)LPP_TPB * 4 - 1) / ((uint64_t)LPP_TPB * 4));
@@ -638,6 +659,17 @@ void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows,
                                cudaStream_t s)
 {
 	k_unpack_add_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(x, xcols, nrows, n1, c, d0loc);
+}
+
+int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1)
+{
+	dim3 g = lpp_rowwise_grid(nrows, n1);
+	return (int)(g.x * g.y);
+}
+void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1,
+                                     const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s)
+{
+	k_unpack_axpy_norm_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(x, y, coef, xcols, nrows, n1, c, d0loc, partials);
 }
 
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,

@@ -77,9 +77,13 @@ class InternalProductCuda:
     def sector(self, nup, ndown, **kw):
         """model.createBasis(nup', ndown') + InternalProduct on it (Engine.h:165-187)."""
         hop, jzz, U, V, D = self._keep
-        return InternalProductCuda(self.model, self.nsite, nup, ndown, self.orbitals, hop, jzz, U, V, D,
-                                   self._desc.feas_u3_all_pairs, self._desc.device, self.rank, self.nranks,
-                                   kw.get("kernel", self.kernel))
+        s = InternalProductCuda(self.model, self.nsite, nup, ndown, self.orbitals, hop, jzz, U, V, D,
+                                self._desc.feas_u3_all_pairs, self._desc.device, self.rank, self.nranks,
+                                kw.get("kernel", self.kernel))
+        if self.nranks > 1 and getattr(self, "_has_comm", False):
+            check(_lib.lib().lpp_comm_share(s.h, self.h))      # same ranks, same device: borrow the communicator
+            s._has_comm = True
+        return s
 
     # --- InternalProductOnTheFly interface
     def rows(self):
@@ -147,6 +151,7 @@ class InternalProductCuda:
     def comm_init(self, unique_id):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         check(_lib.lib().lpp_comm_init(self.h, buf))
+        self._has_comm = True
 
     def p2p_export(self, kernel=None):
         """128 bytes of CUDA IPC handles of this rank's column-shard buffers, or None when two-layout sharding does not apply."""
