@@ -120,6 +120,16 @@ struct lpp_handle {
 	// comm
 	ncclComm_t comm = nullptr;
 	bool comm_borrowed = false;    // lpp_comm_share: the communicator belongs to another handle
+	// LPP_PHASES=1: CUDA-event breakdown of the sharded iteration (printed by lpp_destroy)
+	cudaStream_t copy_stream2 = nullptr;
+	cudaEvent_t ev_copy2 = nullptr;
+	const double* packed_vec = nullptr;   // vector whose column-shard copy (ycol on every rank) is already in place
+	int phases = -1;
+	cudaEvent_t pev[8] = {};
+	cudaEvent_t cev[2] = {};      // around the pack on the second stream
+	double pack_ms = 0;
+	double phase_ms[8] = {};
+	long phase_n = 0;
 	// two-layout sharding (product bases without two-spin terms): the up sweep runs on the ROW shard, the down sweep on the
 	// COLUMN shard, linked by two all-to-all transposes per mat-vec (SURVEY §8e alternative A)
 	int two_layout = -1;          // -1 undecided, 0 no, 1 yes
@@ -215,6 +225,14 @@ extern "C" int lpp_destroy(lpp_handle* h)
 {
 	if (!h) return 0;
 	cudaSetDevice(h->device);
+	if (h->phases == 1 && h->phase_n > 0) {
+		static const char* nm[6] = {"up sweep", "wait pack + allreduce1", "down sweep", "finalize + allreduce2",
+		                            "host trip + unpack/axpy/norm", "reduce + allreduce3"};
+		fprintf(stderr, "[lpp phases] rank %d, %ld iterations:", h->desc.rank, h->phase_n);
+		for (int k = 0; k < 6; k++) fprintf(stderr, " %s %.3f ms |", nm[k], h->phase_ms[k] / h->phase_n);
+		fprintf(stderr, " [pack on the second stream %.3f ms]\n", h->pack_ms / h->phase_n);
+		for (int i = 0; i < 8; i++) if (h->pev[i]) cudaEventDestroy(h->pev[i]);
+	}
 	for (void* q : h->ipc_opened) cudaIpcCloseMemHandle(q);
 	if (h->comm && !h->comm_borrowed && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 	if (h->tiled) lpp_tiled_destroy(h->tiled);
@@ -224,6 +242,8 @@ extern "C" int lpp_destroy(lpp_handle* h)
 	if (h->ev1) cudaEventDestroy(h->ev1);
 	for (cudaEvent_t e : {h->ev_pack, h->ev_ycol, h->ev_xcol, h->ev_recv, h->ev_scal}) if (e) cudaEventDestroy(e);
 	if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+	if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
+	if (h->ev_copy2) cudaEventDestroy(h->ev_copy2);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return 0;
@@ -808,6 +828,30 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 	return 0;
 }
 
+static void phase_mark(lpp_handle* h, int k, cudaStream_t s)
+{
+	if (h->phases < 0) {
+		const char* e = getenv("LPP_PHASES");
+		h->phases = (e && e[0] == '1') ? 1 : 0;
+		if (h->phases)
+			for (int i = 0; i < 8; i++) cudaEventCreate(&h->pev[i]);
+		if (h->phases) { cudaEventCreate(&h->cev[0]); cudaEventCreate(&h->cev[1]); }
+	}
+	if (h->phases) cudaEventRecord(h->pev[k], s);
+}
+static void phase_collect(lpp_handle* h, int last)
+{
+	if (h->phases != 1) return;
+	cudaEventSynchronize(h->pev[last]);
+	for (int k = 0; k < last; k++) {
+		float ms = 0;
+		if (cudaEventElapsedTime(&ms, h->pev[k], h->pev[k + 1]) == cudaSuccess) h->phase_ms[k] += ms;
+	}
+	float pm = 0;
+	if (cudaEventElapsedTime(&pm, h->cev[0], h->cev[1]) == cudaSuccess) h->pack_ms += pm;
+	h->phase_n++;
+}
+
 // x = beta x + alpha H y on the ROW shard (x, y: local rows).  Flow (S = compute stream, C = comm stream):
 //   S pack y -> per-peer column blocks | C all-to-all (y: ROW -> COLUMN layout)  ||  S up sweep on the ROW shard
 //   S down sweep + diagonal on the COLUMN shard | C all-to-all (x: COLUMN -> ROW) | S x_row += received blocks
@@ -827,9 +871,35 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		// that the peer only enters once it has finished reading (stream order).
 		// The pack (NVLink stores, no shared memory) runs on the second stream next to the up sweep (L1/shared bound).
 		C = S;
+		phase_mark(h, 0, S);
+		const bool prepacked = h->packed_vec == y;              // the previous fused sweep already stored y into every ycol
+		h->packed_vec = nullptr;
 		CK(cudaEventRecord(h->ev_pack, S));
 		CK(cudaStreamWaitEvent(h->comm_stream, h->ev_pack, 0));
-		lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, h->comm_stream);
+		// The re-layout is G strided 2-D copies on the copy engines (rows x my-columns-for-peer-q blocks straight into the
+		// peers' column shards), so it costs the up sweep no SM time; LPP_PACK_DMA=0 selects the store kernel instead.
+		static const bool pack_dma = !(getenv("LPP_PACK_DMA") && getenv("LPP_PACK_DMA")[0] == '0');
+		if (h->phases == 1) cudaEventRecord(h->cev[0], h->comm_stream);
+		if (prepacked) {
+			// nothing to move
+		} else if (pack_dma) {
+			if (!h->copy_stream2) {
+				CK(cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking));
+				CK(cudaEventCreateWithFlags(&h->ev_copy2, cudaEventDisableTiming));
+			}
+			CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_pack, 0));
+			for (int q = 0; q < G; q++) {
+				const int qq = (me + q) % G;                     // the local block goes to its own stream (another copy engine)
+				const uint64_t ncq = h->cols.cs[qq + 1] - h->cols.cs[qq];
+				CK(cudaMemcpy2DAsync(h->peer_ycol.p[qq] + d0loc * ncq, ncq * sizeof(double), y + h->cols.cs[qq], n1 * sizeof(double),
+				                     ncq * sizeof(double), nrows, cudaMemcpyDefault, (q == 0) ? h->copy_stream2 : h->comm_stream));
+			}
+			CK(cudaEventRecord(h->ev_copy2, h->copy_stream2));
+			CK(cudaStreamWaitEvent(h->comm_stream, h->ev_copy2, 0));
+		} else {
+			lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, h->comm_stream);
+		}
+		if (h->phases == 1) cudaEventRecord(h->cev[1], h->comm_stream);
 		CK(cudaEventRecord(h->ev_ycol, h->comm_stream));
 		const int nbB = lpp_tiled_up_rows_blocks(h->tiled, nrows);
 		CKR(ensure_partials(h, std::max(nbB, lpp_vec_blocks(h->nloc))));
@@ -837,18 +907,22 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		ab.alpha = alpha; ab.beta = beta; ab.x = x; ab.y = y; ab.row0 = 0; ab.nloc = h->nloc;
 		ab.dot_partials = want_dot ? h->partials : nullptr;
 		if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nrows, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+		phase_mark(h, 1, S);                                    // 0->1 up sweep
 		CK(cudaStreamWaitEvent(S, h->ev_ycol, 0));
 		CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
+		phase_mark(h, 2, S);                                    // 1->2 wait for the pack + all-reduce #1
 		SpmvArgs aa;
 		aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
 		aa.dot_partials = want_dot ? h->partials2 : nullptr;
 		if (lpp_tiled_sweep_down_cols(h->tiled, h->md, h->dn, h->dt, aa, h->ucol0, ncme, S) < 0)
 			return fail(LPP_ERR_CUDA, lpp_tiled_error());
+		phase_mark(h, 3, S);                                    // 2->3 down sweep
 		if (want_dot) {
 			lpp_launch_finalize_sum(h->partials, nbB, h->scal_dev, S);
 			lpp_launch_finalize_sum(h->partials2, h->partials2_cap, h->scal_dev + 1, S);
 		}
 		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 2, kNcclFloat64, kNcclSum, h->comm, S));
+		phase_mark(h, 4, S);                                    // 3->4 finalize + all-reduce #2
 		if (want_dot) CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, S));
 		// defer_unpack: the caller folds the re-layout of the column-shard result into its next pass over x
 		if (!defer_unpack) lpp_launch_unpack_add_p2p(x, h->peer_xcol, nrows, n1, h->cols, d0loc, S);
@@ -976,15 +1050,22 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 		int npb = np;
 		if (fuse_unpack) {
 			const uint64_t n1 = h->md.n1, nrows = h->nloc / n1;
-			npb = lpp_unpack_axpy_norm_blocks(nrows, n1);
+			npb = lpp_unpack_axpy_norm_blocks(nrows, n1, h->desc.nranks);
 			CKR(ensure_partials(h, npb));
-			lpp_launch_unpack_axpy_norm_p2p(x, y, aj / nj, h->peer_xcol, nrows, n1, h->cols, h->row0 / n1, h->partials, h->stream);
+			// LPP_FUSE_PACK=1 also stores the new vector into the peers' column shards from this kernel (the next pack);
+			// measured slower on 2 x B200 (1.71 ms against 0.70 + 0.59 ms for the separate kernels), so it is off by default.
+			static const bool fuse_pack = getenv("LPP_FUSE_PACK") && getenv("LPP_FUSE_PACK")[0] == '1';
+			lpp_launch_unpack_axpy_norm_p2p(x, y, aj / nj, h->peer_xcol, fuse_pack ? &h->peer_ycol : nullptr, nrows, n1, h->cols,
+			                                h->row0 / n1, h->partials, h->stream);
+			if (fuse_pack) h->packed_vec = x;                   // x is the next Lanczos vector (becomes y after the swap)
 		} else {
 			lpp_launch_axpy_norm(x, y, aj / nj, n, h->partials, h->stream);
 		}
 		h->launches += 1;
+		if (fuse_unpack) phase_mark(h, 5, h->stream);            // 4->5 host round trip + fused unpack/axpy/norm
 		double b2 = 0;
 		CKR(reduce_scalar(h, npb, &b2));
+		if (fuse_unpack) { phase_mark(h, 6, h->stream); phase_collect(h, 6); }   // 5->6 reduce + all-reduce #3
 		double bj = sqrt(b2);
 		a[j] = aj;
 		b[j] = bj;

@@ -625,9 +625,12 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__
 
 // x <- x + (peers' column-shard results) - coef * y ;  partials <- block sums of x_new^2.
 // The re-layout of the down-sweep result and the Lanczos "x -= a y, b^2 = |x|^2" sweep in one pass over the row shard.
+// PACK also stores the new vector into the owners' column shards (the pack of the NEXT mat-vec; opt-in, it measured slower).
+// (A variant with one owner per block and 16-byte accesses measured 0.84-0.93 ms against 0.70 ms for this one on 2 x B200.)
+template <bool PACK>
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                                 PeerPtrs xcols, uint64_t nrows, uint64_t n1, ColSplit c,
-                                                                 uint64_t d0loc, double* __restrict__ partials)
+                                                                 PeerPtrs xcols, PeerPtrs ycols, uint64_t nrows, uint64_t n1,
+                                                                 ColSplit c, uint64_t d0loc, double* __restrict__ partials)
 {
 	const uint64_t r = blockIdx.y;
 	double* __restrict__ xrow = x + r * n1;
@@ -638,6 +641,7 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
 		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
 		const double v = xrow[u] + xcols.p[q][(d0loc + r) * nc + cu] - coef * yrow[u];
 		xrow[u] = v;
+		if (PACK) ycols.p[q][(d0loc + r) * nc + cu] = v;
 		s += v * v;
 	}
 	s = lpp_block_sum(s);
@@ -661,15 +665,20 @@ void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows,
 	k_unpack_add_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(x, xcols, nrows, n1, c, d0loc);
 }
 
-int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1)
+int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1, int nranks)
 {
+	(void)nranks;
 	dim3 g = lpp_rowwise_grid(nrows, n1);
 	return (int)(g.x * g.y);
 }
-void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1,
-                                     const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s)
+void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, const PeerPtrs* ycols_or_null,
+                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s)
 {
-	k_unpack_axpy_norm_p2p<<<lpp_rowwise_grid(nrows, n1), LPP_TPB, 0, s>>>(x, y, coef, xcols, nrows, n1, c, d0loc, partials);
+	PeerPtrs yc;
+	for (int i = 0; i < LPP_MAX_RANKS; i++) yc.p[i] = ycols_or_null ? ycols_or_null->p[i] : nullptr;
+	const dim3 g = lpp_rowwise_grid(nrows, n1);
+	if (ycols_or_null) k_unpack_axpy_norm_p2p<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, xcols, yc, nrows, n1, c, d0loc, partials);
+	else k_unpack_axpy_norm_p2p<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, xcols, yc, nrows, n1, c, d0loc, partials);
 }
 
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,

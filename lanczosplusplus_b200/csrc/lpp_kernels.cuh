@@ -86,9 +86,9 @@ void lpp_launch_pack_cols_p2p(const double* src, const PeerPtrs& ycols, uint64_t
                               uint64_t d0loc, cudaStream_t s);
 void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc,
                                cudaStream_t s);
-int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1);
-void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, uint64_t nrows, uint64_t n1,
-                                     const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s);
+int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1, int nranks);
+void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, const PeerPtrs* ycols_or_null,
+                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s);
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,
                           uint64_t d0loc, cudaStream_t s);
 void lpp_launch_unpack_add(double* x, const double* recvbuf, const double* xcol, uint64_t nrows, uint64_t n1, const ColSplit& c,
