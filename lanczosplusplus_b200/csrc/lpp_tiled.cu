@@ -60,6 +60,9 @@ struct TiledPlan {
 	uint32_t* tilesA = nullptr;   // (block, panel) pairs intersecting the local rows: block ids only, panel-major grid
 	uint32_t ntilesA_blocks = 0, npanels = 0;
 	int has_twospin = 0;
+	uint32_t* ts_up = nullptr;    // two-spin tables [site][state] (two orbitals), see k_sweep_twospin_tab
+	uint32_t* ts_dn = nullptr;
+	double u2half = 0, u3 = 0;
 	int dot_blocks = 0;
 	std::vector<void*> allocs;
 	size_t sched_holes = 0, sched_real = 0;
@@ -72,7 +75,7 @@ struct TiledPlan {
 	void* tabP = nullptr;         // packed up table [chunk][group of 4 slots][lane] (k_sweep_up_packed)
 	uint32_t* choffP = nullptr;   // first group of every chunk
 	uint8_t* wcnt4P = nullptr;    // slots per chunk, multiple of 4
-	int packedE16 = 0, packedB = 0;
+	int packedE16 = 0, packedB = 0, packedNG = 8;
 	size_t smemBP = 0;
 	double packed_mean_slots = 0;
 	int leanA = 1, leanB = 0;
@@ -663,9 +666,10 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 // sweep B packed: the lean kernel with (1) a per-warp slot count (a warp's 32 consecutive states execute only the slots
 // they need, rounded to 4: 24 on average instead of 32 on the 4x4 lattice) and (2) the table stored per warp chunk as
 // [chunk][group of 4 slots][lane], so the 4 entries of a group are one coalesced 8-byte (E16: 2-byte entries
-// [15] sign | [13:0] tile position, single hop magnitude) or 16-byte (4-byte lean entries) load per lane.
-template <int R, bool UNI, bool E16, int N4>
-__device__ __forceinline__ void up_packed_gather(const typename std::conditional<E16, uint2, uint4>::type (&ec)[8], const MagTable& mt,
+// [15] sign | [14] magnitude index | [13:0] tile position, at most two hop magnitudes) or 16-byte (4-byte lean entries)
+// load per lane.  NG = groups a state can have: 8 (32 slots) or, with 2-byte entries, 12 (48 slots: FeAs with orbital hoppings).
+template <int R, bool UNI, bool E16, int NG, int N4>
+__device__ __forceinline__ void up_packed_gather(const typename std::conditional<E16, uint2, uint4>::type (&ec)[NG], const MagTable& mt,
                                                  uint32_t ys_s, double (&acc)[R])
 {
 #pragma unroll
@@ -677,7 +681,7 @@ __device__ __forceinline__ void up_packed_gather(const typename std::conditional
 			off[1] = ((w0 >> 16) & 0x3fffu) * (8u * R); sg[1] = w0;
 			off[2] = (w1 & 0x3fffu) * (8u * R); sg[2] = w1 << 16;
 			off[3] = ((w1 >> 16) & 0x3fffu) * (8u * R); sg[3] = w1;
-			mi[0] = mi[1] = mi[2] = mi[3] = 0;
+			mi[0] = (w0 >> 14) & 1u; mi[1] = (w0 >> 30) & 1u; mi[2] = (w1 >> 14) & 1u; mi[3] = (w1 >> 30) & 1u;
 		} else {
 			const uint32_t w[4] = {ec[g].x, ec[g].y, ec[g].z, ec[g].w};
 #pragma unroll
@@ -706,7 +710,7 @@ __device__ __forceinline__ void up_packed_gather(const typename std::conditional
 	}
 }
 
-template <int R, bool UNI, bool E16>
+template <int R, bool UNI, bool E16, int NG>
 __global__ void __launch_bounds__(UPP_THREADS, 1)
 k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __restrict__ choff, const uint8_t* __restrict__ wcnt4,
                   uint32_t bsize, MagTable mt, SpmvArgs a, uint64_t d0, uint64_t dcount, int want_dot)
@@ -749,7 +753,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 	}
 	__syncthreads();
 
-	VT en[8];
+	VT en[NG];
 	double xn_old[R];
 	const bool need_x = a.beta != 0.0;
 	const uint32_t lane = threadIdx.x & 31;
@@ -758,7 +762,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 		const int pc = (int)s_wcnt[c];
 		const VT* __restrict__ base = reinterpret_cast<const VT*>(tabP) + (size_t)s_choff[c] * 32 + lane;
 #pragma unroll
-		for (int g = 0; g < 8; g++)
+		for (int g = 0; g < NG; g++)
 			if (4 * g < pc) en[g] = __ldg(base + g * 32);
 #pragma unroll
 		for (int r = 0; r < R; r++) xn_old[r] = (live[r] && need_x) ? xrow[r][ii] : 0.0;
@@ -771,11 +775,11 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 	const double t0 = mt.mag[0];
 	double contrib = 0.0;
 	for (; i < bsize; i += UPP_THREADS) {
-		VT ec[8];
+		VT ec[NG];
 		double xold[R];
 		const int cnt = (int)s_wcnt[i >> 5];
 #pragma unroll
-		for (int g = 0; g < 8; g++) ec[g] = en[g];
+		for (int g = 0; g < NG; g++) ec[g] = en[g];
 #pragma unroll
 		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
 		if (i + UPP_THREADS < bsize) prefetch(i + UPP_THREADS);
@@ -783,15 +787,12 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = 0.0;
 		switch (cnt >> 2) {                                // warp-uniform: branch-free runs of 4*N independent gathers
+#define LPP_UPP_CASE(N_) case N_: up_packed_gather<R, UNI, E16, NG, (N_ <= NG ? N_ : NG)>(ec, mt, ys_s, acc); break;
 		case 0: break;
-		case 1: up_packed_gather<R, UNI, E16, 1>(ec, mt, ys_s, acc); break;
-		case 2: up_packed_gather<R, UNI, E16, 2>(ec, mt, ys_s, acc); break;
-		case 3: up_packed_gather<R, UNI, E16, 3>(ec, mt, ys_s, acc); break;
-		case 4: up_packed_gather<R, UNI, E16, 4>(ec, mt, ys_s, acc); break;
-		case 5: up_packed_gather<R, UNI, E16, 5>(ec, mt, ys_s, acc); break;
-		case 6: up_packed_gather<R, UNI, E16, 6>(ec, mt, ys_s, acc); break;
-		case 7: up_packed_gather<R, UNI, E16, 7>(ec, mt, ys_s, acc); break;
-		default: up_packed_gather<R, UNI, E16, 8>(ec, mt, ys_s, acc); break;
+			LPP_UPP_CASE(1) LPP_UPP_CASE(2) LPP_UPP_CASE(3) LPP_UPP_CASE(4) LPP_UPP_CASE(5) LPP_UPP_CASE(6) LPP_UPP_CASE(7)
+			LPP_UPP_CASE(8) LPP_UPP_CASE(9) LPP_UPP_CASE(10) LPP_UPP_CASE(11)
+#undef LPP_UPP_CASE
+		default: up_packed_gather<R, UNI, E16, NG, NG>(ec, mt, ys_s, acc); break;
 		}
 #pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -1043,6 +1044,65 @@ __global__ void __launch_bounds__(256) k_sweep_twospin(ModelDev m, SpmvArgs a)
 	}
 }
 
+// sweep C from per-spin tables (two orbitals): entry of (site i, one-spin state s) =
+//   [27] sign of doSign(s, i, 1, i, 0) | [26] sign of doSign(s, i, 0, i, 1) | [25] orbital holding the electron | [24] site i
+//   holds exactly one electron of this species | [23:0] index of the state with that electron in the other orbital.
+// FeBasedSc.h:376-432,678-713 (setU2OffDiagonalTerm / setU3Term): with the up electron in orbital orb2 and orb1 = 1 - orb2,
+// the down electron in orb1 gives the U2 spin exchange (U[2]/2), in orb2 the U3 pair hop (-U[3]; OTF literal: orb2 > orb1 only).
+#define TS_VALID 0x01000000u
+#define TS_ROWS 8              // down states per CTA: the up-table entries of a thread are loaded once for all of them
+__global__ void __launch_bounds__(256) k_sweep_twospin_tab(ModelDev m, const uint32_t* __restrict__ tu, const uint32_t* __restrict__ td,
+                                                          double u2half, double u3, int all_pairs, SpmvArgs a, uint64_t dcount)
+{
+	__shared__ uint32_t tds[TS_ROWS][32];
+	const uint64_t n1 = m.n1;
+	const uint64_t dl0 = (uint64_t)blockIdx.y * TS_ROWS, d0 = a.row0 / n1;
+	for (int q = threadIdx.x; q < TS_ROWS * m.nsite; q += 256) {
+		const int r = q / m.nsite, i = q % m.nsite;
+		tds[r][i] = (dl0 + r < dcount) ? td[(uint64_t)i * m.n2 + d0 + dl0 + r] : 0u;
+	}
+	__syncthreads();
+	const uint64_t u = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+	double contrib = 0.0;
+	if (u < n1) {
+		double acc[TS_ROWS];
+#pragma unroll
+		for (int r = 0; r < TS_ROWS; r++) acc[r] = 0.0;
+		for (int i = 0; i < m.nsite; i++) {
+			const uint32_t eu = __ldg(tu + (uint64_t)i * n1 + u);
+			if (!(eu & TS_VALID)) continue;
+			const uint32_t ou = (eu >> 25) & 1u;
+			// orb1 = 1 - ou: doSign(., i, orb1, i, orb2) is the (0,1) sign when orb1 = 0, the (1,0) sign otherwise
+			const uint32_t su = (ou ? (eu >> 26) : (eu >> 27)) & 1u;
+			const double* __restrict__ ycol = a.y + (eu & 0xffffffu);
+#pragma unroll
+			for (int r = 0; r < TS_ROWS; r++) {
+				const uint32_t ed = tds[r][i];
+				if (!(ed & TS_VALID)) continue;
+				const uint32_t od = (ed >> 25) & 1u;
+				double coef;
+				if (od != ou) coef = u2half;
+				else if (all_pairs || ou == 1u) coef = -u3;
+				else continue;
+				const uint32_t neg = (su ^ (ou ? (ed >> 26) : (ed >> 27))) & 1u;
+				acc[r] += (neg ? -coef : coef) * ycol[(uint64_t)(ed & 0xffffffu) * n1];
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < TS_ROWS; r++) {
+			if (dl0 + r >= dcount) continue;
+			const uint64_t t = (dl0 + r) * n1 + u;
+			const double xn = a.x[t] + a.alpha * acc[r];
+			a.x[t] = xn;
+			contrib += a.y[a.row0 + t] * xn;
+		}
+	}
+	if (a.dot_partials) {
+		double s = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+	}
+}
+
 // =====================================================================================================
 // plan construction
 // =====================================================================================================
@@ -1209,7 +1269,8 @@ static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::
 		if (plan_upload(p, &p->wcntL, wc)) return -1;
 		p->widthL = WL;
 		// packed layout for k_sweep_up_packed: [chunk][group of 4 slots][lane]
-		if (WL <= 32) {
+		const bool e16ok = p->mt.nmag <= 2 && (size_t)bsize + G < (1u << 14);
+		if (WL <= 32 || (WL <= 48 && e16ok)) {
 			const uint32_t nch = (bsize + 31) / 32;
 			std::vector<uint8_t> wc4(nch);
 			std::vector<uint32_t> choff(nch + 1, 0);
@@ -1217,7 +1278,7 @@ static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::
 				wc4[c] = (uint8_t)((wc[c] + 3) & ~3);
 				choff[c + 1] = choff[c] + wc4[c] / 4;
 			}
-			const bool e16 = p->mt.nmag == 1 && (size_t)bsize + G < (1u << 14);
+			const bool e16 = e16ok;
 			const uint32_t hole0 = bsize * (uint32_t)(8 * R);      // zero slot 0 (states past the end of the last chunk)
 			std::vector<uint32_t> pk32;
 			std::vector<uint16_t> pk16;
@@ -1228,9 +1289,9 @@ static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::
 					for (uint32_t l = 0; l < 32; l++)
 						for (uint32_t k = 0; k < 4; k++) {
 							const uint32_t u = c * 32 + l, sidx = 4 * g + k;
-							const uint32_t e = (u < bsize) ? lean[(size_t)sidx * n + u] : hole0;
+							const uint32_t e = (u < bsize && sidx < (uint32_t)WL) ? lean[(size_t)sidx * n + u] : hole0;
 							const size_t at = (((size_t)choff[c] + g) * 32 + l) * 4 + k;
-							if (e16) pk16[at] = (uint16_t)(((e & TE_IDX) / (uint32_t)(8 * R)) | ((e & TE_SIGN) ? 0x8000u : 0u));
+							if (e16) pk16[at] = (uint16_t)(((e & TE_IDX) / (uint32_t)(8 * R)) | ((e & TE_SIGN) ? 0x8000u : 0u) | (((e >> 24) & 1u) << 14));
 							else pk32[at] = e;
 						}
 			if (e16) { uint16_t* d = nullptr; if (plan_upload(p, &d, pk16)) return -1; p->tabP = d; }
@@ -1239,6 +1300,7 @@ static int schedule_conflict_free(TiledPlan* p, SpinPlan* sp, int G, const std::
 			if (plan_upload(p, &p->wcnt4P, wc4)) return -1;
 			p->packedE16 = e16 ? 1 : 0;
 			p->packed_mean_slots = 4.0 * choff[nch] / std::max<uint32_t>(nch, 1);
+			p->packedNG = (WL <= 32) ? 8 : 12;
 		}
 	}
 	uint32_t* dtab = nullptr;
@@ -1414,11 +1476,11 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		if (p->leanB) { SETL(1, true); SETL(1, false); SETL(2, true); SETL(2, false); }
 #undef SETL
 		const char* envp = getenv("LPP_TILED_PACKED");
-		p->packedB = p->leanB && p->tabP != nullptr && !(envp && envp[0] == '0');
-		p->smemBP = p->smemBL + ((size_t)(m.n1 + 31) / 32) * 5 + 16;
-		if (p->smemBP + 1024 > (size_t)maxsm) p->packedB = 0;
-#define SETP(R_, U_, E_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_packed<R_, U_, E_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBP)
-		if (p->packedB) { SETP(1, true, true); SETP(1, true, false); SETP(1, false, false); SETP(2, true, true); SETP(2, true, false); SETP(2, false, false); }
+		p->smemBP = ((size_t)m.n1 + 16 / p->R) * p->R * 8 + ((size_t)(m.n1 + 31) / 32) * 5 + 16;
+		p->packedB = p->v2 && p->R == 2 && p->up.nblocks == 1 && p->tabP != nullptr && !(envp && envp[0] == '0') && (lean & 2) &&
+		             p->smemBP + 1024 <= (size_t)maxsm;
+#define SETP(U_, E_, NG_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_packed<2, U_, E_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBP)
+		if (p->packedB) { SETP(true, true, 8); SETP(false, true, 8); SETP(true, true, 12); SETP(false, true, 12); SETP(true, false, 8); SETP(false, false, 8); }
 #undef SETP
 		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
 	}
@@ -1437,9 +1499,38 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		fprintf(stderr, "[lpp tiled] v2=%d blocksA=%d TA=%d W=%d R=%d pipeB=%d NE=%d dn: blocks=%d max=%u width=%d | up: blocks=%d max=%u width=%d sched real=%zu holes=%zu\n",
 		        p->v2, p->blocksA, p->threadsA, p->W, p->R, p->pipeB, p->NE, p->dn.nblocks, p->dn.max_block, p->dn.width, p->up.nblocks, p->up.max_block,
 		        p->up.width, p->sched_real, p->sched_holes);
+	if (p->has_twospin && m.orbitals == 2 && m.nsite <= 32 && m.n1 < (1u << 24) && m.n2 < (1u << 24) && p->dcount <= 65535ull * TS_ROWS && !(getenv("LPP_TWOSPIN_TAB") && getenv("LPP_TWOSPIN_TAB")[0] == '0')) {
+		for (int spin = 0; spin < 2; spin++) {
+			const uint64_t n = spin ? m.n2 : m.n1;
+			std::vector<word_t> w(n);
+			if (cudaMemcpy(w.data(), spin ? m.b2 : m.b1, sizeof(word_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { g_terr = "basis download failed"; delete p; return -1; }
+			std::vector<std::pair<word_t, uint32_t>> byword(n);
+			for (uint64_t i = 0; i < n; i++) byword[i] = {w[i], (uint32_t)i};
+			std::sort(byword.begin(), byword.end());
+			std::vector<uint32_t> tab((size_t)m.nsite * n, 0u);
+			for (int site = 0; site < m.nsite; site++)
+				for (uint64_t i = 0; i < n; i++) {
+					const int o0 = lpp_feas_occ(w[i], site, 0, 2), o1 = lpp_feas_occ(w[i], site, 1, 2);
+					if (o0 + o1 != 1) continue;
+					const word_t partner = w[i] ^ (lpp_bit(site * 2) | lpp_bit(site * 2 + 1));
+					auto it = std::lower_bound(byword.begin(), byword.end(), std::make_pair(partner, (uint32_t)0));
+					if (it == byword.end() || it->first != partner) { g_terr = "two-spin table: partner state not in the basis"; delete p; return -1; }
+					uint32_t e = it->second | TS_VALID | (o1 ? (1u << 25) : 0u);
+					if (lpp_feas_dosign(w[i], site, 0, site, 1, 2) < 0) e |= 1u << 26;
+					if (lpp_feas_dosign(w[i], site, 1, site, 0, 2) < 0) e |= 1u << 27;
+					tab[(size_t)site * n + i] = e;
+				}
+			if (plan_upload(p, spin ? &p->ts_dn : &p->ts_up, tab)) { delete p; return -1; }
+		}
+		double Uh[4] = {0, 0, 0, 0};
+		if (cudaMemcpy(Uh, m.U, sizeof(double) * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { g_terr = "U download failed"; delete p; return -1; }
+		p->u2half = 0.5 * Uh[2];
+		p->u3 = Uh[3];
+	}
 	// the last sweep owns the dot-product partial sums
-	if (p->has_twospin) p->dot_blocks = (int)((nloc + 255) / 256);
-	else if (p->v2 && p->leanB) p->dot_blocks = (int)((p->dcount + p->R - 1) / p->R);
+	if (p->has_twospin && p->ts_up) p->dot_blocks = (int)(((m.n1 + 255) / 256) * ((p->dcount + TS_ROWS - 1) / TS_ROWS));
+	else if (p->has_twospin) p->dot_blocks = (int)((nloc + 255) / 256);
+	else if (p->v2 && (p->leanB || p->packedB)) p->dot_blocks = (int)((p->dcount + p->R - 1) / p->R);
 	else if (p->v2) p->dot_blocks = (int)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
 	else if (p->up_in_smem) p->dot_blocks = (int)p->dcount;
 	else p->dot_blocks = (int)(((m.n1 + 255) / 256) * p->dcount);
@@ -1502,16 +1593,18 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 		k_sweep_down<<<(unsigned)nblkA, PA_COLS, 0, s>>>(m, dn, dt, a, p->d0, p->dcount, p->nrowchunks);
 	}
 	launches++;
-	if (p->v2 && p->leanB) {
+	if (p->v2 && (p->leanB || p->packedB)) {
 		const unsigned gridL = (unsigned)((p->dcount + p->R - 1) / p->R);
 		const uint32_t bsz = (uint32_t)m.n1;
 		SpmvArgs ab = a;
 		ab.beta = 1.0;                                  // sweep A already applied beta
 #define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
-#define RUNP(R_, U_, E_) k_sweep_up_packed<R_, U_, E_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
+#define RUNP(U_, E_, NG_) k_sweep_up_packed<2, U_, E_, NG_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, ab, p->d0, p->dcount, dot_in_b)
 		if (p->packedB) {
-			if (p->R == 2) { if (p->packedE16) RUNP(2, true, true); else if (p->mt.nmag == 1) RUNP(2, true, false); else RUNP(2, false, false); }
-			else { if (p->packedE16) RUNP(1, true, true); else if (p->mt.nmag == 1) RUNP(1, true, false); else RUNP(1, false, false); }
+			const bool uni = p->mt.nmag == 1;
+			if (p->packedE16 && p->packedNG == 12) { if (uni) RUNP(true, true, 12); else RUNP(false, true, 12); }
+			else if (p->packedE16) { if (uni) RUNP(true, true, 8); else RUNP(false, true, 8); }
+			else { if (uni) RUNP(true, false, 8); else RUNP(false, false, 8); }
 		} else if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
 		else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
 #undef RUNP
@@ -1532,7 +1625,12 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 		k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
 	}
 	launches++;
-	if (p->has_twospin) {
+	if (p->has_twospin && p->ts_up) {
+		// m.U lives on the device; the two couplings were read once at plan creation
+		const dim3 g((unsigned)((m.n1 + 255) / 256), (unsigned)((p->dcount + TS_ROWS - 1) / TS_ROWS), 1);
+		k_sweep_twospin_tab<<<g, 256, 0, s>>>(m, p->ts_up, p->ts_dn, p->u2half, p->u3, m.u3_all_pairs, a, p->dcount);
+		launches++;
+	} else if (p->has_twospin) {
 		k_sweep_twospin<<<(unsigned)((a.nloc + 255) / 256), 256, 0, s>>>(m, a);
 		launches++;
 	}
@@ -1545,7 +1643,7 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 // two-layout multi-GPU entry points: the up sweep runs on the rank's ROW shard (all up states, local down range),
 // the down sweep (+ diagonal) on the rank's COLUMN shard (all down states, local up range).
 // ---------------------------------------------------------------------------------------------------------------
-int lpp_tiled_two_layout_ok(const TiledPlan* p) { return (p->v2 && p->leanB && !p->has_twospin) ? 1 : 0; }
+int lpp_tiled_two_layout_ok(const TiledPlan* p) { return (p->v2 && (p->leanB || p->packedB) && !p->has_twospin) ? 1 : 0; }
 
 int lpp_tiled_up_rows_blocks(const TiledPlan* p, uint64_t nrows) { return (int)((nrows + p->R - 1) / p->R); }
 
@@ -1556,10 +1654,12 @@ int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, 
 	const uint32_t bsz = (uint32_t)m.n1;
 	const int want_dot = a.dot_partials ? 1 : 0;
 #define RUNL(R_, U_) k_sweep_up_lean<R_, 32, U_><<<gridL, PBP_THREADS, p->smemBL, s>>>(m, p->tabL, p->wcntL, 0u, bsz, p->mt, a, 0, nrows, want_dot)
-#define RUNP(R_, U_, E_) k_sweep_up_packed<R_, U_, E_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, a, 0, nrows, want_dot)
+#define RUNP(U_, E_, NG_) k_sweep_up_packed<2, U_, E_, NG_><<<gridL, UPP_THREADS, p->smemBP, s>>>(m, p->tabP, p->choffP, p->wcnt4P, bsz, p->mt, a, 0, nrows, want_dot)
 	if (p->packedB) {
-		if (p->R == 2) { if (p->packedE16) RUNP(2, true, true); else if (p->mt.nmag == 1) RUNP(2, true, false); else RUNP(2, false, false); }
-		else { if (p->packedE16) RUNP(1, true, true); else if (p->mt.nmag == 1) RUNP(1, true, false); else RUNP(1, false, false); }
+		const bool uni = p->mt.nmag == 1;
+		if (p->packedE16 && p->packedNG == 12) { if (uni) RUNP(true, true, 12); else RUNP(false, true, 12); }
+		else if (p->packedE16) { if (uni) RUNP(true, true, 8); else RUNP(false, true, 8); }
+		else { if (uni) RUNP(true, false, 8); else RUNP(false, false, 8); }
 	} else if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
 	else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
 #undef RUNP
