@@ -262,3 +262,49 @@ def test_large_up_basis_c5_structure(lpp, oracle):
     en, _, a, b = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=300, eps=1e-12)).computeOneState(None, want_vector=False)
     assert abs(en - eref) <= 1e-9 * abs(eref)
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# against the golden fixtures of the reference's own model code (tests/golden/*.npz, tools/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(cases.SMALL_CASES))
+def test_engine_matches_reference_fixture(lpp, name):
+    from tests import golden_util as gu
+    case = cases.SMALL_CASES[name]
+    g = gu.load(name, case)
+    # feas_u3_all_pairs=0: the literal on-the-fly loop of FeBasedSc.h:85-88, which is what the fixture's x_otf holds
+    e = cases.make_engine(lpp, dict(case, feas_u3_all_pairs=0))
+    assert e.rows() == int(g["rows"])
+    assert np.array_equal(e.basis(0), g["up_words"])                      # bit-exact, built on device
+    assert np.array_equal(e.perfectIndex(0, g["up_words"]), np.arange(len(g["up_words"]), dtype=np.uint64))
+    if case["model"] != cases.HEISENBERG:
+        assert np.array_equal(e.basis(1), g["dn_words"])
+        assert np.array_equal(e.perfectIndex(1, g["dn_words"]), np.arange(len(g["dn_words"]), dtype=np.uint64))
+    rp, ci, v = e.setupHamiltonian()
+    gu.check_crs(g, rp, ci, v)                                            # rowptr / colind bit-exact, values <= 1e-14
+    y = geo.splitmix64_vector(e.rows(), gu.Y_SEED)
+    for k in kernels_for(lpp, case):
+        x = np.zeros(e.rows())
+        e.matrixVectorProduct(x, y, kernel=k)
+        ref = g["x_stored"] if (k == lpp.KERNEL_STORED or "x_otf" not in g.files) else g["x_otf"]
+        assert relerr(x, ref) <= 1e-13, (name, k)
+    e.close()
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(cases.SMALL_CASES) if cases.SMALL_CASES[n]["model"] == cases.HUBBARD])
+def test_apply_op_matches_reference_fixture(lpp, name):
+    """accModifiedState_ on the device against the reference's getBraIndex / doSignGf results (both spins, c and cdagger)."""
+    from tests import golden_util as gu
+    case = cases.SMALL_CASES[name]
+    g = gu.load(name, case)
+    e = cases.make_engine(lpp, case)
+    e.set_groundstate(geo.splitmix64_vector(e.rows(), gu.SRC_SEED))
+    seen = 0
+    for rec in gu.ops(g):
+        dst = e.sector(rec["nup"], rec["ndown"])
+        e.apply_op(dst, rec["op"], rec["site"], rec["spin"], 1.0, accumulate=False)
+        assert np.array_equal(dst.get_vector(1), g[rec["key"]]), rec      # +-source elements: exact
+        dst.close()
+        seen += 1
+    assert seen >= 8
+    e.close()
