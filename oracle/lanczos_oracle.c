@@ -9,12 +9,16 @@
  * reference legs may load this library.  The product (lanczosplusplus_b200/)
  * never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors / expected outputs
- * (TestSuite/ holds inputs only) and cannot be compiled here because PsimagLite
- * (g1257/PsimagLite, un-vendored, un-pinned; README.md:80-82) is absent.  The
- * oracle is pinned instead on analytic answers, on dense/sparse eigen-solvers
- * from numpy/scipy applied to the CRS it exports, and on the survey-time
- * cross-check values (tests/test_oracle.py).
+ * PINNING.  The reference ships no golden vectors (TestSuite/ holds inputs only) and its executables cannot be built here
+ * (PsimagLite -- g1257/PsimagLite, un-vendored, un-pinned; README.md:80-82 -- and LAPACK are absent).  Two pins:
+ *  (1) MODEL CODE: PINNED.  The reference's own model headers (bases, ranks, signs, row generators, diagonal, stored
+ *      assembly, on-the-fly product, getBraIndex/doSignGf) are compiled unmodified against oracle/psimag_shim/ into
+ *      oracle/_ref/liblpp_ref.so (ref_bridge.cpp).  This restatement reproduces them exactly: basis words, ranks, rowptr,
+ *      colind bit-exact, CRS values and operator applications identical, x += H y to 1e-14 (tests/test_reference_pin.py,
+ *      and tests/test_golden.py against the committed outputs under tests/golden/).
+ *  (2) PSIMAGLITE PARTS: PARITY UNPINNED.  SparseRow's sort-and-merge, CrsMatrix, LanczosSolver and ContinuedFraction are
+ *      external and absent; they are restated from SURVEY App. B and pinned only on analytic answers, numpy/scipy
+ *      eigen-solvers applied to the exported CRS and the survey-time cross-check values (tests/test_oracle.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference/src).  PsimagLite pieces (SparseRow, CrsMatrix, LanczosSolver,

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs.  The product package never imports this module.
-PARITY UNPINNED by reference golden vectors (none exist; see lanczos_oracle.c header).
+Model code pinned by the reference's own headers (oracle/reference.py, tests/golden/); the PsimagLite solver parts
+stay PARITY UNPINNED (see the lanczos_oracle.c header).
 """
 import ctypes as C
 import os

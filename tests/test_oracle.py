@@ -1,4 +1,5 @@
-"""Pins for the CPU oracle (PARITY UNPINNED by reference fixtures: the reference ships none).
+"""Independent pins for the CPU oracle: energies and spectra (the PsimagLite solver parts have no reference fixture -- PARITY
+UNPINNED there; the model code is pinned by tests/test_golden.py and tests/test_reference_pin.py).
 
 Pins used instead: analytic energies, dense/sparse eigensolvers on the exported CRS, and the survey-time
 independent restatement values of SURVEY App. E / BASELINE.md §2.
