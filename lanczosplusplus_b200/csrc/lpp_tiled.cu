@@ -79,6 +79,15 @@ struct TiledPlan {
 	size_t smemBP = 0;
 	double packed_mean_slots = 0;
 	int leanA = 1, leanB = 0;
+	// staged down sweep (k_sweep_down_staged): runs of consecutive down states that share their high sites
+	uint32_t* stTab = nullptr;    // [n2][stWidth] entries, in-run sources first (run-local row), then the others (global row)
+	uint16_t* stCnt = nullptr;    // [n2] in-run count | other count << 8
+	uint32_t* stOff = nullptr;    // [stNblk + 1] first down state of every run
+	std::vector<uint32_t> stOff_host;
+	uint32_t stNblk = 0, stMaxRows = 0;
+	int stWidth = 0, stagedA = 0, stPC = 64, stSplit = 0, stNR = 2;
+	size_t smemST = 0;
+	double stInternal = 0;
 	DownRowsPlan* drows = nullptr;   // row-walking sweep A (k_sweep_down_rows, lpp_dtile.cu); nullptr: streaming kernel
 	DownTilePlan* dtile = nullptr;   // shared-memory tile kernel for sweep A (lpp_dtile.cu, opt-in); nullptr: streaming kernel
 	size_t smemAL = 0, smemBL = 0;
@@ -731,6 +740,9 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 		xrow[r] = a.x + dl * n1;
 	}
 	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+	// tile fill: a warp copies 256 contiguous bytes of one row per instruction into every other 8-byte slot of the interleaved
+	// tile (2-way bank conflict on the shared-memory side).  Alternating the rows across lanes instead removes that conflict
+	// but splits every quarter-warp over two global lines and was measured slower (2.03 vs 1.69 ms).
 	for (uint32_t i = threadIdx.x; i < bsize; i += UPP_THREADS) {
 #pragma unroll
 		for (int r = 0; r < R; r++) {
@@ -783,7 +795,11 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 #pragma unroll
 		for (int r = 0; r < R; r++) xold[r] = xn_old[r];
 		if (i + UPP_THREADS < bsize) prefetch(i + UPP_THREADS);
-		double acc[R];
+		double acc[R], yown[R];
+		if (R == 2) {                                      // own elements for the dot: one 16-byte load (no 2-way conflict), issued early
+			const double2 yo = reinterpret_cast<const double2*>(ys)[i];
+			yown[0] = yo.x; yown[R - 1] = yo.y;
+		} else yown[0] = ys[i];
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = 0.0;
 		switch (cnt >> 2) {                                // warp-uniform: branch-free runs of 4*N independent gathers
@@ -800,7 +816,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 			const double hv = UNI ? t0 * acc[r] : acc[r];
 			double xn = a.beta * xold[r] + a.alpha * hv;
 			xrow[r][i] = xn;
-			contrib += ys[i * R + r] * xn;
+			contrib += yown[r] * xn;
 		}
 	}
 	if (want_dot && a.dot_partials) {
@@ -940,6 +956,146 @@ __global__ void __launch_bounds__(PAL_COLS, (VEC == 2) ? 3 : 4) k_sweep_down_lea
 
 static inline int down_lean_vec(const ColView& cv) { return (cv.pitch % 2 == 0 && cv.ncols % 2 == 0) ? 2 : 1; }
 static inline uint32_t down_lean_panels(const ColView& cv) { return (uint32_t)((cv.ncols + (uint64_t)PAL_COLS * down_lean_vec(cv) - 1) / ((uint64_t)PAL_COLS * down_lean_vec(cv))); }
+
+
+// sweep A staged: the streaming down sweep with the in-run operands taken from shared memory.  Down states are ordered by
+// their word (colex), so the states that share the occupation of the high sites [split, nsite) are one consecutive run
+// (<= C(split, k) rows); every hop between two of the low sites stays inside its run (4x4 lattice, split 8: 12 of the 32
+// bonds, 37.5 % of the operands).  A CTA owns (run, panel of PC columns): it stages the run's rows of y once (coalesced
+// 16-byte cp.async), then every row takes its in-run sources from that tile (conflict-free 16-byte LDS, consecutive lanes =
+// consecutive columns) and only the other sources as coalesced row reads from L2.  The kernel is bound by the L2->SM
+// fabric like k_sweep_down_lean, with fewer bytes to move.  Panel-major grid: a panel's slab of y (Ndn x PC doubles) stays
+// L2 resident while its runs are processed.
+#define DST_THREADS 256
+struct StEntry {
+	unsigned long long off;    // in-run source: byte offset of its row in the tile; other source: byte offset of its row in y
+	double amp;
+};
+template <int PC, int NB>
+__global__ void __launch_bounds__(DST_THREADS, (NB <= 4) ? 3 : 2)
+k_sweep_down_staged(ModelDev m, const uint32_t* __restrict__ stab, const uint16_t* __restrict__ scnt, const uint32_t* __restrict__ sboff,
+                    uint32_t blk0, uint32_t nblk_loc, int width, uint32_t maxrows, MagTable mt, DiagTables dt, SpmvArgs a, uint64_t d0,
+                    uint64_t dcount, ColView cv)
+{
+	extern __shared__ double ys[];                                   // [run row][PC]
+	StEntry* ent = reinterpret_cast<StEntry*>(ys + (size_t)maxrows * PC);     // [run row][width]
+	double* s_dv2 = reinterpret_cast<double*>(ent + (size_t)maxrows * width); // [run row] one-spin diagonal part
+	word_t* s_k2 = reinterpret_cast<word_t*>(s_dv2 + maxrows);       // [run row] down word
+	uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_k2 + maxrows);   // [run row] in-run | others << 8
+	constexpr int HP = PC / 2;                                       // 16-byte pieces (column pairs) per row
+	constexpr int RPI = DST_THREADS / HP;                            // row slots per CTA
+	const uint32_t panel = blockIdx.x / nblk_loc, blk = blk0 + blockIdx.x % nblk_loc;
+	const uint32_t b0 = sboff[blk], nb = sboff[blk + 1] - b0;
+	const uint64_t pitch = cv.pitch, pitch8 = cv.pitch * 8ull;
+	const uint64_t c0 = (uint64_t)panel * PC;
+	const uint32_t ys_s = (uint32_t)__cvta_generic_to_shared(ys);
+	for (uint32_t q = threadIdx.x; q < nb * HP; q += DST_THREADS) {
+		const uint32_t r = q / HP, cp = q % HP;
+		const uint64_t c = c0 + 2ull * cp;
+		if (c < cv.ncols)
+			asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ys_s + (r * PC + 2u * cp) * 8u), "l"(a.y + (uint64_t)(b0 + r) * pitch + c));
+	}
+	asm volatile("cp.async.commit_group;");
+	for (uint32_t q = threadIdx.x; q < nb * (uint32_t)width; q += DST_THREADS) {
+		const uint32_t r = q / width, k = q % width;
+		const uint32_t en = stab[(size_t)b0 * width + q];
+		const uint32_t cnt = scnt[b0 + r];
+		const uint32_t ci = cnt & 0xffu, ct = ci + (cnt >> 8);
+		StEntry e;
+		const double mg = mt.mag[(en >> 24) & 63u];
+		e.amp = (k < ct) ? ((en & TE_SIGN) ? -mg : mg) : 0.0;
+		e.off = (k < ci) ? (unsigned long long)(en & TE_IDX) * (PC * 8ull) : (unsigned long long)(en & TE_IDX) * pitch8;
+		ent[q] = e;
+	}
+	for (uint32_t q = threadIdx.x; q < nb; q += DST_THREADS) {
+		s_cnt[q] = scnt[b0 + q];
+		s_dv2[q] = dt.dv2[b0 + q];
+		s_k2[q] = m.b2[b0 + q];
+	}
+	asm volatile("cp.async.wait_group 0;");
+	__syncthreads();
+
+	const uint32_t rs = threadIdx.x / HP, cp = threadIdx.x % HP;
+	const uint64_t c = c0 + 2ull * cp;
+	double contrib = 0.0;
+	if (c < cv.ncols) {
+		const word_t k1a = m.b1[cv.u0 + c], k1b = m.b1[cv.u0 + c + 1];
+		const double dv1a = dt.dv1[cv.u0 + c], dv1b = dt.dv1[cv.u0 + c + 1];
+		const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + c);
+		const bool need_x = a.beta != 0.0;
+		const uint32_t tile_s = ys_s + 2u * cp * 8u;                 // this thread's column pair in row 0 of the tile
+#pragma unroll 1
+		for (uint32_t r = rs; r < nb; r += RPI) {
+			const uint64_t d = (uint64_t)b0 + r;
+			if (d < d0 || d >= d0 + dcount) continue;
+			const uint64_t t = (d - d0) * pitch + c;
+			const uint32_t cnt = s_cnt[r];
+			const int ci = (int)(cnt & 0xffu), kend = ci + (int)(cnt >> 8);
+			const StEntry* __restrict__ er = ent + r * width;
+			double2 xv = make_double2(0.0, 0.0);
+			if (need_x) xv = *reinterpret_cast<const double2*>(a.x + t);
+			double2 h0 = make_double2(0.0, 0.0), h1 = make_double2(0.0, 0.0);
+			// straight-line batches of N independent L2 row reads (N is warp-uniform: no per-slot predicates)
+#define DST_BATCH(N_)                                                                                                   \
+	{                                                                                                                   \
+		StEntry e_[N_];                                                                                                 \
+		double2 v_[N_];                                                                                                 \
+		_Pragma("unroll") for (int j = 0; j < N_; j++) { e_[j] = er[k + j]; v_[j] = *reinterpret_cast<const double2*>(ycol + e_[j].off); } \
+		_Pragma("unroll") for (int j = 0; j < N_; j++) {                                                                \
+			if (j & 1) { h1.x = fma(e_[j].amp, v_[j].x, h1.x); h1.y = fma(e_[j].amp, v_[j].y, h1.y); }                  \
+			else { h0.x = fma(e_[j].amp, v_[j].x, h0.x); h0.y = fma(e_[j].amp, v_[j].y, h0.y); }                        \
+		}                                                                                                               \
+	}
+			int k = 0;
+			for (; k + 2 <= ci; k += 2) {
+				const StEntry ea = er[k], eb = er[k + 1];
+				double2 va, vb;
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(va.x), "=d"(va.y) : "r"(tile_s + (uint32_t)ea.off));
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vb.x), "=d"(vb.y) : "r"(tile_s + (uint32_t)eb.off));
+				h0.x = fma(ea.amp, va.x, h0.x); h0.y = fma(ea.amp, va.y, h0.y);
+				h1.x = fma(eb.amp, vb.x, h1.x); h1.y = fma(eb.amp, vb.y, h1.y);
+			}
+			if (k < ci) {
+				const StEntry ea = er[k];
+				double2 va;
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(va.x), "=d"(va.y) : "r"(tile_s + (uint32_t)ea.off));
+				h0.x = fma(ea.amp, va.x, h0.x); h0.y = fma(ea.amp, va.y, h0.y);
+			}
+			for (k = ci; k + NB <= kend; k += NB) DST_BATCH(NB)
+			switch (kend - k) {
+			case 7: DST_BATCH(7) break;
+			case 6: DST_BATCH(6) break;
+			case 5: DST_BATCH(5) break;
+			case 4: DST_BATCH(4) break;
+			case 3: DST_BATCH(3) break;
+			case 2: DST_BATCH(2) break;
+			case 1: DST_BATCH(1) break;
+			default: break;
+			}
+#undef DST_BATCH
+			double2 yv;
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(yv.x), "=d"(yv.y) : "r"(tile_s + r * (PC * 8u)));
+			const word_t k2 = s_k2[r];
+			const double dv2 = s_dv2[r];
+			double dga, dgb;
+			if (m.model == LPP_MODEL_HUBBARD && dt.uniformU) {
+				dga = dt.U0 * (double)lpp_popc(k1a & k2) + dv1a + dv2;
+				dgb = dt.U0 * (double)lpp_popc(k1b & k2) + dv1b + dv2;
+			} else {
+				dga = tiled_diag(m, dt, k1a, k2, cv.u0 + c, d);
+				dgb = tiled_diag(m, dt, k1b, k2, cv.u0 + c + 1, d);
+			}
+			double xa = a.alpha * fma(dga, yv.x, h0.x + h1.x), xb = a.alpha * fma(dgb, yv.y, h0.y + h1.y);
+			if (need_x) { xa = fma(a.beta, xv.x, xa); xb = fma(a.beta, xv.y, xb); }
+			contrib += yv.x * xa + yv.y * xb;
+			*reinterpret_cast<double2*>(a.x + t) = make_double2(xa, xb);
+		}
+	}
+	if (a.dot_partials) {
+		double sum = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = sum;
+	}
+}
 
 // =====================================================================================================
 // v1 sweeps (fallbacks: too many distinct amplitudes, or one-spin bases that cannot be blocked)
@@ -1484,6 +1640,83 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 #undef SETP
 		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
 	}
+	// staged down sweep: runs of consecutive down states sharing the occupation of the sites >= split
+	if (mags_ok && p->leanA && dn.n < (1u << 24) && dn.width >= 1 && dn.width <= 255 && (getenv("LPP_DSTAGE") && getenv("LPP_DSTAGE")[0] == '1')) {
+		const uint64_t n2 = dn.n;
+		const int W = dn.width;
+		std::vector<uint32_t> hidx((size_t)W * n2), hcnt(n2);
+		std::vector<double> hval((size_t)W * n2);
+		std::vector<word_t> w2(n2);
+		if (cudaMemcpy(hidx.data(), dn.idx, hidx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+		    cudaMemcpy(hval.data(), dn.val, hval.size() * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess ||
+		    cudaMemcpy(hcnt.data(), dn.cnt, n2 * sizeof(uint32_t), cudaMemcpyDeviceToHost) != cudaSuccess ||
+		    cudaMemcpy(w2.data(), m.b2, n2 * sizeof(word_t), cudaMemcpyDeviceToHost) != cudaSuccess) {
+			g_terr = "down table download failed";
+			delete p;
+			return -1;
+		}
+		const char* envr = getenv("LPP_DSTAGE_ROWS");
+		const char* envc = getenv("LPP_DSTAGE_PC");
+		const uint32_t cap = envr ? (uint32_t)atoi(envr) : 72u;
+		p->stPC = (envc && atoi(envc) == 128) ? 128 : 64;
+		// largest split whose longest run fits the cap
+		int split = -1;
+		std::vector<uint32_t> off;
+		for (int sp = m.nbits; sp >= 1 && split < 0; sp--) {
+			std::vector<uint32_t> o(1, 0u);
+			uint32_t mx = 0;
+			for (uint64_t d = 1; d <= n2; d++)
+				if (d == n2 || (w2[d] >> sp) != (w2[d - 1] >> sp)) { mx = std::max<uint32_t>(mx, (uint32_t)d - o.back()); o.push_back((uint32_t)d); }
+			if (mx <= cap) { split = sp; off.swap(o); p->stMaxRows = mx; }
+		}
+		if (split >= 1) {
+			const int WP = (W + 3) & ~3;
+			std::vector<uint32_t> tab((size_t)n2 * WP);
+			std::vector<uint16_t> cnt(n2);
+			size_t nint = 0, ntot = 0;
+			bool ok = true;
+			for (size_t b = 0; b + 1 < off.size() && ok; b++)
+				for (uint32_t d = off[b]; d < off[b + 1] && ok; d++) {
+					uint32_t* row = tab.data() + (size_t)d * WP;
+					int ci = 0, ce = 0;
+					uint32_t ext[256];
+					for (uint32_t k = 0; k < hcnt[d]; k++) {
+						const uint32_t src = hidx[(size_t)k * n2 + d];
+						const double v = hval[(size_t)k * n2 + d];
+						int mi = -1;
+						for (int q = 0; q < p->mt.nmag; q++) if (p->mt.mag[q] == fabs(v)) mi = q;
+						if (mi < 0) { ok = false; break; }
+						const uint32_t e = ((uint32_t)mi << 24) | (v < 0 ? TE_SIGN : 0u);
+						if (src >= off[b] && src < off[b + 1]) row[ci++] = e | (src - off[b]);
+						else ext[ce++] = e | src;
+					}
+					for (int k = 0; k < ce; k++) row[ci + k] = ext[k];
+					for (int k = ci + ce; k < WP; k++) row[k] = d;            // padding: never dereferenced past the counts
+					cnt[d] = (uint16_t)(ci | (ce << 8));
+					nint += ci;
+					ntot += ci + ce;
+				}
+			p->stInternal = ntot ? (double)nint / (double)ntot : 0.0;
+			p->smemST = (size_t)p->stMaxRows * p->stPC * 8 + (size_t)p->stMaxRows * WP * 16 + (size_t)p->stMaxRows * 20 + 16;
+			if (ok && p->stInternal >= 0.15 && p->smemST + 1024 <= (size_t)maxsm) {
+				if (plan_upload(p, &p->stTab, tab) || plan_upload(p, &p->stCnt, cnt) || plan_upload(p, &p->stOff, off)) { delete p; return -1; }
+				p->stOff_host = off;
+				p->stNblk = (uint32_t)off.size() - 1;
+				p->stWidth = WP;
+				p->stSplit = split;
+				cudaError_t e = cudaSuccess;
+#define SETS(PC_, NB_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_down_staged<PC_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemST)
+				SETS(64, 4); SETS(64, 8); SETS(128, 4); SETS(128, 8);
+#undef SETS
+				{ const char* envn = getenv("LPP_DSTAGE_NB"); p->stNR = (envn && atoi(envn) == 4) ? 4 : 8; }
+				if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
+				p->stagedA = 1;
+			}
+		}
+		if (getenv("LPP_VERBOSE"))
+			fprintf(stderr, "[lpp tiled] staged down sweep: on=%d split=%d runs=%u max rows=%u in-run operands=%.3f smem=%zu PC=%d\n", p->stagedA,
+			        split, p->stNblk, p->stMaxRows, p->stInternal, p->smemST, p->stPC);
+	}
 	if (mags_ok) {
 		int rd = lpp_dtile_create(m, dn, dt.dv2, p->mt, s, &p->dtile);
 		if (rd < 0) { g_terr = std::string("down tile plan: ") + lpp_dtile_error(); delete p; return -1; }
@@ -1547,6 +1780,37 @@ void lpp_tiled_destroy(TiledPlan* p)
 	delete p;
 }
 
+
+// staged down sweep launcher: runs that intersect the local rows [d0, d0 + dcount)
+static inline bool staged_accepts(const TiledPlan* p, const ColView& cv) { return p->stagedA && cv.pitch % 2 == 0 && cv.ncols % 2 == 0; }
+static inline void staged_range(const TiledPlan* p, uint64_t d0, uint64_t dcount, uint32_t* blk0, uint32_t* nblk)
+{
+	const std::vector<uint32_t>& off = p->stOff_host;
+	uint32_t a = (uint32_t)(std::upper_bound(off.begin(), off.end(), (uint32_t)d0) - off.begin()) - 1;
+	uint32_t b = (uint32_t)(std::lower_bound(off.begin(), off.end(), (uint32_t)(d0 + dcount)) - off.begin());
+	*blk0 = a;
+	*nblk = (dcount == 0 || b <= a) ? 0u : b - a;
+}
+static inline uint32_t staged_grid(const TiledPlan* p, uint64_t d0, uint64_t dcount, const ColView& cv)
+{
+	uint32_t blk0, nblk;
+	staged_range(p, d0, dcount, &blk0, &nblk);
+	return (uint32_t)((cv.ncols + p->stPC - 1) / p->stPC) * nblk;
+}
+static int staged_launch(TiledPlan* p, const ModelDev& m, const DiagTables& dt, const SpmvArgs& a, uint64_t d0, uint64_t dcount, const ColView& cv,
+                         cudaStream_t s)
+{
+	uint32_t blk0, nblk;
+	staged_range(p, d0, dcount, &blk0, &nblk);
+	const uint32_t grid = (uint32_t)((cv.ncols + p->stPC - 1) / p->stPC) * nblk;
+	if (grid == 0) return 0;
+#define RUNS(PC_, NB_) k_sweep_down_staged<PC_, NB_><<<grid, DST_THREADS, p->smemST, s>>>(m, p->stTab, p->stCnt, p->stOff, blk0, nblk, p->stWidth, p->stMaxRows, p->mt, dt, a, d0, dcount, cv)
+	if (p->stNR == 4) { if (p->stPC == 128) RUNS(128, 4); else RUNS(64, 4); }
+	else { if (p->stPC == 128) RUNS(128, 8); else RUNS(64, 8); }
+#undef RUNS
+	return 0;
+}
+
 int lpp_tiled_dot_blocks(const TiledPlan* p) { return p->dot_blocks; }
 
 int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const HopTable& dn, const DiagTables& dt,
@@ -1580,6 +1844,10 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 			k_sweep_down_blocks<16><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
 		else
 			k_sweep_down_blocks<32><<<gridA, TA_THREADS, p->smemA, s>>>(m, p->dn, p->mt, dt, a, p->d0, p->dcount, p->tilesA, p->ntilesA_blocks);
+	} else if (p->leanA && staged_accepts(p, cvfull)) {
+		SpmvArgs aa = a;
+		aa.dot_partials = nullptr;
+		staged_launch(p, m, dt, aa, p->d0, p->dcount, cvfull, s);
 	} else if (p->leanA) {
 		const uint32_t nchunks = (uint32_t)((p->dcount + PAL_ROWS - 1) / PAL_ROWS);
 		SpmvArgs aa = a;
@@ -1674,6 +1942,7 @@ int lpp_tiled_down_cols_blocks(const TiledPlan* p, const ModelDev& m, uint64_t n
 	const ColView cvt{ncols, ncols, 0};
 	if (p->drows && !p->dtile && lpp_drows_accepts(p->drows, cvt)) return lpp_drows_grid(p->drows, cvt);
 	if (p->dtile && lpp_dtile_accepts(p->dtile, cvt)) return lpp_dtile_grid(p->dtile, cvt);
+	if (staged_accepts(p, cvt)) return (int)staged_grid(p, 0, m.n2, cvt);
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, 0};
 	return (int)(down_lean_panels(cv) * nchunks);
@@ -1691,6 +1960,12 @@ int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& d
 	}
 	if (p->dtile && lpp_dtile_accepts(p->dtile, cv)) {
 		if (lpp_dtile_sweep(p->dtile, m, dt, a, 0, m.n2, cv, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
+		return 1;
+	}
+	if (staged_accepts(p, cv)) {
+		staged_launch(p, m, dt, a, 0, m.n2, cv, s);
+		cudaError_t es = cudaGetLastError();
+		if (es != cudaSuccess) { g_terr = cudaGetErrorString(es); return -1; }
 		return 1;
 	}
 	if (down_lean_vec(cv) == 2) k_sweep_down_lean<2><<<lpp_tiled_down_cols_blocks(p, m, ncols), PAL_COLS, p->smemAL, s>>>(m, dn, dt, a, 0, m.n2, nchunks, cv);

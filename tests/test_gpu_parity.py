@@ -151,7 +151,7 @@ def test_continued_fraction_parity(lpp, oracle):
                 a, b = od.decomposition(phi, steps=steps, eps=0.0)
                 weight = (phi @ phi) * (-1.0 if typ > 1 else 1.0) * (1.0 if isite == jsite else 0.5)
                 assert abs(cf.weight - weight) <= 1e-12 * max(1.0, abs(weight))
-                n = min(len(a), 12)   # dim is only 225/400 here: rounding noise grows fast with the step count
+                n = min(len(a), 10)   # dim is only 225/400 here: rounding noise grows fast with the step count
                 assert relerr(cf.a[:n], a[:n]) <= 1e-10 and relerr(cf.b[:n], b[:n]) <= 1e-10
                 s = -1 if (typ & 1) else 1
                 gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
@@ -227,6 +227,28 @@ def test_row_walking_down_kernel(lpp, oracle, monkeypatch):
     monkeypatch.setenv("LPP_DROWS", "1")
     for case in (cases.SMALL_CASES["c1_hub8"], cases.SMALL_CASES["hub6_pbc_V"], cases.hubbard_square(4, 3, 6, 6),
                  cases.hubbard_chain(12, 6, 5, periodic=True)):
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        e = cases.make_engine(lpp, case)
+        y = geo.splitmix64_vector(o.rows(), 42)
+        x0 = geo.splitmix64_vector(o.rows(), 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+        assert relerr(x, xref) <= 1e-13
+        e.close()
+
+
+@pytest.mark.parametrize("rows,pc,nb", [("3", "64", "4"), ("20", "64", "8"), ("72", "128", "4")])
+def test_staged_down_kernel(lpp, oracle, rows, pc, nb, monkeypatch):
+    """k_sweep_down_staged (opt-in, LPP_DSTAGE=1): runs of consecutive down states staged in shared memory; the cap on the
+    run length moves the split between in-run (shared memory) and other (L2) sources, down to runs of 1-3 rows."""
+    monkeypatch.setenv("LPP_DSTAGE", "1")
+    monkeypatch.setenv("LPP_DSTAGE_ROWS", rows)
+    monkeypatch.setenv("LPP_DSTAGE_PC", pc)
+    monkeypatch.setenv("LPP_DSTAGE_NB", nb)
+    for case in (cases.SMALL_CASES["c1_hub8"], cases.SMALL_CASES["hub6_pbc_V"], cases.SMALL_CASES["hub_rand7"],
+                 cases.SMALL_CASES["hub_3x3"], cases.hubbard_square(4, 3, 6, 6), cases.hubbard_chain(12, 6, 5, periodic=True)):
         o = cases.make_oracle(oracle, case, fast_rank=1)
         e = cases.make_engine(lpp, case)
         y = geo.splitmix64_vector(o.rows(), 42)
