@@ -26,6 +26,10 @@ BYTES_PER_ROW_SPMV = 24.0    # read y, read x, write x
 BYTES_PER_ROW_ITER = 48.0    # fused Lanczos iteration
 
 
+def metric_name(workload_name, desc):
+    return METRIC if workload_name == "c3" else "Lanczos s/iteration (%s, on-the-fly SpMV, fp64)" % desc
+
+
 def workload(name):
     from lanczosplusplus_b200 import geometry as geo
     if name == "c3":
@@ -137,12 +141,50 @@ def cpu_sample(case, budget_rows, faithful, steps, warmup):
     return dict(s_per_iter=mv + sw, spmv_s=mv, sweeps_s=sw, cores=orc.num_threads(), rows=rows, sample_rows=n)
 
 
+def compiled_reference_check(case):
+    """The reference's own HubbardHelper / FeBasedSc product (oracle/_ref: its model headers compiled against the PsimagLite
+    shim) next to the port on a sector of the SAME lattice small enough to run whole (the reference has no row-range entry
+    point): rows/s of both.  Returns None when the prebuilt library did not travel with the snapshot."""
+    try:
+        from oracle import oracle as orc, reference as ref
+        from lanczosplusplus_b200 import geometry as geo
+        if case["model"] == 2 or ref.build() is None:
+            return None
+        small = dict(case, ndown=2)
+        nt = orc.num_threads()
+        ref.set_threads(nt)
+        r = ref.ReferenceModel(small["model"], small["nsite"], small["nup"], small["ndown"], small["orbitals"],
+                               hop=small.get("hop"), U=small.get("U"), V=small.get("V"), D=small.get("D"))
+        o = orc.OracleModel(small["model"], small["nsite"], small["nup"], small["ndown"], small["orbitals"],
+                            hop=small.get("hop"), U=small.get("U"), V=small.get("V"), D=small.get("D"), u3_all_pairs=0,
+                            fast_rank=0)
+        n = r.rows()
+        if n > 4_000_000:
+            return None
+        y = geo.splitmix64_vector(n, 42)
+        out = {}
+        xs = []
+        for name, f in (("reference", lambda x: r.matvec(x, y)), ("port", lambda x: o.matvec(x, y, faithful=True))):
+            x = np.zeros(n)
+            f(x)
+            x[:] = 0
+            t0 = time.perf_counter()
+            f(x)
+            out[name + "_rows_per_s"] = n / (time.perf_counter() - t0)
+            xs.append(x)
+        out.update(rows=n, cores=nt, sector="%d up %d down of the same lattice" % (small["nup"], small["ndown"]),
+                   max_abs_diff=float(np.abs(xs[0] - xs[1]).max()))
+        return out
+    except Exception as exc:      # the check is informative only
+        return {"unavailable": str(exc)[:200]}
+
+
 def run_reference(args, case, desc):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     r = cpu_sample(case, args.cpu_rows, True, max(1, min(args.steps, 3)), min(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": r["s_per_iter"], "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(args.workload, desc), "value": r["s_per_iter"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_iter"] * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "rows": r["rows"]},
@@ -151,7 +193,8 @@ def run_reference(args, case, desc):
                                        "scaled by %d/%d" % ((r["rows"] - r["sample_rows"]) // 2, r["sample_rows"],
                                                             r["rows"], r["sample_rows"])},
             "spmv_gbs": BYTES_PER_ROW_SPMV * r["rows"] / r["spmv_s"] / 1e9,
-            "e2e": {"value": r["s_per_iter"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": r["s_per_iter"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "compiled_reference_check": compiled_reference_check(case)}
     print(json.dumps(line), flush=True)
 
 
@@ -244,7 +287,7 @@ def main():
     spmv_bytes = BYTES_PER_ROW_SPMV * rows / world           # per GPU, per launch of the SpMV
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     traffic, traffic_kernels = measured_traffic(args.workload, world)
-    line = {"metric": METRIC, "value": iter_ms * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric_name(args.workload, desc), "value": iter_ms * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": iter_ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "rows": rows, "kernel": args.kernel, "l2": "vectors (1.3 GB) exceed L2; no flush",

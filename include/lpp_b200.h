@@ -38,7 +38,9 @@ typedef enum {
 typedef enum {
 	LPP_MODEL_HUBBARD = 0,    /* HubbardOneBand        : src/Models/HubbardOneOrbital  */
 	LPP_MODEL_FEAS = 1,       /* FeAsBasedSc INT_PAPER33: src/Models/FeBasedSc          */
-	LPP_MODEL_HEISENBERG = 2  /* Heisenberg, TwiceS=1  : src/Models/Heisenberg         */
+	LPP_MODEL_HEISENBERG = 2, /* Heisenberg, TwiceS=1  : src/Models/Heisenberg         */
+	LPP_MODEL_TJ = 3          /* Tj1Orbital (TjMultiOrb, Orbitals=1, no JHundInfinity): src/Models/TjMultiOrb;
+	                             stored CRS (the reference's only path for it) and the generic on-the-fly kernel */
 } lpp_model;
 
 /* How x += H y is evaluated (LanczosDriver1.h:222-238 chooses Stored vs OnTheFly from SolverOptions=). */
@@ -75,6 +77,9 @@ typedef struct {
 	int32_t device;       /* CUDA device ordinal */
 	int32_t rank;         /* row sharding over the slow (spin-down) index: this shard ... */
 	int32_t nranks;       /* ... of nranks (1 = whole Hilbert space on this GPU) */
+	/* t-J only (NULL otherwise), TjMultiOrb.h:68-79: hop = term 0, jpm = term 1, jzz = term 2, w = term 3 */
+	const double* jpm;
+	const double* w;
 } lpp_desc;
 
 /* PsimagLite::ParametersForSolver: <prefix>Steps, <prefix>Eps, <prefix>MinSteps. */
@@ -107,6 +112,12 @@ int lpp_basis_export(const lpp_handle* h, int32_t spin, uint64_t* words);
 /* perfectIndex of n one-spin words computed on device (BasisOneSpin.h:73-81; closed form replacing the linear
  * searches of BasisOneSpinFeAs.h:96-101 and BasisHeisenberg.h:73-80). */
 int lpp_rank(const lpp_handle* h, int32_t spin, const uint64_t* words, uint64_t n, uint64_t* index);
+/* basis(i, SPIN_UP) / basis(i, SPIN_DOWN) for rows [first, first+count) (BasisBase::operator(), e.g.
+ * BasisHubbardLanczos.h:77-84, BasisTjMultiOrbLanczos.h:127-141), computed on the device; either output may be NULL. */
+int lpp_row_words(const lpp_handle* h, uint64_t first, uint64_t count, uint64_t* up_words, uint64_t* down_words);
+/* perfectIndex(ket1, ket2) of the full basis for n word pairs (BasisHubbardLanczos.h:59-63, BasisFeAsBasedSc.h:91-100,
+ * BasisTjMultiOrbLanczos.h:71-112; Heisenberg ignores ket2), computed on the device. */
+int lpp_rank_pairs(const lpp_handle* h, const uint64_t* up_words, const uint64_t* down_words, uint64_t n, uint64_t* index);
 
 /* MatrixType::matrixVectorProduct(x, y): x += H y with caller-owned HOST vectors of rows() doubles
  * (InternalProductOnTheFly.h:120-123 -> HubbardHelper.h:105-134 / FeBasedSc.h:228-245).  Single shard only. */

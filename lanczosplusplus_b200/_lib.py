@@ -78,7 +78,8 @@ class Desc(C.Structure):
                 ("U", C.POINTER(C.c_double)), ("nU", C.c_int32),
                 ("V", C.POINTER(C.c_double)), ("nV", C.c_int32),
                 ("D", C.POINTER(C.c_double)), ("nD", C.c_int32),
-                ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32)]
+                ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("jpm", C.POINTER(C.c_double)), ("w", C.POINTER(C.c_double))]
 
 
 class SolverParams(C.Structure):
@@ -104,6 +105,8 @@ SYMBOLS = {
     "lpp_basis_size": (C.c_int, [_VP, C.c_int32, C.POINTER(C.c_uint64)]),
     "lpp_basis_export": (C.c_int, [_VP, C.c_int32, _VP]),
     "lpp_rank": (C.c_int, [_VP, C.c_int32, _VP, C.c_uint64, _VP]),
+    "lpp_row_words": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
+    "lpp_rank_pairs": (C.c_int, [_VP, _VP, _VP, C.c_uint64, _VP]),
     "lpp_matvec_host": (C.c_int, [_VP, C.c_int32, _VP, _VP]),
     "lpp_matvec_device": (C.c_int, [_VP, C.c_int32, _VP, _VP]),
     "lpp_crs_build": (C.c_int, [_VP, C.POINTER(C.c_int64)]),

@@ -17,6 +17,7 @@ typedef uint64_t word_t;
 #define LPP_MODEL_HUBBARD 0
 #define LPP_MODEL_FEAS 1
 #define LPP_MODEL_HEISENBERG 2
+#define LPP_MODEL_TJ 3        // TjMultiOrb with Orbitals=1 (Tj1Orbital): no double occupancy
 
 LPP_HD int lpp_popc(word_t a)
 {
@@ -51,7 +52,9 @@ struct ModelDev {
 	const word_t* b2;       // spin down
 	const uint64_t* binom;  // LPP_BINOM_N^2
 	const double* hop;      // nbits x nbits
-	const double* jzz;      // Heisenberg
+	const double* jzz;      // Heisenberg term 1 / t-J term 2
+	const double* jpm;      // t-J term 1 (S+S- couplings); unused otherwise
+	const double* w;        // t-J term 3 (n_i n_j couplings); unused otherwise
 	const double* U;
 	const double* V;
 	const double* D;
@@ -352,6 +355,107 @@ LPP_HD void lpp_heis_offdiag(const ModelDev& m, word_t ket, Emit& emit)
 	}
 }
 
+// ---------------------------------------------------------------- t-J (TjMultiOrb.h with Orbitals=1)
+// Basis (BasisTjMultiOrbLanczos.h:30-42,351-366): all (up, down) pairs without doubly occupied sites, as combined words
+// (down << nsite) | up sorted ascending.  Ascending order = down words in colex order (slow index i2), and for a fixed down
+// word the up words that avoid its sites in ascending order = colex order of the up word compressed onto the nsite - ndn
+// free sites (fast index i1).  rows = C(nsite, ndn) * C(nsite - ndn, nup); b2 = colex(nsite, ndn), b1 = colex(nsite - ndn, nup).
+LPP_HD word_t lpp_deposit(word_t compressed, word_t freemask)      // k-th bit of `compressed` -> k-th set bit of `freemask`
+{
+	word_t out = 0;
+	while (compressed) {
+		const int b = lpp_ctz(freemask);
+		if (compressed & 1) out |= lpp_bit(b);
+		compressed >>= 1;
+		freemask &= freemask - 1;
+	}
+	return out;
+}
+LPP_HD word_t lpp_extract(word_t w, word_t freemask)               // inverse of lpp_deposit
+{
+	word_t out = 0;
+	int k = 0;
+	while (freemask) {
+		const int b = lpp_ctz(freemask);
+		if ((w >> b) & 1) out |= lpp_bit(k);
+		k++;
+		freemask &= freemask - 1;
+	}
+	return out;
+}
+LPP_HD uint64_t lpp_rank_colex_any(const ModelDev& m, word_t w)
+{
+	if (m.rlo) {
+		word_t lo = w & lpp_below(m.lobits);
+		return (uint64_t)m.rlo[lo] + (uint64_t)m.rhi[((uint64_t)lpp_popc(lo) << (m.nbits - m.lobits)) + (w >> m.lobits)];
+	}
+	return lpp_rank_colex(m.binom, w);
+}
+// closed form of the search BasisTjMultiOrbLanczos.h:71-112
+LPP_HD uint64_t lpp_tj_rank(const ModelDev& m, word_t k1, word_t k2)
+{
+	const word_t freemask = ~k2 & lpp_below(m.nsite);
+	return lpp_rank_colex_any(m, lpp_extract(k1, freemask)) + lpp_rank_colex_any(m, k2) * m.n1;
+}
+// TjMultiOrb.h:586-647 for one orbital (proij = 1): potentialV[i] n_up + potentialV[i+nsite] n_dn,
+// sum_{i<j} (n_iu - n_id)(n_ju - n_jd) jzz(i,j)/4 + (n_iu + n_id)(n_ju + n_jd) w(i,j)
+LPP_HD double lpp_tj_diag(const ModelDev& m, word_t k1, word_t k2)
+{
+	const int nsite = m.nsite;
+	double s = 0;
+	for (int i = 0; i < nsite; i++) {
+		const int niu = (int)((k1 >> i) & 1), nid = (int)((k2 >> i) & 1);
+		s += m.V[i] * (double)niu;
+		s += m.V[i + nsite] * (double)nid;
+		for (int j = i + 1; j < nsite; j++) {
+			const int nju = (int)((k1 >> j) & 1), njd = (int)((k2 >> j) & 1);
+			s += (double)((niu - nid) * (nju - njd)) * m.jzz[i * nsite + j] * 0.25;
+			s += (double)((niu + nid) * (nju + njd)) * m.w[i * nsite + j];
+		}
+	}
+	return s;
+}
+// TjMultiOrb.h:649-695 (projected hopping, j >= i; value h(i,j) (-1)^{bits of the moving species strictly between i and j})
+// and :697-771 with :773-801 (S+S-: h = jpm(i,j)/2 times the parities of bra1 and bra2 over [i, j))
+template <class Emit>
+LPP_HD void lpp_tj_offdiag(const ModelDev& m, word_t k1, word_t k2, Emit& emit)
+{
+	const int nsite = m.nsite;
+	for (int i = 0; i < nsite; i++) {
+		const int s1i = (int)((k1 >> i) & 1), s2i = (int)((k2 >> i) & 1);
+		for (int j = i; j < nsite; j++) {
+			const double h = m.hop[i * nsite + j];
+			if (h == 0) continue;
+			const int s1j = (int)((k1 >> j) & 1), s2j = (int)((k2 >> j) & 1);
+			if (s1i + s1j == 1 && !(s1j == 0 && s2j > 0) && !(s1j > 0 && s2i > 0)) {
+				const word_t bra1 = k1 ^ (lpp_bit(i) | lpp_bit(j));
+				const double extra = (s1i == 1) ? -1.0 : 1.0;
+				emit(lpp_tj_rank(m, bra1, k2), h * extra * (double)lpp_sign_range(k1, i, j));
+			}
+			if (s2i + s2j == 1 && !(s2j == 0 && s1j > 0) && !(s2j > 0 && s1i > 0)) {
+				const word_t bra2 = k2 ^ (lpp_bit(i) | lpp_bit(j));
+				const double extra = (s2i == 1) ? -1.0 : 1.0;
+				emit(lpp_tj_rank(m, k1, bra2), h * extra * (double)lpp_sign_range(k2, i, j));
+			}
+		}
+		for (int j = i; j < nsite; j++) {
+			const double h = m.jpm[i * nsite + j] * 0.5;
+			if (h == 0) continue;
+			const int s1j = (int)((k1 >> j) & 1), s2j = (int)((k2 >> j) & 1);
+			if (s1i == 1 && s1j == 0 && s2i == 0 && s2j == 1) {
+				const word_t bra1 = (k1 ^ lpp_bit(i)) | lpp_bit(j);
+				const word_t bra2 = (k2 | lpp_bit(i)) ^ lpp_bit(j);
+				emit(lpp_tj_rank(m, bra1, bra2), h * (double)(lpp_sign_range(bra1, i, j) * lpp_sign_range(bra2, i, j)));
+			}
+			if (s1i == 0 && s1j == 1 && s2i == 1 && s2j == 0) {
+				const word_t bra1 = (k1 | lpp_bit(i)) ^ lpp_bit(j);
+				const word_t bra2 = (k2 ^ lpp_bit(i)) | lpp_bit(j);
+				emit(lpp_tj_rank(m, bra1, bra2), h * (double)(lpp_sign_range(bra1, i, j) * lpp_sign_range(bra2, i, j)));
+			}
+		}
+	}
+}
+
 // ---------------------------------------------------------------- full rows
 struct LppRowKets {
 	word_t k1, k2;
@@ -364,6 +468,9 @@ LPP_HD LppRowKets lpp_row_kets(const ModelDev& m, uint64_t row)
 	LppRowKets k;
 	if (m.model == LPP_MODEL_HEISENBERG) {
 		k.i1 = row; k.i2 = 0; k.k1 = m.b1[row]; k.k2 = 0;
+	} else if (m.model == LPP_MODEL_TJ) {
+		k.i1 = row % m.n1; k.i2 = row / m.n1; k.k2 = m.b2[k.i2];
+		k.k1 = lpp_deposit(m.b1[k.i1], ~k.k2 & lpp_below(m.nsite));
 	} else {
 		k.i1 = row % m.n1; k.i2 = row / m.n1; k.k1 = m.b1[k.i1]; k.k2 = m.b2[k.i2];
 	}
@@ -374,6 +481,7 @@ LPP_HD double lpp_row_diag(const ModelDev& m, const LppRowKets& k)
 {
 	if (m.model == LPP_MODEL_HUBBARD) return lpp_hubbard_diag(m, k.k1, k.k2);
 	if (m.model == LPP_MODEL_FEAS) return lpp_feas_diag(m, k.k1, k.k2);
+	if (m.model == LPP_MODEL_TJ) return lpp_tj_diag(m, k.k1, k.k2);
 	return lpp_heis_diag(m, k.k1);
 }
 
@@ -401,6 +509,10 @@ LPP_HD void lpp_row_offdiag(const ModelDev& m, const LppRowKets& k, int stored, 
 		lpp_heis_offdiag(m, k.k1, emit);
 		return;
 	}
+	if (m.model == LPP_MODEL_TJ) {
+		lpp_tj_offdiag(m, k.k1, k.k2, emit);
+		return;
+	}
 	LppUpAdapter<Emit> up{emit, k.i2, m.n1};
 	LppDnAdapter<Emit> dn{emit, k.i1, m.n1};
 	if (m.model == LPP_MODEL_HUBBARD) {
@@ -412,6 +524,15 @@ LPP_HD void lpp_row_offdiag(const ModelDev& m, const LppRowKets& k, int stored, 
 		LppTwoAdapter<Emit> two{emit, m.n1};
 		lpp_feas_twospin(m, k.k1, k.k2, stored ? 1 : m.u3_all_pairs, two);
 	}
+}
+
+// perfectIndex(ket1, ket2) of the full basis (BasisHubbardLanczos.h:59-63, BasisFeAsBasedSc.h:91-100, BasisHeisenberg.h:73-80,
+// BasisTjMultiOrbLanczos.h:71-112)
+LPP_HD uint64_t lpp_rank_pair(const ModelDev& m, word_t k1, word_t k2)
+{
+	if (m.model == LPP_MODEL_HEISENBERG) return lpp_rank_onespin(m, 0, k1);
+	if (m.model == LPP_MODEL_TJ) return lpp_tj_rank(m, k1, k2);
+	return lpp_rank_onespin(m, 0, k1) + lpp_rank_onespin(m, 1, k2) * m.n1;
 }
 
 // ---------------------------------------------------------------- Green-function sign and operator targets

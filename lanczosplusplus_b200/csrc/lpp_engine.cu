@@ -87,7 +87,7 @@ static int nccl_load()
 // ------------------------------------------------------------------ handle
 struct lpp_handle {
 	lpp_desc desc;
-	std::vector<double> hop, jzz, U, V, D;
+	std::vector<double> hop, jzz, U, V, D, jpm, w;
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	ModelDev md;
@@ -256,7 +256,14 @@ static int create_impl(const lpp_desc* d, lpp_handle* h)
 	const int no = (model == LPP_MODEL_FEAS) ? d->orbitals : 1;
 	h->desc.orbitals = no;
 	const int nb = nsite * no;
-	if (model < 0 || model > 2) return fail(LPP_ERR_ARG, "unknown model");
+	if (model < 0 || model > 3) return fail(LPP_ERR_ARG, "unknown model");
+	if (model == LPP_MODEL_TJ) {
+		if (d->orbitals > 1) return fail(LPP_ERR_ARG, "t-J: Orbitals=1 only (Tj1Orbital)");
+		if (nsite > 31) return fail(LPP_ERR_ARG, "t-J: at most 31 sites (combined word down << nsite | up)");
+		if (d->nup < 0 || d->ndown < 0 || d->nup + d->ndown > nsite) return fail(LPP_ERR_ARG, "t-J: nup + ndown must not exceed the number of sites");
+		if (d->nV != 0 && d->nV != 2 * nsite) return fail(LPP_ERR_ARG, "t-J: potentialV holds 2*nsite values (or none)");
+		if (d->nranks != 1) return fail(LPP_ERR_ARG, "t-J: single GPU only");
+	}
 	if (nsite < 1 || nb > 62) return fail(LPP_ERR_ARG, "nsite*orbitals must be in [1,62]");
 	if (no < 1 || no > LPP_MAX_ORB) return fail(LPP_ERR_ARG, "orbitals must be in [1,4]");
 	if (d->nup < 0 || d->nup > nb || (model != LPP_MODEL_HEISENBERG && (d->ndown < 0 || d->ndown > nb)))
@@ -280,7 +287,11 @@ static int create_impl(const lpp_desc* d, lpp_handle* h)
 		if (d->nU < 4 || d->nU > 6) return fail(LPP_ERR_ARG, "FeAsMode INT_PAPER33 expects 4, 5 or 6 U values");
 		if (d->nU == 4 || d->nU == 5) { h->U[4] = h->U[2]; h->U[5] = 0.0; }  // ParametersModelFeAs.h:147-151
 	}
-	const int needV = (model == LPP_MODEL_FEAS) ? 2 * no * nsite : nsite;
+	h->jpm.assign((size_t)nb * nb, 0.0);
+	h->w.assign((size_t)nb * nb, 0.0);
+	if (model == LPP_MODEL_TJ && d->jpm) h->jpm.assign(d->jpm, d->jpm + (size_t)nb * nb);
+	if (model == LPP_MODEL_TJ && d->w) h->w.assign(d->w, d->w + (size_t)nb * nb);
+	const int needV = (model == LPP_MODEL_FEAS) ? 2 * no * nsite : (model == LPP_MODEL_TJ ? 2 * nsite : nsite);
 	h->V.assign(needV, 0.0);
 	if (d->V) for (int i = 0; i < std::min(needV, d->nV); i++) h->V[i] = d->V[i];
 	h->D.assign(std::max(nsite, 1), 0.0);
@@ -297,6 +308,8 @@ static int create_impl(const lpp_desc* d, lpp_handle* h)
 	double* p;
 	CKR(dev_upload(h, &p, h->hop.data(), h->hop.size())); m.hop = p;
 	CKR(dev_upload(h, &p, h->jzz.data(), h->jzz.size())); m.jzz = p;
+	CKR(dev_upload(h, &p, h->jpm.data(), h->jpm.size())); m.jpm = p;
+	CKR(dev_upload(h, &p, h->w.data(), h->w.size())); m.w = p;
 	CKR(dev_upload(h, &p, h->U.data(), h->U.size())); m.U = p;
 	CKR(dev_upload(h, &p, h->V.data(), h->V.size())); m.V = p;
 	CKR(dev_upload(h, &p, h->D.data(), h->D.size())); m.D = p;
@@ -310,6 +323,14 @@ static int create_impl(const lpp_desc* d, lpp_handle* h)
 		CKR(dev_alloc(h, &b2, m.n2));
 		lpp_launch_build_feas(m, 0, m.n1, b1, h->stream);
 		lpp_launch_build_feas(m, 1, m.n2, b2, h->stream);
+	} else if (model == LPP_MODEL_TJ) {
+		// fast index: up words compressed onto the nsite - ndown sites the down word leaves free; slow index: down words
+		m.n1 = binom[(nsite - d->ndown) * LPP_BINOM_N + d->nup];
+		m.n2 = binom[nsite * LPP_BINOM_N + d->ndown];
+		CKR(dev_alloc(h, &b1, m.n1));
+		CKR(dev_alloc(h, &b2, m.n2));
+		lpp_launch_build_colex(m.binom, nsite - d->ndown, d->nup, m.n1, b1, h->stream);
+		lpp_launch_build_colex(m.binom, nsite, d->ndown, m.n2, b2, h->stream);
 	} else {
 		m.n1 = binom[nsite * LPP_BINOM_N + d->nup];
 		m.n2 = (model == LPP_MODEL_HUBBARD) ? binom[nsite * LPP_BINOM_N + d->ndown] : 1;
@@ -428,11 +449,46 @@ extern "C" int lpp_rank(const lpp_handle* hc, int32_t spin, const uint64_t* word
 	return 0;
 }
 
+extern "C" int lpp_row_words(const lpp_handle* hc, uint64_t first, uint64_t count, uint64_t* up_words, uint64_t* down_words)
+{
+	lpp_handle* h = const_cast<lpp_handle*>(hc);
+	if (!h) return fail(LPP_ERR_ARG, "null argument");
+	if (first > h->rows || count > h->rows - first) return fail(LPP_ERR_ARG, "row range outside the basis");
+	CK(cudaSetDevice(h->device));
+	word_t* du = nullptr; word_t* dd = nullptr;
+	if (up_words) CK(cudaMalloc((void**)&du, sizeof(word_t) * std::max<uint64_t>(count, 1)));
+	if (down_words) CK(cudaMalloc((void**)&dd, sizeof(word_t) * std::max<uint64_t>(count, 1)));
+	lpp_launch_row_words(h->md, first, count, du, dd, h->stream);
+	CK(cudaStreamSynchronize(h->stream));
+	if (du) CK(cudaMemcpy(up_words, du, sizeof(word_t) * count, cudaMemcpyDeviceToHost));
+	if (dd) CK(cudaMemcpy(down_words, dd, sizeof(word_t) * count, cudaMemcpyDeviceToHost));
+	cudaFree(du); cudaFree(dd);
+	return 0;
+}
+
+extern "C" int lpp_rank_pairs(const lpp_handle* hc, const uint64_t* up_words, const uint64_t* down_words, uint64_t n, uint64_t* index)
+{
+	lpp_handle* h = const_cast<lpp_handle*>(hc);
+	if (!h || !up_words || !down_words || !index) return fail(LPP_ERR_ARG, "null argument");
+	CK(cudaSetDevice(h->device));
+	word_t* du; word_t* dd; uint64_t* di;
+	CK(cudaMalloc((void**)&du, sizeof(word_t) * std::max<uint64_t>(n, 1)));
+	CK(cudaMalloc((void**)&dd, sizeof(word_t) * std::max<uint64_t>(n, 1)));
+	CK(cudaMalloc((void**)&di, sizeof(uint64_t) * std::max<uint64_t>(n, 1)));
+	CK(cudaMemcpy(du, up_words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(dd, down_words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
+	lpp_launch_rank_pairs(h->md, du, dd, n, di, h->stream);
+	CK(cudaStreamSynchronize(h->stream));
+	CK(cudaMemcpy(index, di, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+	cudaFree(du); cudaFree(dd); cudaFree(di);
+	return 0;
+}
+
 // ------------------------------------------------------------------ tables / CRS
 static int ensure_tables(lpp_handle* h)
 {
 	if (h->tables_ready) return 0;
-	if (h->md.model == LPP_MODEL_HEISENBERG) return fail(LPP_ERR_ARG, "hop tables exist for product bases only");
+	if (h->md.model == LPP_MODEL_HEISENBERG || h->md.model == LPP_MODEL_TJ) return fail(LPP_ERR_ARG, "hop tables exist for product bases only");
 	const ModelDev& m = h->md;
 	for (int spin = 0; spin < 2; spin++) {
 		HopTable& t = spin ? h->dn : h->up;
@@ -504,6 +560,7 @@ extern "C" int lpp_crs_export(const lpp_handle* h, int64_t* rowptr, int64_t* col
 // ------------------------------------------------------------------ SpMV dispatch
 static int resolve_kernel(const lpp_handle* h, int kernel)
 {
+	if (h->md.model == LPP_MODEL_TJ) return (kernel == LPP_KERNEL_STORED) ? LPP_KERNEL_STORED : LPP_KERNEL_GENERIC;   // not a product basis
 	if (kernel == LPP_KERNEL_AUTO) return (h->md.model == LPP_MODEL_HEISENBERG) ? LPP_KERNEL_TABLE : LPP_KERNEL_TILED;
 	if (h->md.model == LPP_MODEL_HEISENBERG && kernel == LPP_KERNEL_TILED) return LPP_KERNEL_TABLE;
 	return kernel;

@@ -136,6 +136,28 @@ void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out,
 {
 	k_build_feas<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, n, out);
 }
+__global__ void __launch_bounds__(LPP_TPB) k_row_words(ModelDev m, uint64_t first, uint64_t count, word_t* up, word_t* dn)
+{
+	uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x;
+	if (t >= count) return;
+	const LppRowKets k = lpp_row_kets(m, first + t);
+	if (up) up[t] = k.k1;
+	if (dn) dn[t] = k.k2;
+}
+__global__ void __launch_bounds__(LPP_TPB) k_rank_pairs(ModelDev m, const word_t* __restrict__ up, const word_t* __restrict__ dn, uint64_t n,
+                                                       uint64_t* __restrict__ out)
+{
+	uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x;
+	if (t < n) out[t] = lpp_rank_pair(m, up[t], dn[t]);
+}
+void lpp_launch_row_words(const ModelDev& m, uint64_t first, uint64_t count, word_t* up, word_t* dn, cudaStream_t s)
+{
+	if (count) k_row_words<<<(unsigned)((count + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, first, count, up, dn);
+}
+void lpp_launch_rank_pairs(const ModelDev& m, const word_t* up, const word_t* dn, uint64_t n, uint64_t* out, cudaStream_t s)
+{
+	if (n) k_rank_pairs<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, up, dn, n, out);
+}
 void lpp_launch_rank(const ModelDev& m, int spin, const word_t* w, uint64_t n, uint64_t* out, cudaStream_t s)
 {
 	k_rank<<<(unsigned)((n + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(m, spin, w, n, out);

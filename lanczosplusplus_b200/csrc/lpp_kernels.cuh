@@ -32,6 +32,8 @@ struct SpmvArgs {
 void lpp_launch_build_colex(const uint64_t* binom, int nsite, int npart, uint64_t n, word_t* out, cudaStream_t s);
 void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out, cudaStream_t s);
 void lpp_launch_rank(const ModelDev& m, int spin, const word_t* w, uint64_t n, uint64_t* out, cudaStream_t s);
+void lpp_launch_row_words(const ModelDev& m, uint64_t first, uint64_t count, word_t* up, word_t* dn, cudaStream_t s);
+void lpp_launch_rank_pairs(const ModelDev& m, const word_t* up, const word_t* dn, uint64_t n, uint64_t* out, cudaStream_t s);
 void lpp_launch_split_tables(const uint64_t* binom, int nbits, int lobits, uint32_t* rlo, uint32_t* rhi, cudaStream_t s);
 void lpp_launch_lut(const word_t* b, uint64_t n, uint32_t* lut, cudaStream_t s);
 void lpp_launch_hop_count(const ModelDev& m, int spin, uint64_t n, uint32_t* cnt, uint32_t* maxcnt, cudaStream_t s);

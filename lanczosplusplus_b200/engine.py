@@ -14,10 +14,10 @@ import numpy as np
 from . import _lib
 from ._lib import Desc, LppError, SolverParams, Timing, check
 
-HUBBARD, FEAS, HEISENBERG = 0, 1, 2
+HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TABLE, KERNEL_TILED, KERNEL_STORED = 0, 1, 2, 3, 4
 OP_C, OP_CDAGGER, OP_N = 1, 3, 4
-MODEL_NAMES = {"HubbardOneBand": HUBBARD, "FeAsBasedSc": FEAS, "Heisenberg": HEISENBERG}
+MODEL_NAMES = {"HubbardOneBand": HUBBARD, "FeAsBasedSc": FEAS, "Heisenberg": HEISENBERG, "Tj1Orbital": TJ, "TjMultiOrb": TJ}
 
 
 def _f64(a):
@@ -45,19 +45,21 @@ class InternalProductCuda:
     Mirrors InternalProductOnTheFly: rows(), matrixVectorProduct(x, y) (InternalProductOnTheFly.h:115-123)."""
 
     def __init__(self, model, nsite, nup, ndown=0, orbitals=1, hop=None, jzz=None, U=None, V=None, D=None,
-                 feas_u3_all_pairs=1, device=0, rank=0, nranks=1, kernel=KERNEL_AUTO):
+                 feas_u3_all_pairs=1, device=0, rank=0, nranks=1, kernel=KERNEL_AUTO, jpm=None, w=None):
         if isinstance(model, str):
             model = MODEL_NAMES[model]
         self.model, self.nsite, self.nup, self.ndown = model, nsite, nup, ndown
         self.orbitals = orbitals if model == FEAS else 1
         self.kernel = kernel
         self._keep = tuple(map(_f64, (hop, jzz, U, V, D)))
+        self._keep_tj = tuple(map(_f64, (jpm, w)))          # t-J: geometry terms 1 and 3 (TjMultiOrb.h:68-79)
         hop, jzz, U, V, D = self._keep
+        jpm, w = self._keep_tj
         if hop is None:
             raise LppError("hop matrix is required")
         d = Desc(model, nsite, self.orbitals, nup, ndown, feas_u3_all_pairs, _dp(hop), _dp(jzz), _dp(U),
                  0 if U is None else U.size, _dp(V), 0 if V is None else V.size, _dp(D), 0 if D is None else D.size,
-                 device, rank, nranks)
+                 device, rank, nranks, _dp(jpm), _dp(w))
         self._desc = d
         self.h = C.c_void_p()
         check(_lib.lib().lpp_create(C.byref(d), C.byref(self.h)))
@@ -79,7 +81,7 @@ class InternalProductCuda:
         hop, jzz, U, V, D = self._keep
         s = InternalProductCuda(self.model, self.nsite, nup, ndown, self.orbitals, hop, jzz, U, V, D,
                                 self._desc.feas_u3_all_pairs, self._desc.device, self.rank, self.nranks,
-                                kw.get("kernel", self.kernel))
+                                kw.get("kernel", self.kernel), jpm=self._keep_tj[0], w=self._keep_tj[1])
         if self.nranks > 1 and getattr(self, "_has_comm", False):
             check(_lib.lib().lpp_comm_share(s.h, self.h))      # same ranks, same device: borrow the communicator
             s._has_comm = True
@@ -121,6 +123,21 @@ class InternalProductCuda:
         w = np.ascontiguousarray(words, dtype=np.uint64)
         out = np.zeros(w.size, dtype=np.uint64)
         check(_lib.lib().lpp_rank(self.h, spin, w.ctypes.data, w.size, out.ctypes.data))
+        return out
+
+    def row_words(self, first=0, count=None):
+        """basis(i, SPIN_UP), basis(i, SPIN_DOWN) for rows [first, first+count) (BasisBase::operator())."""
+        count = self.rows() - first if count is None else count
+        up, dn = np.zeros(count, dtype=np.uint64), np.zeros(count, dtype=np.uint64)
+        check(_lib.lib().lpp_row_words(self.h, first, count, up.ctypes.data, dn.ctypes.data))
+        return up, dn
+
+    def perfectIndexPairs(self, up_words, down_words):
+        """perfectIndex(ket1, ket2) of the full basis."""
+        u = np.ascontiguousarray(up_words, dtype=np.uint64)
+        d = np.ascontiguousarray(down_words, dtype=np.uint64)
+        out = np.zeros(u.size, dtype=np.uint64)
+        check(_lib.lib().lpp_rank_pairs(self.h, u.ctypes.data, d.ctypes.data, u.size, out.ctypes.data))
         return out
 
     # --- stored CRS (InternalProductStored)

@@ -36,7 +36,7 @@
 
 typedef uint64_t word_t;
 
-enum { ORC_HUBBARD = 0, ORC_FEAS = 1, ORC_HEISENBERG = 2 };
+enum { ORC_HUBBARD = 0, ORC_FEAS = 1, ORC_HEISENBERG = 2, ORC_TJ = 3 };
 enum { ORC_OP_C = 1, ORC_OP_CDAGGER = 3, ORC_OP_N = 4 }; /* LabeledOperator.h:10-17 */
 
 typedef struct {
@@ -60,6 +60,11 @@ typedef struct {
 	int combn;
 	int32_t* lut1;     /* word -> index tables when fast_rank */
 	int32_t* lut2;
+	/* t-J (TjMultiOrb, Orbitals=1): combined words (down << nsite) | up, sorted; couplings of geometry terms 1 and 3 */
+	word_t* tj;
+	size_t ntj;
+	double* jpm;
+	double* w;
 } orc_model;
 
 /* ---------------------------------------------------------------- bit utils */
@@ -377,12 +382,91 @@ void orc_destroy(orc_model* m)
 	if (!m) return;
 	free(m->hop); free(m->jzz); free(m->U); free(m->V); free(m->Dani);
 	free(m->b1); free(m->b2); free(m->comb); free(m->lut1); free(m->lut2);
+	free(m->tj); free(m->jpm); free(m->w);
 	free(m);
 }
 
 size_t orc_rows(const orc_model* m)
 {
+	if (m->model == ORC_TJ) return m->ntj;
 	return (m->model == ORC_HEISENBERG) ? m->n1 : m->n1 * m->n2;
+}
+
+/* ---------------------------------------------------------------- t-J basis
+ * BasisTjMultiOrbLanczos.h:30-42: fillOneSector for both species (:321-349, the BasisOneSpin ripple), combineAndFilter
+ * (:351-366: every pair without a doubly occupied site, combined as (down << n) | up), std::sort. */
+static int cmp_word(const void* a, const void* b)
+{
+	word_t x = *(const word_t*)a, y = *(const word_t*)b;
+	return (x > y) - (x < y);
+}
+
+orc_model* orc_create_tj(int nsite, int nup, int ndown, const double* hop, const double* jpm, const double* jzz,
+                         const double* w, const double* V, int nV)
+{
+	orc_model* m = (orc_model*)calloc(1, sizeof(orc_model));
+	m->model = ORC_TJ;
+	m->nsite = nsite;
+	m->orbitals = 1;
+	m->nup = nup;
+	m->ndown = ndown;
+	size_t nn = (size_t)nsite * nsite;
+	m->hop = (double*)calloc(nn, sizeof(double));
+	m->jpm = (double*)calloc(nn, sizeof(double));
+	m->jzz = (double*)calloc(nn, sizeof(double));
+	m->w = (double*)calloc(nn, sizeof(double));
+	if (hop) memcpy(m->hop, hop, sizeof(double) * nn);
+	if (jpm) memcpy(m->jpm, jpm, sizeof(double) * nn);
+	if (jzz) memcpy(m->jzz, jzz, sizeof(double) * nn);
+	if (w) memcpy(m->w, w, sizeof(double) * nn);
+	m->V = (double*)calloc(2 * (size_t)nsite, sizeof(double));
+	if (V) memcpy(m->V, V, sizeof(double) * (size_t)(nV < 2 * nsite ? nV : 2 * nsite));
+	m->n1 = onespin_size(nsite, nup);
+	m->n2 = onespin_size(nsite, ndown);
+	m->b1 = (word_t*)malloc(sizeof(word_t) * m->n1);
+	m->b2 = (word_t*)malloc(sizeof(word_t) * m->n2);
+	onespin_fill(nsite, nup, m->b1);
+	onespin_fill(nsite, ndown, m->b2);
+	size_t cap = 1024, cnt = 0;
+	m->tj = (word_t*)malloc(sizeof(word_t) * cap);
+	for (size_t i = 0; i < m->n1; i++)
+		for (size_t j = 0; j < m->n2; j++) {
+			if (m->b1[i] & m->b2[j]) continue;               /* one or more doubly occupied sites */
+			if (cnt == cap) { cap *= 2; m->tj = (word_t*)realloc(m->tj, sizeof(word_t) * cap); }
+			m->tj[cnt++] = (m->b2[j] << nsite) | m->b1[i];
+		}
+	qsort(m->tj, cnt, sizeof(word_t), cmp_word);
+	m->ntj = cnt;
+	return m;
+}
+
+/* BasisTjMultiOrbLanczos.h:71-112: bisection (with a linear fallback) over the sorted combined words */
+static size_t tj_perfect_index(const orc_model* m, word_t k1, word_t k2)
+{
+	word_t key = (k2 << m->nsite) | k1;
+	size_t lo = 0, hi = m->ntj;
+	while (lo < hi) {
+		size_t mid = lo + (hi - lo) / 2;
+		if (m->tj[mid] < key) lo = mid + 1;
+		else hi = mid;
+	}
+	if (lo >= m->ntj || m->tj[lo] != key) {
+		fprintf(stderr, "orc: t-J perfectIndex: state not in the basis\n");
+		abort();
+	}
+	return lo;
+}
+
+/* basis(i, spin) for every row (BasisBase::operator(); BasisTjMultiOrbLanczos.h:127-141) */
+static inline void row_kets(const orc_model* m, size_t r, word_t* k1, word_t* k2);
+void orc_row_words(const orc_model* m, int spin, word_t* out)
+{
+	size_t n = orc_rows(m);
+	for (size_t r = 0; r < n; r++) {
+		word_t k1, k2;
+		row_kets(m, r, &k1, &k2);
+		out[r] = spin == 0 ? k1 : k2;
+	}
 }
 
 size_t orc_basis_size(const orc_model* m, int spin) { return spin == 0 ? m->n1 : m->n2; }
@@ -411,8 +495,12 @@ size_t orc_rank(const orc_model* m, int spin, word_t w) { return rank1(m, spin, 
 /* BasisHubbardLanczos.h:59-63 ; BasisFeAsBasedSc.h:97-100 */
 static inline size_t perfect_index(const orc_model* m, word_t k1, word_t k2)
 {
+	if (m->model == ORC_TJ) return tj_perfect_index(m, k1, k2);
+	if (m->model == ORC_HEISENBERG) return rank1(m, 0, k1);
 	return rank1(m, 0, k1) + rank1(m, 1, k2) * m->n1;
 }
+
+size_t orc_perfect_index(const orc_model* m, word_t k1, word_t k2) { return perfect_index(m, k1, k2); }
 
 /* --------------------------------------------------------------- sparse row */
 typedef struct {
@@ -678,9 +766,114 @@ static void heis_offdiag(const orc_model* m, srow* row, word_t ket)
 }
 
 /* ------------------------------------------------------------ generic rows */
+/* ---------------------------------------------------------------- t-J rows (TjMultiOrb.h, Orbitals=1) */
+/* BasisTjMultiOrbLanczos.h:378-396: parity of the occupied sites in [i, j) */
+static int tj_dosign(word_t ket, int i, int j)
+{
+	int sum = 0;
+	for (int c = i + 1; c < j; c++) if (ket & (((word_t)1) << c)) sum++;
+	for (int c = i; c < i + 1; c++) if (ket & (((word_t)1) << c)) sum++;
+	return (sum & 1) ? -1 : 1;
+}
+
+/* TjMultiOrb.h:784-801: parity of the occupied sites in [i, j], both ends included */
+static int tj_parity_from(int i, int j, word_t ket)
+{
+	if (i == j) return (ket & (((word_t)1) << j)) ? -1 : 1;
+	word_t mask = ket & (((((word_t)1) << (i + 1)) - 1) ^ ((((word_t)1) << j) - 1));
+	int s = (popc(mask) & 1) ? -1 : 1;
+	if (ket & (((word_t)1) << i)) s = -s;
+	if (ket & (((word_t)1) << j)) s = -s;
+	return s;
+}
+
+/* TjMultiOrb.h:773-782 */
+static double tj_sign_spsm(int i, int j, word_t bra1, word_t bra2)
+{
+	int s = 1;
+	if (j > 0) s *= tj_parity_from(0, j - 1, bra2);
+	if (i > 0) s *= tj_parity_from(0, i - 1, bra2);
+	if (i > 0) s *= tj_parity_from(0, i - 1, bra1);
+	if (j > 0) s *= tj_parity_from(0, j - 1, bra1);
+	return (double)s;
+}
+
+/* TjMultiOrb.h:586-647, one orbital (proij = 1) */
+static double tj_diag(const orc_model* m, word_t ket1, word_t ket2)
+{
+	int nsite = m->nsite;
+	double s = 0;
+	for (int i = 0; i < nsite; i++) {
+		int niup = (int)((ket1 >> i) & 1), nidown = (int)((ket2 >> i) & 1);
+		s += m->V[i] * niup;
+		s += m->V[i + nsite] * nidown;
+		for (int j = i + 1; j < nsite; j++) {
+			int njup = (int)((ket1 >> j) & 1), njdown = (int)((ket2 >> j) & 1);
+			s += (niup - nidown) * (njup - njdown) * m->jzz[i * nsite + j] * 0.25;
+			s += (niup + nidown) * (njup + njdown) * m->w[i * nsite + j];
+		}
+	}
+	return s;
+}
+
+/* TjMultiOrb.h:649-695 */
+static void tj_hops(const orc_model* m, srow* row, word_t ket1, word_t ket2, int i)
+{
+	int nsite = m->nsite;
+	word_t mi = ((word_t)1) << i;
+	int s1i = (ket1 & mi) ? 1 : 0, s2i = (ket2 & mi) ? 1 : 0;
+	for (int j = 0; j < nsite; j++) {
+		if (j < i) continue;
+		double h = m->hop[i * nsite + j];
+		if (h == 0) continue;
+		word_t mj = ((word_t)1) << j;
+		int s1j = (ket1 & mj) ? 1 : 0, s2j = (ket2 & mj) ? 1 : 0;
+		if (s1i + s1j == 1 && !(s1j == 0 && s2j > 0) && !(s1j > 0 && s2i > 0)) {
+			word_t bra1 = ket1 ^ (mi | mj);
+			double extraSign = (s1i == 1) ? -1 : 1;
+			srow_add(row, perfect_index(m, bra1, ket2), h * extraSign * tj_dosign(ket1, i, j));
+		}
+		if (s2i + s2j == 1 && !(s2j == 0 && s1j > 0) && !(s2j > 0 && s1i > 0)) {
+			word_t bra2 = ket2 ^ (mi | mj);
+			double extraSign = (s2i == 1) ? -1 : 1;
+			srow_add(row, perfect_index(m, ket1, bra2), h * extraSign * tj_dosign(ket2, i, j));
+		}
+	}
+}
+
+/* TjMultiOrb.h:697-771 */
+static void tj_spsm(const orc_model* m, srow* row, word_t ket1, word_t ket2, int i)
+{
+	int nsite = m->nsite;
+	word_t mi = ((word_t)1) << i;
+	int s1i = (ket1 & mi) ? 1 : 0, s2i = (ket2 & mi) ? 1 : 0;
+	for (int j = 0; j < nsite; j++) {
+		if (j < i) continue;
+		double h = m->jpm[i * nsite + j] * 0.5;
+		if (h == 0) continue;
+		word_t mj = ((word_t)1) << j;
+		int s1j = (ket1 & mj) ? 1 : 0, s2j = (ket2 & mj) ? 1 : 0;
+		if (s1i == 1 && s1j == 0 && s2i == 0 && s2j == 1) {
+			word_t bra1 = (ket1 ^ mi) | mj;
+			word_t bra2 = (ket2 | mi) ^ mj;
+			srow_add(row, perfect_index(m, bra1, bra2), h * tj_sign_spsm(i, j, bra1, bra2));
+		}
+		if (s1i == 0 && s1j == 1 && s2i == 1 && s2j == 0) {
+			word_t bra1 = (ket1 | mi) ^ mj;
+			word_t bra2 = (ket2 ^ mi) | mj;
+			srow_add(row, perfect_index(m, bra1, bra2), h * tj_sign_spsm(i, j, bra1, bra2));
+		}
+	}
+}
+
 static inline void row_kets(const orc_model* m, size_t r, word_t* k1, word_t* k2)
 {
 	if (m->model == ORC_HEISENBERG) { *k1 = m->b1[r]; *k2 = 0; return; }
+	if (m->model == ORC_TJ) { /* BasisTjMultiOrbLanczos.h:127-141 */
+		*k1 = m->tj[r] & ((((word_t)1) << m->nsite) - 1);
+		*k2 = m->tj[r] >> m->nsite;
+		return;
+	}
 	/* BasisHubbardLanczos.h:77-84 ; BasisFeAsBasedSc.h:84-89 */
 	*k1 = m->b1[r % m->n1];
 	*k2 = m->b2[r / m->n1];
@@ -690,6 +883,7 @@ static double row_diag(const orc_model* m, word_t k1, word_t k2)
 {
 	if (m->model == ORC_HUBBARD) return hubbard_diag(m, k1, k2);
 	if (m->model == ORC_FEAS) return feas_diag(m, k1, k2);
+	if (m->model == ORC_TJ) return tj_diag(m, k1, k2);
 	return heis_diag(m, k1);
 }
 
@@ -710,6 +904,11 @@ static void row_offdiag(const orc_model* m, srow* row, word_t k1, word_t k2, int
 					feas_u3(m, row, k1, k2, i, orb, orb2);
 				}
 			}
+		}
+	} else if (m->model == ORC_TJ) { /* TjMultiOrb.h:112-117 (one orbital) */
+		for (int i = 0; i < m->nsite; i++) {
+			tj_hops(m, row, k1, k2, i);
+			tj_spsm(m, row, k1, k2, i);
 		}
 	} else {
 		heis_offdiag(m, row, k1);

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liblpp_oracle.so")
 
-HUBBARD, FEAS, HEISENBERG = 0, 1, 2
+HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
 OP_C, OP_CDAGGER, OP_N = 1, 3, 4
 
 
@@ -36,6 +36,11 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_int] * 5 + [dp, dp, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int]
+        L.orc_create_tj.restype = C.c_void_p
+        L.orc_create_tj.argtypes = [C.c_int] * 3 + [dp, dp, dp, dp, dp, C.c_int]
+        L.orc_row_words.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_perfect_index.restype = C.c_size_t
+        L.orc_perfect_index.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_rows.restype = C.c_size_t
         L.orc_rows.argtypes = [C.c_void_p]
@@ -123,11 +128,15 @@ class OracleModel:
     """CPU restatement of one (model, sector): HubbardOneOrbital / FeBasedSc(INT_PAPER33) / Heisenberg S=1/2."""
 
     def __init__(self, model, nsite, nup, ndown=0, orbitals=1, hop=None, jzz=None, U=None, V=None, D=None,
-                 u3_all_pairs=1, fast_rank=0):
+                 u3_all_pairs=1, fast_rank=0, jpm=None, w=None):
         self.model, self.nsite, self.orbitals = model, nsite, (orbitals if model == FEAS else 1)
         self.nup, self.ndown = nup, ndown
-        hop, jzz, U, V, D = map(_f64, (hop, jzz, U, V, D))
-        self._keep = (hop, jzz, U, V, D)
+        hop, jzz, U, V, D, jpm, w = map(_f64, (hop, jzz, U, V, D, jpm, w))
+        self._keep = (hop, jzz, U, V, D, jpm, w)
+        if model == TJ:      # Tj1Orbital: geometry terms hop, jpm, jzz, w (TjMultiOrb.h:68-79)
+            self.h = lib().orc_create_tj(nsite, nup, ndown, _dptr(hop), _dptr(jpm), _dptr(jzz), _dptr(w), _dptr(V),
+                                         0 if V is None else V.size)
+            return
         self.h = lib().orc_create(model, nsite, orbitals, nup, ndown, _dptr(hop), _dptr(jzz), _dptr(U),
                                   0 if U is None else U.size, _dptr(V), 0 if V is None else V.size, _dptr(D),
                                   0 if D is None else D.size, u3_all_pairs, fast_rank)
@@ -145,6 +154,15 @@ class OracleModel:
         out = np.zeros(n, dtype=np.uint64)
         lib().orc_basis_words(self.h, spin, out.ctypes.data)
         return out
+
+    def row_words(self, spin):
+        """basis(i, spin) for every row."""
+        out = np.zeros(self.rows(), dtype=np.uint64)
+        lib().orc_row_words(self.h, spin, out.ctypes.data)
+        return out
+
+    def perfect_index(self, ket1, ket2):
+        return lib().orc_perfect_index(self.h, int(ket1), int(ket2))
 
     def rank(self, spin, word):
         return lib().orc_rank(self.h, spin, int(word))

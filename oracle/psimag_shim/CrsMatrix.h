@@ -11,6 +11,7 @@ class CrsMatrix {
 public:
 	typedef T value_type;
 	CrsMatrix() : nrow_(0), ncol_(0) {}
+	CrsMatrix(SizeType nrow, SizeType ncol) { resize(nrow, ncol); }
 	void resize(SizeType nrow, SizeType ncol)
 	{
 		nrow_ = nrow; ncol_ = ncol;
@@ -50,5 +51,47 @@ private:
 	std::vector<SizeType> rowptr_, colind_;
 	std::vector<T> values_;
 };
+// C = A^dagger and C = A B: only the JHundInfinity=1 branch of TjMultiOrb.h (two orbitals, out of scope) and
+// ProgramGlobals::transform reach these; they exist so that the reference headers compile
+template <typename T> void transposeConjugate(CrsMatrix<T>& c, const CrsMatrix<T>& a)
+{
+	std::vector<std::vector<std::pair<SizeType, T> > > rows(a.cols());
+	for (SizeType i = 0; i < a.rows(); ++i)
+		for (SizeType k = a.getRowPtr(i); k < a.getRowPtr(i + 1); ++k) rows[a.getCol(k)].push_back(std::make_pair(i, conj(a.getValue(k))));
+	c.resize(a.cols(), a.rows());
+	SizeType counter = 0;
+	for (SizeType i = 0; i < rows.size(); ++i) {
+		c.setRow(i, counter);
+		for (SizeType k = 0; k < rows[i].size(); ++k) { c.pushCol(rows[i][k].first); c.pushValue(rows[i][k].second); counter++; }
+	}
+	c.setRow(rows.size(), counter);
+}
+template <typename T> void multiply(CrsMatrix<T>& c, const CrsMatrix<T>& a, const CrsMatrix<T>& b)
+{
+	c.resize(a.rows(), b.cols());
+	SizeType counter = 0;
+	std::vector<T> acc(b.cols());
+	std::vector<char> used(b.cols());
+	for (SizeType i = 0; i < a.rows(); ++i) {
+		c.setRow(i, counter);
+		std::fill(acc.begin(), acc.end(), T(0));
+		std::fill(used.begin(), used.end(), 0);
+		for (SizeType k = a.getRowPtr(i); k < a.getRowPtr(i + 1); ++k)
+			for (SizeType l = b.getRowPtr(a.getCol(k)); l < b.getRowPtr(a.getCol(k) + 1); ++l) {
+				acc[b.getCol(l)] += a.getValue(k) * b.getValue(l);
+				used[b.getCol(l)] = 1;
+			}
+		for (SizeType j = 0; j < b.cols(); ++j)
+			if (used[j]) { c.pushCol(j); c.pushValue(acc[j]); counter++; }
+	}
+	c.setRow(a.rows(), counter);
+}
+template <typename V, typename T> void multiply(V& x, const CrsMatrix<T>& a, const V& y)
+{
+	for (SizeType i = 0; i < a.rows(); ++i) {
+		x[i] = 0;
+		for (SizeType k = a.getRowPtr(i); k < a.getRowPtr(i + 1); ++k) x[i] += a.getValue(k) * y[a.getCol(k)];
+	}
+}
 } // namespace PsimagLite
 #endif

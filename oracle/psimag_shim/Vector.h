@@ -44,6 +44,22 @@ inline double real(const std::complex<double>& x) { return x.real(); }
 inline double imag(const std::complex<double>& x) { return x.imag(); }
 inline std::complex<double> conj(const std::complex<double>& x) { return std::conj(x); }
 
+// Sort<V>::sort(v, permutation): ascending sort that also returns where every element came from (used by the
+// JHundInfinity branch of TjMultiOrb.h only)
+template <typename V>
+class Sort {
+public:
+	void sort(V& v, std::vector<SizeType>& perm)
+	{
+		perm.resize(v.size());
+		for (SizeType i = 0; i < perm.size(); ++i) perm[i] = i;
+		std::stable_sort(perm.begin(), perm.end(), [&v](SizeType a, SizeType b) { return v[a] < v[b]; });
+		V w(v.size());
+		for (SizeType i = 0; i < perm.size(); ++i) w[i] = v[perm[i]];
+		v.swap(w);
+	}
+};
+
 template <typename V> void vectorPrint(const V& v, const char* label, std::ostream& os)
 {
 	os << label << " " << v.size() << "\n";

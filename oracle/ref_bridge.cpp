@@ -2,7 +2,7 @@
 //
 // Compiles the REFERENCE'S OWN model headers, unmodified and from where they lie under /root/reference/src
 // (HubbardOneOrbital.h + HubbardHelper.h + BasisHubbardLanczos.h + BasisOneSpin.h, FeBasedSc.h + BasisFeAsBasedSc.h +
-// BasisOneSpinFeAs.h + Partitions.h, Heisenberg.h + BasisHeisenberg.h, ModelBase.h, BasisBase.h, ProgramGlobals.h,
+// BasisOneSpinFeAs.h + Partitions.h, Heisenberg.h + BasisHeisenberg.h, TjMultiOrb.h + BasisTjMultiOrbLanczos.h, ModelBase.h, BasisBase.h, ProgramGlobals.h,
 // LabeledOperator.h, RahulOperator.h and the three Parameters*.h), against oracle/psimag_shim/ -- a minimal stand-in for the
 // un-vendored PsimagLite containers those headers include (Vector, Matrix, CrsMatrix, SparseRow, BitManip::count,
 // Parallelizer).  Output: oracle/_ref/liblpp_ref.so (git-ignored; built by `make -C oracle _ref` when /root/reference exists).
@@ -18,6 +18,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <type_traits>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ template <typename T> bool isHermitian(const CrsMatrix<T>& m)
 #include "BasisFeAsBasedSc.h"
 #include "FeBasedSc.h"
 #include "Heisenberg.h"
+#include "TjMultiOrb.h"
 
 // static members the reference defines in LanczosDriver0.cpp:53-58 and ProgramGlobals.cpp:5
 SizeType LanczosPlusPlus::BasisOneSpin::nsite_ = 0;
@@ -61,14 +63,16 @@ namespace {
 
 class BridgeGeometry {
 public:
-	BridgeGeometry(SizeType nsite, SizeType orbitals, SizeType terms, const double* t0, const double* t1)
+	BridgeGeometry(SizeType nsite, SizeType orbitals, SizeType terms, const double* t0, const double* t1, const double* t2 = nullptr,
+	               const double* t3 = nullptr)
 	    : nsite_(nsite), orbitals_(orbitals), terms_(terms)
 	{
 		const SizeType nb = nsite * orbitals;
-		term0_.assign(nb * nb, 0.0);
-		term1_.assign(nb * nb, 0.0);
-		if (t0) std::memcpy(term0_.data(), t0, sizeof(double) * nb * nb);
-		if (t1) std::memcpy(term1_.data(), t1, sizeof(double) * nb * nb);
+		const double* t[4] = {t0, t1, t2, t3};
+		for (int q = 0; q < 4; q++) {
+			term_[q].assign(nb * nb, 0.0);
+			if (t[q]) std::memcpy(term_[q].data(), t[q], sizeof(double) * nb * nb);
+		}
 	}
 	SizeType numberOfSites() const { return nsite_; }
 	SizeType terms() const { return terms_; }
@@ -77,11 +81,11 @@ public:
 		const SizeType nb = nsite_ * orbitals_;
 		const SizeType a = i * orbitals_ + orb1, b = j * orbitals_ + orb2;
 		if (term >= terms_) throw PsimagLite::RuntimeError("BridgeGeometry: term out of range\n");
-		return (term == 0) ? term0_[a * nb + b] : term1_[a * nb + b];
+		return term_[term][a * nb + b];
 	}
 private:
 	SizeType nsite_, orbitals_, terms_;
-	std::vector<double> term0_, term1_;
+	std::vector<double> term_[4];
 };
 
 class BridgeInput {
@@ -94,6 +98,10 @@ public:
 		if (it == lines.end()) throw std::runtime_error("BridgeInput: no " + label);
 		std::istringstream ss(it->second);
 		ss >> x;
+	}
+	template <typename T> typename std::enable_if<std::is_arithmetic<T>::value, void>::type read(T& x, const std::string& label)
+	{
+		readline(x, label);                    // ParametersTjMultiOrb.h:99 reads the scalar Orbitals= with read()
 	}
 	template <typename T> void read(std::vector<T>& v, const std::string& label)
 	{
@@ -113,6 +121,7 @@ typedef LanczosPlusPlus::HubbardOneOrbital<double, BridgeGeometry, BridgeInput> 
 typedef LanczosPlusPlus::BasisFeAsBasedSc<BridgeGeometry> BasisFeAsType;
 typedef LanczosPlusPlus::FeBasedSc<double, BasisFeAsType, BridgeInput> FeAsType;
 typedef LanczosPlusPlus::Heisenberg<double, BridgeGeometry, BridgeInput> HeisenbergType;
+typedef LanczosPlusPlus::TjMultiOrb<double, BridgeGeometry, BridgeInput> TjType;
 typedef LanczosPlusPlus::LabeledOperator LabeledOperatorType;
 
 struct RefModel {
@@ -197,6 +206,25 @@ void* ref_create(int model, int nsite, int orbitals, int nup, int ndown, const d
 	} else {
 		throw std::runtime_error("ref_create: unknown model");
 	}
+	r->basis = &r->model->basis();
+	return r.release();
+	REF_CATCH(nullptr)
+}
+
+// Tj1Orbital: TjMultiOrb with Orbitals=1; geometry terms 0..3 = hopping, S+S- coupling, SzSz coupling, n n coupling
+// (TjMultiOrb.h:68-79); potentialV holds 2*nsite values or none (ParametersTjMultiOrb.h:91-93)
+void* ref_create_tj(int nsite, int nup, int ndown, const double* hop, const double* jpm, const double* jzz, const double* w,
+                    const double* V, int nV)
+{
+	REF_TRY
+	CoutSilencer quiet;
+	std::unique_ptr<RefModel> r(new RefModel());
+	r->kind = 3;
+	BridgeInput io;
+	r->geometry.reset(new BridgeGeometry(nsite, 1, 4, hop, jpm, jzz, w));
+	io.lines["Orbitals="] = "1";
+	if (V && nV > 0) io.vectors["potentialV"].assign(V, V + nV);
+	r->model.reset(new TjType(nup, ndown, io, *r->geometry));
 	r->basis = &r->model->basis();
 	return r.release();
 	REF_CATCH(nullptr)

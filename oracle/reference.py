@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_ref", "liblpp_ref.so")
 REFERENCE_SRC = "/root/reference/src"
 
-HUBBARD, FEAS, HEISENBERG = 0, 1, 2
+HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
 OP_C, OP_SZ, OP_CDAGGER, OP_N, OP_SPLUS, OP_SMINUS = 1, 2, 3, 4, 5, 6
 
 
@@ -49,6 +49,8 @@ def lib():
         L.ref_last_error.restype = C.c_char_p
         L.ref_create.restype = C.c_void_p
         L.ref_create.argtypes = [C.c_int] * 5 + [dp, dp, dp, C.c_int, dp, C.c_int, dp, C.c_int]
+        L.ref_create_tj.restype = C.c_void_p
+        L.ref_create_tj.argtypes = [C.c_int] * 3 + [dp, dp, dp, dp, dp, C.c_int]
         L.ref_new_sector.restype = C.c_void_p
         L.ref_new_sector.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_destroy.argtypes = [C.c_void_p]
@@ -85,14 +87,20 @@ class ReferenceModel:
     """One (model, sector) of the reference: HubbardOneOrbital / FeBasedSc INT_PAPER33 / Heisenberg S=1/2."""
 
     def __init__(self, model, nsite, nup, ndown=0, orbitals=1, hop=None, jzz=None, U=None, V=None, D=None, _handle=None,
-                 _parent=None):
+                 _parent=None, jpm=None, w=None):
         self.model, self.nsite, self.nup, self.ndown = model, nsite, nup, ndown
         self.orbitals = orbitals if model == FEAS else 1
         self._parent = _parent                     # keeps the owning model alive for new-sector handles
         if _handle is not None:
             self.h = _handle
             return
-        hop, jzz, U, V, D = map(_f64, (hop, jzz, U, V, D))
+        hop, jzz, U, V, D, jpm, w = map(_f64, (hop, jzz, U, V, D, jpm, w))
+        if model == TJ:
+            self.h = lib().ref_create_tj(nsite, nup, ndown, _dptr(hop), _dptr(jpm), _dptr(jzz), _dptr(w), _dptr(V),
+                                         0 if V is None else V.size)
+            if not self.h:
+                raise RuntimeError("reference: " + lib().ref_last_error().decode())
+            return
         self.h = lib().ref_create(model, nsite, self.orbitals, nup, ndown, _dptr(hop), _dptr(jzz), _dptr(U),
                                   0 if U is None else U.size, _dptr(V), 0 if V is None else V.size, _dptr(D),
                                   0 if D is None else D.size)

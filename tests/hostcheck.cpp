@@ -10,7 +10,7 @@
 struct HostModel {
 	ModelDev m;
 	std::vector<uint64_t> binom;
-	std::vector<double> hop, jzz, U, V, D;
+	std::vector<double> hop, jzz, U, V, D, jpm, w;
 	std::vector<word_t> b1, b2;
 	LppFeasLayout L1, L2;
 	std::vector<uint32_t> rlo, rhi, lut1, lut2;
@@ -32,7 +32,9 @@ HostModel* hc_create(int model, int nsite, int orbitals, int nup, int ndown, con
 	h->U.assign(needU, 0.0);
 	for (int i = 0; i < needU && i < nU; i++) h->U[i] = U[i];
 	if (model == LPP_MODEL_FEAS && (nU == 4 || nU == 5)) { h->U[4] = h->U[2]; h->U[5] = 0; }
-	const int needV = model == LPP_MODEL_FEAS ? 2 * no * nsite : nsite;
+	const int needV = model == LPP_MODEL_FEAS ? 2 * no * nsite : (model == LPP_MODEL_TJ ? 2 * nsite : nsite);
+	h->jpm.assign((size_t)nb * nb, 0.0);
+	h->w.assign((size_t)nb * nb, 0.0);
 	h->V.assign(needV, 0.0);
 	for (int i = 0; i < needV && i < nV; i++) h->V[i] = V[i];
 	h->D.assign(nsite, 0.0);
@@ -43,6 +45,7 @@ HostModel* hc_create(int model, int nsite, int orbitals, int nup, int ndown, con
 	m.u3_all_pairs = u3_all_pairs;
 	m.binom = h->binom.data();
 	m.hop = h->hop.data(); m.jzz = h->jzz.data(); m.U = h->U.data(); m.V = h->V.data(); m.D = h->D.data();
+	m.jpm = h->jpm.data(); m.w = h->w.data();
 	if (model == LPP_MODEL_FEAS) {
 		h->L1 = lpp_feas_layout(h->binom, nsite, no, nup);
 		h->L2 = lpp_feas_layout(h->binom, nsite, no, ndown);
@@ -54,6 +57,12 @@ HostModel* hc_create(int model, int nsite, int orbitals, int nup, int ndown, con
 		h->b1.resize(m.n1); h->b2.resize(m.n2);
 		for (uint64_t i = 0; i < m.n1; i++) h->b1[i] = lpp_unrank_feas(m, 0, i);
 		for (uint64_t i = 0; i < m.n2; i++) h->b2[i] = lpp_unrank_feas(m, 1, i);
+	} else if (model == LPP_MODEL_TJ) {      // same set-up as create_impl in lpp_engine.cu
+		m.n1 = h->binom[(nsite - ndown) * LPP_BINOM_N + nup];
+		m.n2 = h->binom[nsite * LPP_BINOM_N + ndown];
+		h->b1.resize(m.n1); h->b2.resize(m.n2);
+		for (uint64_t i = 0; i < m.n1; i++) h->b1[i] = lpp_unrank_colex(m.binom, nsite - ndown, nup, i);
+		for (uint64_t i = 0; i < m.n2; i++) h->b2[i] = lpp_unrank_colex(m.binom, nsite, ndown, i);
 	} else {
 		m.n1 = h->binom[nsite * LPP_BINOM_N + nup];
 		m.n2 = model == LPP_MODEL_HUBBARD ? h->binom[nsite * LPP_BINOM_N + ndown] : 1;
@@ -82,6 +91,24 @@ HostModel* hc_create(int model, int nsite, int orbitals, int nup, int ndown, con
 	}
 	return h;
 }
+
+// t-J couplings of geometry terms 1 and 3 (TjMultiOrb.h:68-79)
+void hc_set_tj(HostModel* h, const double* jpm, const double* w)
+{
+	const size_t nn = (size_t)h->m.nbits * h->m.nbits;
+	if (jpm) h->jpm.assign(jpm, jpm + nn);
+	if (w) h->w.assign(w, w + nn);
+	h->m.jpm = h->jpm.data();
+	h->m.w = h->w.data();
+}
+void hc_row_words(const HostModel* h, int spin, uint64_t* out)
+{
+	for (uint64_t r = 0; r < h->m.rows; r++) {
+		const LppRowKets k = lpp_row_kets(h->m, r);
+		out[r] = spin ? k.k2 : k.k1;
+	}
+}
+uint64_t hc_rank_pair(const HostModel* h, uint64_t k1, uint64_t k2) { return lpp_rank_pair(h->m, k1, k2); }
 
 void hc_destroy(HostModel* h) { delete h; }
 uint64_t hc_rows(const HostModel* h) { return h->m.rows; }

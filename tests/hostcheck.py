@@ -22,6 +22,10 @@ def lib():
         dp = C.POINTER(C.c_double)
         L.hc_create.restype = C.c_void_p
         L.hc_create.argtypes = [C.c_int] * 5 + [dp, dp, dp, C.c_int, dp, C.c_int, dp, C.c_int, C.c_int, C.c_int]
+        L.hc_set_tj.argtypes = [C.c_void_p, dp, dp]
+        L.hc_row_words.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hc_rank_pair.restype = C.c_uint64
+        L.hc_rank_pair.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
         L.hc_destroy.argtypes = [C.c_void_p]
         L.hc_rows.restype = C.c_uint64
         L.hc_rows.argtypes = [C.c_void_p]
@@ -57,6 +61,9 @@ class HostModel:
         self.h = lib().hc_create(c["model"], c["nsite"], c["orbitals"], c["nup"], c["ndown"], _p(hop), _p(jzz), _p(U),
                                  0 if U is None else U.size, _p(V), 0 if V is None else V.size, _p(D),
                                  0 if D is None else D.size, c.get("feas_u3_all_pairs", 1), use_tables)
+        if c["model"] == 3:
+            self._keep_tj = [_f(c.get("jpm")), _f(c.get("w"))]
+            lib().hc_set_tj(self.h, _p(self._keep_tj[0]), _p(self._keep_tj[1]))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -73,6 +80,14 @@ class HostModel:
 
     def rank(self, spin, w):
         return lib().hc_rank(self.h, spin, int(w))
+
+    def row_words(self, spin):
+        out = np.zeros(self.rows(), dtype=np.uint64)
+        lib().hc_row_words(self.h, spin, out.ctypes.data)
+        return out
+
+    def rank_pair(self, k1, k2):
+        return lib().hc_rank_pair(self.h, int(k1), int(k2))
 
     def crs(self):
         nnz = lib().hc_crs(self.h, None, None, None)

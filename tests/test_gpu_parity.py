@@ -330,3 +330,61 @@ def test_apply_op_matches_reference_fixture(lpp, name):
         seen += 1
     assert seen >= 8
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Tj1Orbital (TjMultiOrb.h with Orbitals=1): basis built on the device in closed form, stored CRS (the reference's path for
+# this model) and the generic on-the-fly kernel
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(cases.TJ_CASES))
+def test_tj_matches_reference_fixture(lpp, oracle, name):
+    from tests import golden_util as gu
+    case = cases.TJ_CASES[name]
+    g = gu.load(name, case)
+    e = cases.make_engine(lpp, case)
+    assert e.rows() == int(g["rows"])
+    up, dn = e.row_words()
+    assert np.array_equal(up, g["up_words"]) and np.array_equal(dn, g["dn_words"])          # bit-exact order
+    assert np.array_equal(e.perfectIndexPairs(up, dn), np.arange(e.rows(), dtype=np.uint64))
+    rp, ci, v = e.setupHamiltonian()
+    gu.check_crs(g, rp, ci, v)                                                               # rowptr / colind bit-exact
+    y = geo.splitmix64_vector(e.rows(), gu.Y_SEED)
+    for k in (lpp.KERNEL_GENERIC, lpp.KERNEL_STORED, lpp.KERNEL_AUTO):
+        x = np.zeros(e.rows())
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, g["x_stored"]) <= 1e-13, (name, k)
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["tj8_V", "tj_3x3", "tj7_rand"])
+def test_tj_lanczos_energy(lpp, oracle, name):
+    case = cases.TJ_CASES[name]
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 1234)
+    e0, _, a0, b0 = o.ground_state(init, 200, 1e-12, 4)
+    for k in (lpp.KERNEL_GENERIC, lpp.KERNEL_STORED):
+        e = cases.make_engine(lpp, case, kernel=k)
+        e1, _, a1, b1 = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=200, eps=1e-12, minsteps=4)).computeOneState(
+            init, want_vector=False)
+        assert abs(e1 - e0) <= 1e-10 * max(1.0, abs(e0)), (name, k)
+        n = min(len(a0), len(a1), 20)
+        assert relerr(a1[:n], a0[:n]) <= 1e-10 and relerr(b1[:n], b0[:n]) <= 1e-10
+        e.close()
+
+
+def test_tj_medium_size_vs_oracle(lpp, oracle):
+    """4x4 lattice with two holes (7 up, 7 down): dim 16!/(7! 7! 2!) = 411 840; product's closed-form rank vs the oracle's search."""
+    case = cases.tj_square(4, 4, 7, 7)
+    o = cases.make_oracle(oracle, case)
+    e = cases.make_engine(lpp, case)
+    assert e.rows() == o.rows() == 411840
+    up, dn = e.row_words()
+    assert np.array_equal(up, o.row_words(0)) and np.array_equal(dn, o.row_words(1))
+    y = geo.splitmix64_vector(o.rows(), 42)
+    xref = np.zeros(o.rows())
+    o.matvec(xref, y, faithful=False)
+    for k in (lpp.KERNEL_GENERIC, lpp.KERNEL_STORED):
+        x = np.zeros(o.rows())
+        e.matrixVectorProduct(x, y, kernel=k)
+        assert relerr(x, xref) <= 1e-13, k
+    e.close()

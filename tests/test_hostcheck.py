@@ -34,6 +34,38 @@ def test_basis_rank_crs_matvec(oracle, name, tables):
     assert np.abs(x0 - x1).max() <= 1e-13 * max(1.0, np.abs(x0).max())
 
 
+@pytest.mark.parametrize("name", sorted(cases.TJ_CASES))
+@pytest.mark.parametrize("tables", [0, 1])
+def test_tj_basis_rank_crs_matvec(oracle, name, tables):
+    """Tj1Orbital: closed-form basis / rank of the product's code against the literal restatement (sorted combined words)."""
+    case = cases.TJ_CASES[name]
+    o = cases.make_oracle(oracle, case)
+    h = HostModel(case, use_tables=tables)
+    assert h.rows() == o.rows()
+    w1, w2 = o.row_words(0), o.row_words(1)
+    assert np.array_equal(h.row_words(0), w1) and np.array_equal(h.row_words(1), w2)   # bit-exact ordering
+    for i in range(0, len(w1), max(1, len(w1) // 97)):
+        assert h.rank_pair(w1[i], w2[i]) == i == o.perfect_index(w1[i], w2[i])
+    rp0, ci0, v0 = o.crs()
+    rp1, ci1, v1 = h.crs()
+    assert np.array_equal(rp0, rp1) and np.array_equal(ci0, ci1)
+    assert np.abs(v0 - v1).max() <= 1e-14 * max(1.0, np.abs(v0).max())
+    y = geo.splitmix64_vector(o.rows(), 42)
+    x0 = geo.splitmix64_vector(o.rows(), 7)
+    x1 = x0.copy()
+    o.matvec(x0, y, faithful=True)
+    h.matvec(x1, y)
+    assert np.abs(x0 - x1).max() <= 1e-13 * max(1.0, np.abs(x0).max())
+
+
+def test_tj_larger_basis_bit_exact(oracle):
+    case = cases.tj_square(4, 3, 5, 4)          # 12 sites, 3 holes: dim 27 720
+    o = cases.make_oracle(oracle, case)
+    h = HostModel(case, use_tables=1)
+    assert h.rows() == o.rows() == 27720
+    assert np.array_equal(h.row_words(0), o.row_words(0)) and np.array_equal(h.row_words(1), o.row_words(1))
+
+
 def test_bigger_bases_bit_exact(oracle):
     for case in (cases.hubbard_square(4, 4, 8, 8), cases.feas_cluster(2, 4, 6, 6), cases.heisenberg_ring(16, 8),
                  cases.hubbard_chain(18, 9, 9)):

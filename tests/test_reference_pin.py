@@ -19,13 +19,16 @@ MEDIUM = {
     "feas_input100_small": cases.feas_chain(4, 4, 4),
     "feas_2x2_quirk": dict(cases.feas_cluster(2, 2, 2, 3), feas_u3_all_pairs=0),
     "heis14": cases.heisenberg_ring(14, 7),
+    "tj10": cases.tj_chain(10, 4, 4, periodic=True),
+    "tj_4x3": cases.tj_square(4, 3, 5, 4),
+    "tj9_rand": cases.tj_chain(9, 3, 4, seed=11),
 }
 
 
 def make_reference(case):
     return reference.ReferenceModel(case["model"], case["nsite"], case["nup"], case["ndown"], case["orbitals"],
                                     hop=case.get("hop"), jzz=case.get("jzz"), U=case.get("U"), V=case.get("V"),
-                                    D=case.get("D"))
+                                    D=case.get("D"), jpm=case.get("jpm"), w=case.get("w"))
 
 
 @pytest.mark.parametrize("name", sorted(MEDIUM))
@@ -37,7 +40,9 @@ def test_oracle_vs_live_reference(oracle, name):
     assert o.rows() == n
     w1, w2 = r.row_words(0), r.row_words(1)
     b1 = o.basis(0)
-    if case["model"] == cases.HEISENBERG:
+    if case["model"] == cases.TJ:
+        assert np.array_equal(w1, o.row_words(0)) and np.array_equal(w2, o.row_words(1))
+    elif case["model"] == cases.HEISENBERG:
         assert np.array_equal(w1, b1)
     else:
         b2 = o.basis(1)
@@ -47,7 +52,7 @@ def test_oracle_vs_live_reference(oracle, name):
     rp, ci, v = r.crs()
     rp0, ci0, v0 = o.crs()
     assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0) and np.array_equal(v, v0)
-    if case["model"] != cases.HEISENBERG:
+    if case["model"] not in (cases.HEISENBERG, cases.TJ):
         y = geo.splitmix64_vector(n, 3)
         x = geo.splitmix64_vector(n, 4)
         x0 = x.copy()

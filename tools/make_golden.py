@@ -2,7 +2,8 @@
 
 Run here (needs /root/reference to build oracle/_ref):  python tools/make_golden.py
 Every fixture holds, for one case of tests/cases.py::SMALL_CASES:
-  up_words, dn_words        one-spin bases in the reference's order (BasisOneSpin / BasisOneSpinFeAs / BasisHeisenberg)
+  up_words, dn_words        one-spin bases in the reference's order (BasisOneSpin / BasisOneSpinFeAs / BasisHeisenberg);
+                            for Tj1Orbital (not a product basis): basis(i, SPIN_UP), basis(i, SPIN_DOWN) of every row
   nnz, rowptr, colind, values   the stored Hamiltonian of model.setupHamiltonian (full arrays when nnz <= 50 000, else
                             sha256 digests of the int64 rowptr/colind arrays plus sum / abs-sum of the values)
   x_otf                     x = 0 + H y through model.matrixVectorProduct (on-the-fly path; absent for Heisenberg)
@@ -43,12 +44,12 @@ def inputs_digest(case):
 def make_reference(case):
     return ref.ReferenceModel(case["model"], case["nsite"], case["nup"], case["ndown"], case["orbitals"],
                               hop=case.get("hop"), jzz=case.get("jzz"), U=case.get("U"), V=case.get("V"),
-                              D=case.get("D"))
+                              D=case.get("D"), jpm=case.get("jpm"), w=case.get("w"))
 
 
 def op_list(case):
     """(op, site, spin, orb) tuples exercised per model (fermionic c / cdagger; both spins: quirk C.3 lives in spin 1)."""
-    if case["model"] == cases.HEISENBERG:
+    if case["model"] in (cases.HEISENBERG, cases.TJ):
         return []
     n = case["nsite"]
     sites = sorted({0, n // 2, n - 1})
@@ -67,6 +68,8 @@ def generate(name, case):
     w1, w2 = r.row_words(0), r.row_words(1)
     if case["model"] == cases.HEISENBERG:
         up, dn = w1, np.zeros(0, dtype=np.uint64)
+    elif case["model"] == cases.TJ:            # not a product basis: the fixture keeps basis(i, spin) for every row
+        up, dn = w1, w2
     else:
         n1 = int(np.argmax(w2 != w2[0])) if np.any(w2 != w2[0]) else n
         up, dn = w1[:n1].copy(), w2[::n1].copy()
@@ -80,7 +83,7 @@ def generate(name, case):
     xs = np.zeros(n)
     np.add.at(xs, np.repeat(np.arange(n), np.diff(rowptr)), values * y[colind])
     out["x_stored"] = xs
-    if case["model"] != cases.HEISENBERG:
+    if case["model"] not in (cases.HEISENBERG, cases.TJ):     # these two have no on-the-fly product in the reference
         x = np.zeros(n)
         r.matvec(x, y)
         out["x_otf"] = x
@@ -108,7 +111,7 @@ def main():
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
     total = 0
-    for name, case in cases.SMALL_CASES.items():
+    for name, case in list(cases.SMALL_CASES.items()) + list(cases.TJ_CASES.items()):
         data = generate(name, case)
         path = os.path.join(gdir, name + ".npz")
         np.savez_compressed(path, **data)
