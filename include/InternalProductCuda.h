@@ -15,13 +15,14 @@
  *
  * Requirements on ModelType beyond the reference's ModelBase (three one-line accessors):
  *   const ParametersModelType& params() const;     // hubbardU / potentialV / orbitals / anisotropyD ...
- *   static int cudaModelId();                       // LPP_MODEL_HUBBARD | LPP_MODEL_FEAS | LPP_MODEL_HEISENBERG
+ *   static int cudaModelId();                       // LPP_MODEL_HUBBARD | LPP_MODEL_FEAS | LPP_MODEL_HEISENBERG | LPP_MODEL_TJ
  */
 #ifndef INTERNALPRODUCT_CUDA_H
 #define INTERNALPRODUCT_CUDA_H
 
 #include <vector>
 #include <cassert>
+#include <cstring>
 #include "Vector.h"
 #include "Matrix.h"
 #include "lpp_b200.h"
@@ -146,7 +147,7 @@ private:
 
 		// term 0 (and term 1 for Heisenberg): the values the models read through geometry_(i,orb,j,orb2,term)
 		// HubbardHelper.h:60-71 ; FeBasedSc.h:320-323 ; Heisenberg.h:54-58
-		std::vector<double> hop(nb*nb, 0.0), jzz;
+		std::vector<double> hop(nb*nb, 0.0), jzz, jpm, w;
 		for (SizeType i = 0; i < nsite; ++i)
 			for (SizeType o1 = 0; o1 < orbitals; ++o1)
 				for (SizeType j = 0; j < nsite; ++j)
@@ -159,9 +160,20 @@ private:
 					jzz[i*nb + j] = geometry(i, 0, j, 0, 1);
 		}
 
+		if (modelId == LPP_MODEL_TJ) {       // TjMultiOrb.h:68-79: terms 1, 2, 3 = S+S-, SzSz, n n couplings
+			jpm.resize(nb*nb, 0.0); jzz.resize(nb*nb, 0.0); w.resize(nb*nb, 0.0);
+			for (SizeType i = 0; i < nsite; ++i)
+				for (SizeType j = 0; j < nsite; ++j) {
+					jpm[i*nb + j] = geometry(i, 0, j, 0, 1);
+					jzz[i*nb + j] = geometry(i, 0, j, 0, 2);
+					w[i*nb + j] = geometry(i, 0, j, 0, 3);
+				}
+		}
+
 		typename ProgramGlobals::PairIntType parts = basis_.parts();   // (nup, ndown) or (twiceS, szPlusConst)
 
 		lpp_desc d;
+		std::memset(&d, 0, sizeof(d));
 		d.model = modelId;
 		d.nsite = nsite;
 		d.orbitals = orbitals;
@@ -170,6 +182,8 @@ private:
 		d.feas_u3_all_pairs = 1;
 		d.hop = &(hop[0]);
 		d.jzz = jzz.size() ? &(jzz[0]) : 0;
+		d.jpm = jpm.size() ? &(jpm[0]) : 0;
+		d.w = w.size() ? &(w[0]) : 0;
 		model_.params().exportForCuda(d);   // fills U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy
 		d.device = 0;
 		d.rank = 0;
