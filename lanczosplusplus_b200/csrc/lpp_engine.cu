@@ -844,6 +844,27 @@ static int reduce_scalar(lpp_handle* h, int npartials, double* out)
 	return 0;
 }
 
+// nv sums at once: partials laid out [nv][npartials]
+static int reduce_scalars(lpp_handle* h, int npartials, int nv, double* out)
+{
+	lpp_launch_finalize_sums(h->partials, npartials, nv, h->scal_dev, h->stream);
+	h->launches += 1;
+	cudaStream_t cs = h->stream;
+	if (h->desc.nranks > 1) {
+		if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
+		if (h->comm_stream && !h->p2p) {
+			cs = h->comm_stream;
+			CK(cudaEventRecord(h->ev_scal, h->stream));
+			CK(cudaStreamWaitEvent(cs, h->ev_scal, 0));
+		}
+		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, nv, kNcclFloat64, kNcclSum, h->comm, cs));
+	}
+	CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, sizeof(double) * nv, cudaMemcpyDeviceToHost, cs));
+	CK(cudaStreamSynchronize(cs));
+	for (int k = 0; k < nv; k++) out[k] = h->scal_host[k];
+	return 0;
+}
+
 // ------------------------------------------------------------------ two-layout sharded SpMV
 static int ensure_two_layout(lpp_handle* h, int kernel)
 {
@@ -1088,9 +1109,29 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	if (!(nrm2 > 0)) return fail(LPP_ERR_ARG, "initial Lanczos vector has zero norm");
 	double nj = sqrt(nrm2), nprev = 1.0, bprev = 0.0, eold = 100.0;
 	if ((uint64_t)steps > h->rows) steps = (int)h->rows;
+	// <prefix>Options=reortho: every Lanczos vector is kept on the device (un-normalised U_k with its squared norm) and the new
+	// vector is orthogonalised against all of them after x -= a y; freed when the loop ends
+	struct SavedVectors {
+		std::vector<double*> v;
+		std::vector<double> n2;
+		~SavedVectors() { for (double* q : v) cudaFree(q); }
+	} saved;
+	const bool reortho = p->reortho != 0;
+	const int npro = lpp_vec_blocks(n * 2);
+	if (reortho) CKR(ensure_partials(h, std::max(np, npro * LPP_RO_NV)));
 	int j = 0;
 	for (; j < steps; j++) {
 		if (tm && j == tm->from) { CK(cudaEventRecord(h->ev0, h->stream)); tm->launches_at_from = h->launches; }
+		if (reortho) {
+			double* keep = nullptr;
+			if (cudaMalloc((void**)&keep, sizeof(double) * std::max<uint64_t>(n, 1)) != cudaSuccess) {
+				cudaGetLastError();
+				return fail(LPP_ERR_CUDA, "reortho: out of device memory for the saved Lanczos vectors (steps x rows x 8 bytes)");
+			}
+			saved.v.push_back(keep);
+			saved.n2.push_back(nj * nj);
+			CK(cudaMemcpyAsync(keep, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+		}
 		if (zcoef) { lpp_launch_axpy(z, y, zcoef[j] / nj, n, h->stream); h->launches += 1; }
 		double dot = 0;
 		const bool fuse_unpack = h->two_layout == 1 && h->p2p;
@@ -1123,6 +1164,21 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 		double b2 = 0;
 		CKR(reduce_scalar(h, npb, &b2));
 		if (fuse_unpack) { phase_mark(h, 6, h->stream); phase_collect(h, 6); }   // 5->6 reduce + all-reduce #3
+		if (reortho) {
+			for (size_t k0 = 0; k0 < saved.v.size(); k0 += LPP_RO_NV) {
+				RoVecs r;
+				r.nv = (int)std::min<size_t>(LPP_RO_NV, saved.v.size() - k0);
+				for (int k = 0; k < LPP_RO_NV; k++) { r.v[k] = saved.v[k0 + std::min(k, r.nv - 1)]; r.coef[k] = 0.0; }
+				double dots[LPP_RO_NV];
+				lpp_launch_reortho_dots(x, r, n, h->partials, h->stream);
+				h->launches += 1;
+				CKR(reduce_scalars(h, npro, r.nv, dots));
+				for (int k = 0; k < r.nv; k++) r.coef[k] = dots[k] / saved.n2[k0 + k];
+				lpp_launch_reortho_axpy_norm(x, r, n, h->partials, h->stream);
+				h->launches += 1;
+			}
+			CKR(reduce_scalar(h, npro, &b2));
+		}
 		double bj = sqrt(b2);
 		a[j] = aj;
 		b[j] = bj;

@@ -527,6 +527,60 @@ __global__ void __launch_bounds__(1024) k_finalize_sum(const double* __restrict_
 	if (threadIdx.x == 0) out[0] = s;
 }
 
+// full reorthogonalisation (<prefix>Options=reortho), classical Gram-Schmidt against a block of saved Lanczos vectors:
+// one pass computes the block's dot products with x, one pass subtracts the projections and accumulates |x|^2
+__global__ void __launch_bounds__(LPP_TPB) k_reortho_dots(const double* __restrict__ x, RoVecs r, uint64_t n, double* __restrict__ partials)
+{
+	double s[LPP_RO_NV];
+#pragma unroll
+	for (int k = 0; k < LPP_RO_NV; k++) s[k] = 0.0;
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LPP_TPB) {
+		const double xi = x[i];
+#pragma unroll
+		for (int k = 0; k < LPP_RO_NV; k++)
+			if (k < r.nv) s[k] += r.v[k][i] * xi;
+	}
+#pragma unroll
+	for (int k = 0; k < LPP_RO_NV; k++) {
+		const double t = lpp_block_sum(s[k]);
+		if (threadIdx.x == 0) partials[(uint64_t)k * gridDim.x + blockIdx.x] = t;
+	}
+}
+__global__ void __launch_bounds__(LPP_TPB) k_reortho_axpy_norm(double* __restrict__ x, RoVecs r, uint64_t n, double* __restrict__ partials)
+{
+	double s = 0.0;
+	for (uint64_t i = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; i < n; i += (uint64_t)gridDim.x * LPP_TPB) {
+		double t = x[i];
+#pragma unroll
+		for (int k = 0; k < LPP_RO_NV; k++)
+			if (k < r.nv) t -= r.coef[k] * r.v[k][i];
+		x[i] = t;
+		s += t * t;
+	}
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// out[k] = sum of the k-th row of partials[nv][n]
+__global__ void __launch_bounds__(1024) k_finalize_sums(const double* __restrict__ partials, int n, double* __restrict__ out)
+{
+	double s = 0.0;
+	for (int i = threadIdx.x; i < n; i += 1024) s += partials[(uint64_t)blockIdx.x * n + i];
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+void lpp_launch_reortho_dots(const double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s)
+{
+	k_reortho_dots<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(x, r, n, partials);
+}
+void lpp_launch_reortho_axpy_norm(double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s)
+{
+	k_reortho_axpy_norm<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(x, r, n, partials);
+}
+void lpp_launch_finalize_sums(const double* partials, int n, int nv, double* out, cudaStream_t s)
+{
+	k_finalize_sums<<<nv, 1024, 0, s>>>(partials, n, out);
+}
+
 void lpp_launch_fill_random(double* v, uint64_t row0, uint64_t n, uint64_t seed, cudaStream_t s)
 {
 	k_fill_random<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(v, row0, n, seed);

@@ -29,6 +29,15 @@ struct SpmvArgs {
 	uint64_t row0, nloc;     // first global row and number of local rows
 };
 
+#define LPP_RO_NV 4
+struct RoVecs {              // a block of saved Lanczos vectors and the projections to subtract
+	const double* v[LPP_RO_NV];
+	double coef[LPP_RO_NV];
+	int nv;
+};
+void lpp_launch_reortho_dots(const double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_reortho_axpy_norm(double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_finalize_sums(const double* partials, int n, int nv, double* out, cudaStream_t s);
 void lpp_launch_build_colex(const uint64_t* binom, int nsite, int npart, uint64_t n, word_t* out, cudaStream_t s);
 void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out, cudaStream_t s);
 void lpp_launch_rank(const ModelDev& m, int spin, const word_t* w, uint64_t n, uint64_t* out, cudaStream_t s);

@@ -203,13 +203,14 @@ def comm_unique_id():
 
 
 class ParametersForSolver:
-    """PsimagLite::ParametersForSolver(io, prefix): <prefix>Steps=, <prefix>Eps=, <prefix>MinSteps= (SURVEY App. B.1)."""
+    """PsimagLite::ParametersForSolver(io, prefix): <prefix>Steps=, <prefix>Eps=, <prefix>MinSteps=, <prefix>Options= (SURVEY App. B.1)."""
 
-    def __init__(self, io=None, prefix="Lanczos", steps=200, eps=1e-12, minsteps=4, seed=1234):
+    def __init__(self, io=None, prefix="Lanczos", steps=200, eps=1e-12, minsteps=4, seed=1234, options=""):
         io = io or {}
         self.steps = int(io.get(prefix + "Steps", steps))
         self.eps = float(io.get(prefix + "Eps", eps))
         self.minsteps = int(io.get(prefix + "MinSteps", minsteps))
+        self.options = str(io.get(prefix + "Options", options))     # "reortho": full reorthogonalisation, vectors saved on device
         self.seed = seed
 
 
@@ -222,7 +223,7 @@ class LanczosSolver:
 
     def _p(self):
         p = self.params
-        return SolverParams(p.steps, p.minsteps, p.eps, self.mat.kernel, 0, p.seed)
+        return SolverParams(p.steps, p.minsteps, p.eps, self.mat.kernel, 1 if "reortho" in p.options else 0, p.seed)
 
     def decomposition(self, init=None, use_modified=False):
         """-> (a, b, <init|init>) ; Engine.h:474-478."""

@@ -1184,6 +1184,82 @@ static void one_step(orc_mv_fn mv, void* ctx, int64_t n, double* x, double* y, d
 	*b_out = b;
 }
 
+/* <prefix>Options=reortho (PARITY UNPINNED: PsimagLite's own routine is absent): after x -= a y the new
+ * vector is orthogonalised against every saved Lanczos vector v_0..v_j, classical Gram-Schmidt in blocks of 4 in basis order,
+ * and b is the norm of the result.  Same step with reorthogonalisation as one_step() above. */
+#define ORC_RO_NV 4
+static void one_step_reortho(orc_mv_fn mv, void* ctx, int64_t n, double* x, double* y, double** saved, int nsaved,
+                             double* a_out, double* b_out)
+{
+	mv(ctx, x, y);
+	double a = 0;
+#pragma omp parallel for reduction(+ : a) schedule(static)
+	for (int64_t i = 0; i < n; i++) a += y[i] * x[i];
+#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < n; i++) x[i] -= a * y[i];
+	for (int k0 = 0; k0 < nsaved; k0 += ORC_RO_NV) {
+		int nv = nsaved - k0 < ORC_RO_NV ? nsaved - k0 : ORC_RO_NV;
+		double c[ORC_RO_NV] = {0, 0, 0, 0};
+		for (int k = 0; k < nv; k++) {
+			double s = 0;
+			const double* v = saved[k0 + k];
+#pragma omp parallel for reduction(+ : s) schedule(static)
+			for (int64_t i = 0; i < n; i++) s += v[i] * x[i];
+			c[k] = s;
+		}
+#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < n; i++) {
+			double t = x[i];
+			for (int k = 0; k < nv; k++) t -= c[k] * saved[k0 + k][i];
+			x[i] = t;
+		}
+	}
+	double b = 0;
+#pragma omp parallel for reduction(+ : b) schedule(static)
+	for (int64_t i = 0; i < n; i++) b += x[i] * x[i];
+	b = sqrt(b);
+	const double div = (b < 1e-10) ? 1.0 : b;
+#pragma omp parallel for schedule(static)
+	for (int64_t i = 0; i < n; i++) {
+		double tmp = y[i];
+		y[i] = x[i] / div;
+		x[i] = -b * tmp;
+	}
+	*a_out = a;
+	*b_out = b;
+}
+
+/* decomposition with every Lanczos vector saved and full reorthogonalisation; returns the step count */
+int orc_lanczos_decomposition_reortho(const orc_model* m, const double* init, int steps, double eps, int minsteps,
+                                      double* a, double* b)
+{
+	mv_model_ctx c = {m, 0};
+	int64_t n = (int64_t)orc_rows(m);
+	double* x = (double*)calloc(n, sizeof(double));
+	double* y = (double*)malloc(sizeof(double) * n);
+	double nrm = 0;
+	for (int64_t i = 0; i < n; i++) nrm += init[i] * init[i];
+	nrm = sqrt(nrm);
+	for (int64_t i = 0; i < n; i++) y[i] = init[i] / nrm;
+	if (steps > n) steps = (int)n;
+	double** saved = (double**)calloc(steps > 0 ? steps : 1, sizeof(double*));
+	double eold = 100.0;
+	int j = 0;
+	for (; j < steps; j++) {
+		saved[j] = (double*)malloc(sizeof(double) * n);
+		memcpy(saved[j], y, sizeof(double) * n);
+		one_step_reortho(mv_model, &c, n, x, y, saved, j + 1, &a[j], &b[j]);
+		if (eps > 0) {
+			double enew = tridiag_lowest(j + 1, a, b);
+			if (fabs(enew - eold) < eps && (j >= minsteps || n <= 4)) { j++; break; }
+			eold = enew;
+		}
+	}
+	for (int k = 0; k < steps; k++) free(saved[k]);
+	free(saved); free(x); free(y);
+	return j;
+}
+
 /* PsimagLite LanczosSolver::decomposition.  If zcoef!=NULL (second pass, App. B.4)
  * accumulates z += zcoef[j] * v_j while replaying exactly nfixed steps. Returns the step count. */
 static int decomposition(orc_mv_fn mv, void* ctx, int64_t n, const double* init, int steps, double eps,

@@ -69,6 +69,9 @@ def lib():
         L.orc_lanczos_decomposition.restype = C.c_int
         L.orc_lanczos_decomposition.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int,
                                                 C.c_void_p, C.c_void_p]
+        L.orc_lanczos_decomposition_reortho.restype = C.c_int
+        L.orc_lanczos_decomposition_reortho.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                                                        C.c_void_p]
         L.orc_lanczos_decomposition_crs.restype = C.c_int
         L.orc_lanczos_decomposition_crs.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
@@ -204,6 +207,17 @@ class OracleModel:
         init = _f64(init)
         ns = lib().orc_lanczos_decomposition(self.h, 1 if faithful else 0, init.ctypes.data, steps, eps, minsteps,
                                              a.ctypes.data, b.ctypes.data)
+        return a[:ns].copy(), b[:ns].copy()
+
+    def decomposition_reortho(self, init, steps=200, eps=1e-12, minsteps=4):
+        """Lanczos decomposition with every vector saved and full reorthogonalisation (<prefix>Options=reortho)."""
+        n = self.rows()
+        cap = min(steps, n) + 1
+        a = np.zeros(cap)
+        b = np.zeros(cap)
+        init = _f64(init)
+        ns = lib().orc_lanczos_decomposition_reortho(self.h, init.ctypes.data, steps, eps, minsteps, a.ctypes.data,
+                                                     b.ctypes.data)
         return a[:ns].copy(), b[:ns].copy()
 
     def ground_state(self, init, steps=200, eps=1e-12, minsteps=4, want_vector=True, faithful=False):

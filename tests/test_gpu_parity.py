@@ -388,3 +388,58 @@ def test_tj_medium_size_vs_oracle(lpp, oracle):
         e.matrixVectorProduct(x, y, kernel=k)
         assert relerr(x, xref) <= 1e-13, k
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# <prefix>Options=reortho: every Lanczos vector saved on the device, full reorthogonalisation after x -= a y
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1_hub8", "feas4", "heis12", "tj8_V"])
+def test_reortho_matches_oracle_and_resolves_the_spectrum(lpp, oracle, name):
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    o = cases.make_oracle(oracle, case)
+    n = o.rows()
+    init = geo.splitmix64_vector(n, 99)
+    steps = min(n, 120)
+    a0, b0 = o.decomposition_reortho(init, steps=steps, eps=0.0)
+    e = cases.make_engine(lpp, case)
+    a1, b1, _ = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=steps, eps=0.0, options="reortho")).decomposition(init)
+    assert len(a1) == len(a0) == steps
+    # the map (H, v0) -> (a, b) is itself ill conditioned at late steps for clustered spectra (heis12): the first 40 steps are
+    # compared coefficient by coefficient, the whole run through its converged Ritz values
+    m = 40
+    assert relerr(a1[:m], a0[:m]) <= 1e-10 and relerr(b1[:m], b0[:m]) <= 1e-10
+    assert np.abs(lpp.tridiag_eig(a1, b1)[:5] - oracle.tridiag_eig(a0, b0)[:5]).max() <= 1e-9
+    # without it the same run drifts once the lowest Ritz values converge; with it the Ritz values are eigenvalues of H, once each
+    rp, ci, v = o.crs()
+    import scipy.sparse as sp
+    H = sp.csr_matrix((v, ci, rp), shape=(n, n)).toarray()
+    exact = np.linalg.eigvalsh(H) if n <= 1600 else None
+    ritz = lpp.tridiag_eig(a1, b1)
+    if exact is not None:
+        assert abs(ritz[0] - exact[0]) <= 1e-10 * max(1.0, abs(exact[0]))
+        conv = ritz[:5]
+        for r in conv:                                                # the lowest Ritz values sit on distinct eigenvalues: no ghosts
+            assert np.abs(exact - r).min() <= 1e-8
+        assert np.all(np.diff(conv) > 1e-9) or len(np.unique(np.round(exact[:8], 9))) < 8
+    e.close()
+
+
+def test_reortho_full_space_reproduces_all_eigenvalues(lpp, oracle):
+    """steps = dim on a small sector: only a recurrence that stays orthogonal yields the complete spectrum."""
+    case = cases.hubbard_chain(5, 2, 2, U=3.0)                        # dim 100
+    o = cases.make_oracle(oracle, case)
+    n = o.rows()
+    rp, ci, v = o.crs()
+    import scipy.sparse as sp
+    exact = np.linalg.eigvalsh(sp.csr_matrix((v, ci, rp), shape=(n, n)).toarray())
+    e = cases.make_engine(lpp, case)
+    init = geo.splitmix64_vector(n, 3)
+    a, b, _ = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=n, eps=0.0, options="reortho")).decomposition(init)
+    # the Krylov space of a random vector misses symmetry-degenerate copies: compare as sets of distinct values
+    k = int(np.argmax(b < 1e-8)) + 1 if np.any(b < 1e-8) else len(a)     # the Krylov space may close before dim steps
+    ritz = lpp.tridiag_eig(a[:k], b[:k])
+    distinct = np.unique(np.round(exact, 8))
+    for r in ritz:
+        assert np.abs(distinct - r).min() <= 1e-8
+    assert len(ritz) >= 0.5 * len(distinct)
+    e.close()
