@@ -4,10 +4,10 @@
 // read the input file, build the geometry's connection matrix, construct the model sector, run the Lanczos ground
 // state, print "Energy=".  Only the subset of the PsimagLite InputNg format used by the configs is understood:
 //   TotalNumberOfSites= NumberOfTerms= GeometryKind=chain|ladder GeometryOptions=ConstantValues IsPeriodicX= LadderLeg=
-//   Connectors ... (one block per geometry direction/term, in file order)   Model=HubbardOneBand|FeAsBasedSc|Heisenberg
+//   Connectors ... (one block per geometry direction/term, in file order)   Model=HubbardOneBand|FeAsBasedSc|Heisenberg|Tj1Orbital
 //   hubbardU / potentialV / MagneticField / AnisotropyD vectors   Orbitals= FeAsMode=INT_PAPER33
 //   TargetElectronsUp= TargetElectronsDown= TargetSzPlusConst= HeisenbergTwiceS=1
-//   SolverOptions= (InternalProductCuda | InternalProductStored)  LanczosSteps= LanczosEps= LanczosMinSteps= Threads=(ignored)
+//   SolverOptions= (InternalProductCuda | InternalProductStored)  LanczosSteps= LanczosEps= LanczosMinSteps= LanczosOptions=reortho Threads=(ignored)
 // Usage: lanczos_b200 -f input.inp [-p precision] [--parse-only]
 #include <cmath>
 #include <cstdio>
@@ -158,7 +158,7 @@ int main(int argc, char** argv)
 		memset(&d, 0, sizeof(d));
 		d.nsite = geti(in, "TotalNumberOfSites", 0, true);
 		d.orbitals = 1;
-		std::vector<double> U, V, D, jzz;
+		std::vector<double> U, V, D, jzz, jpm, w;
 		if (in.vectors.count("hubbardU")) U = in.vectors["hubbardU"][0];
 		if (in.vectors.count("potentialV")) V = in.vectors["potentialV"][0];
 		if (model == "HubbardOneBand") {
@@ -179,6 +179,15 @@ int main(int argc, char** argv)
 			if (in.vectors.count("MagneticField")) V = in.vectors["MagneticField"][0];
 			if (in.vectors.count("AnisotropyD")) D = in.vectors["AnisotropyD"][0];
 			jzz = connection_matrix(in, d.nsite, 1, 1);
+		} else if (model == "Tj1Orbital" || model == "TjMultiOrb") {
+			// TjMultiOrb.h:52-80: four geometry terms (hopping, S+S-, SzSz, n n); Orbitals=1 only
+			d.model = LPP_MODEL_TJ;
+			if (geti(in, "Orbitals", 1) != 1) throw std::runtime_error("t-J: only Orbitals=1 is on the path");
+			d.nup = geti(in, "TargetElectronsUp", 0, true);
+			d.ndown = geti(in, "TargetElectronsDown", 0, true);
+			jpm = connection_matrix(in, d.nsite, 1, 1);
+			jzz = connection_matrix(in, d.nsite, 1, 2);
+			w = connection_matrix(in, d.nsite, 1, 3);
 		} else {
 			throw std::runtime_error("Model=" + model + " is not on the accelerated path");
 		}
@@ -186,6 +195,8 @@ int main(int argc, char** argv)
 		d.feas_u3_all_pairs = 1;
 		d.hop = hop.data();
 		d.jzz = jzz.empty() ? nullptr : jzz.data();
+		d.jpm = jpm.empty() ? nullptr : jpm.data();
+		d.w = w.empty() ? nullptr : w.data();
 		d.U = U.empty() ? nullptr : U.data(); d.nU = (int)U.size();
 		d.V = V.empty() ? nullptr : V.data(); d.nV = (int)V.size();
 		d.D = D.empty() ? nullptr : D.data(); d.nD = (int)D.size();
@@ -196,7 +207,7 @@ int main(int argc, char** argv)
 		p.minsteps = geti(in, "LanczosMinSteps", 4);
 		p.eps = getd(in, "LanczosEps", 1e-12);
 		p.kernel = opts.find("InternalProductStored") != std::string::npos ? LPP_KERNEL_STORED : LPP_KERNEL_AUTO;
-		p.reortho = 0;
+		p.reortho = gets(in, "LanczosOptions", "none").find("reortho") != std::string::npos ? 1 : 0;
 		p.seed = 1234;
 		if (parse_only) {
 			std::cout << "model=" << d.model << " nsite=" << d.nsite << " orbitals=" << d.orbitals << " nup=" << d.nup
