@@ -8,14 +8,15 @@
  * fullDiag().  All arithmetic happens in liblpp_b200.so (include/lpp_b200.h); this header only marshals the
  * model description and converts status codes into the reference's err() exceptions.
  *
- * Compiles inside the reference tree (needs PsimagLite for SizeType, err(), Vector.h, Matrix.h); it is NOT
- * compiled in this repository because PsimagLite is not available here.  The standalone
- * equivalent used by this repository's own driver and tests is lanczosplusplus_b200/engine.py +
- * host/lanczos_b200.cpp, which call the same C-ABI.
+ * Compiles inside the reference tree (needs PsimagLite for SizeType, err(), Vector.h, Matrix.h).  In this repository it is
+ * compiled against the reference's own Engine/Model headers and the PsimagLite stand-in of oracle/psimag_shim by
+ * tests/adapter_check.cpp (built into oracle/_ref/adapter_check), which runs it side by side with the reference's
+ * InternalProductOnTheFly and InternalProductStored on the same models.
  *
- * Requirements on ModelType beyond the reference's ModelBase (three one-line accessors):
- *   const ParametersModelType& params() const;     // hubbardU / potentialV / orbitals / anisotropyD ...
- *   static int cudaModelId();                       // LPP_MODEL_HUBBARD | LPP_MODEL_FEAS | LPP_MODEL_HEISENBERG | LPP_MODEL_TJ
+ * Requirements on ModelType beyond the reference's ModelBase: two virtual functions added to Engine/ModelBase.h and
+ * overridden by the four models on the path:
+ *   virtual int cudaModelId() const;                  // LPP_MODEL_HUBBARD | LPP_MODEL_FEAS | LPP_MODEL_HEISENBERG | LPP_MODEL_TJ
+ *   virtual void exportForCuda(lpp_desc& d) const;    // U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy (mp_ is private)
  */
 #ifndef INTERNALPRODUCT_CUDA_H
 #define INTERNALPRODUCT_CUDA_H
@@ -141,7 +142,7 @@ private:
 
 		const GeometryType& geometry = model_.geometry();
 		const SizeType nsite = geometry.numberOfSites();
-		const int modelId = ModelType::cudaModelId();
+		const int modelId = model_.cudaModelId();
 		const SizeType orbitals = (modelId == LPP_MODEL_FEAS) ? model_.orbitals(0) : 1;
 		const SizeType nb = nsite*orbitals;
 
@@ -184,7 +185,7 @@ private:
 		d.jzz = jzz.size() ? &(jzz[0]) : 0;
 		d.jpm = jpm.size() ? &(jpm[0]) : 0;
 		d.w = w.size() ? &(w[0]) : 0;
-		model_.params().exportForCuda(d);   // fills U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy
+		model_.exportForCuda(d);            // fills U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy
 		d.device = 0;
 		d.rank = 0;
 		d.nranks = 1;

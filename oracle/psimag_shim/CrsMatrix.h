@@ -51,6 +51,17 @@ private:
 	std::vector<SizeType> rowptr_, colind_;
 	std::vector<T> values_;
 };
+// isHermitian(A [, verbose]) as the models assert it after setupHamiltonian
+template <typename T> bool isHermitian(const CrsMatrix<T>& a, bool = false)
+{
+	if (a.rows() != a.cols()) return false;
+	const Matrix<T> d = a.toDense();
+	for (SizeType i = 0; i < d.n_row(); ++i)
+		for (SizeType j = i + 1; j < d.n_col(); ++j)
+			if (std::abs(d(i, j) - conj(d(j, i))) > 1e-12) return false;
+	return true;
+}
+
 // C = A^dagger and C = A B: only the JHundInfinity=1 branch of TjMultiOrb.h (two orbitals, out of scope) and
 // ProgramGlobals::transform reach these; they exist so that the reference headers compile
 template <typename T> void transposeConjugate(CrsMatrix<T>& c, const CrsMatrix<T>& a)

@@ -32,5 +32,51 @@ template <typename T> std::ostream& operator<<(std::ostream& os, const Matrix<T>
 	}
 	return os;
 }
+// diag(m, eigs, 'V'): eigenvalues ascending, eigenvectors in the columns of m.  PsimagLite calls LAPACK; the stand-in is a
+// cyclic Jacobi iteration (only DefaultSymmetry::fullDiag reaches it, for matrices up to 4900 rows).
+template <typename T> void diag(Matrix<T>& m, std::vector<T>& eigs, char)
+{
+	const SizeType n = m.n_row();
+	Matrix<T> v(n, n);
+	for (SizeType i = 0; i < n; ++i) v(i, i) = 1;
+	for (int sweep = 0; sweep < 100; ++sweep) {
+		T off = 0;
+		for (SizeType p = 0; p < n; ++p)
+			for (SizeType q = p + 1; q < n; ++q) off += m(p, q) * m(p, q);
+		if (off < 1e-26) break;
+		for (SizeType p = 0; p < n; ++p)
+			for (SizeType q = p + 1; q < n; ++q) {
+				if (std::abs(m(p, q)) < 1e-300) continue;
+				const T theta = (m(q, q) - m(p, p)) / (2 * m(p, q));
+				const T t = (theta >= 0 ? 1 : -1) / (std::abs(theta) + std::sqrt(theta * theta + 1));
+				const T c = 1 / std::sqrt(t * t + 1), s = t * c;
+				for (SizeType k = 0; k < n; ++k) {
+					const T a = m(k, p), b = m(k, q);
+					m(k, p) = c * a - s * b;
+					m(k, q) = s * a + c * b;
+				}
+				for (SizeType k = 0; k < n; ++k) {
+					const T a = m(p, k), b = m(q, k);
+					m(p, k) = c * a - s * b;
+					m(q, k) = s * a + c * b;
+				}
+				for (SizeType k = 0; k < n; ++k) {
+					const T a = v(k, p), b = v(k, q);
+					v(k, p) = c * a - s * b;
+					v(k, q) = s * a + c * b;
+				}
+			}
+	}
+	std::vector<SizeType> order(n);
+	for (SizeType i = 0; i < n; ++i) order[i] = i;
+	std::sort(order.begin(), order.end(), [&m](SizeType a, SizeType b) { return m(a, a) < m(b, b); });
+	eigs.resize(n);
+	Matrix<T> out(n, n);
+	for (SizeType j = 0; j < n; ++j) {
+		eigs[j] = m(order[j], order[j]);
+		for (SizeType i = 0; i < n; ++i) out(i, j) = v(i, order[j]);
+	}
+	m = out;
+}
 } // namespace PsimagLite
 #endif

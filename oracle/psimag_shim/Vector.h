@@ -31,6 +31,9 @@ template <typename T> struct Vector { typedef std::vector<T> Type; };
 template <typename T> struct IsVectorLike { enum { True = false }; };
 template <typename T> struct IsVectorLike<std::vector<T> > { enum { True = true }; };
 
+template <typename A, typename B> struct IsSame { enum { True = false }; };
+template <typename A> struct IsSame<A, A> { enum { True = true }; };
+
 template <bool B, typename T> struct EnableIf {};
 template <typename T> struct EnableIf<true, T> { typedef T Type; };
 

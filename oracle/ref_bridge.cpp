@@ -27,23 +27,6 @@
 #include "Matrix.h"
 #include "CrsMatrix.h"
 
-namespace PsimagLite {
-// Heisenberg.h:122 asserts isHermitian(matrix); found by argument-dependent lookup
-template <typename T> bool isHermitian(const CrsMatrix<T>& m)
-{
-	if (m.rows() != m.cols()) return false;
-	std::map<std::pair<SizeType, SizeType>, T> e;
-	for (SizeType i = 0; i < m.rows(); ++i)
-		for (SizeType k = m.getRowPtr(i); k < m.getRowPtr(i + 1); ++k) e[std::make_pair(i, m.getCol(k))] += m.getValue(k);
-	for (auto& kv : e) {
-		auto it = e.find(std::make_pair(kv.first.second, kv.first.first));
-		const T other = (it == e.end()) ? T(0) : it->second;
-		if (std::abs(kv.second - other) > 1e-12) return false;
-	}
-	return true;
-}
-} // namespace PsimagLite
-
 #include "ProgramGlobals.h"
 #include "HubbardOneOrbital.h"
 #include "BasisFeAsBasedSc.h"

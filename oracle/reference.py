@@ -14,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_ref", "liblpp_ref.so")
+ADAPTER_CHECK = os.path.join(_HERE, "_ref", "adapter_check")
 REFERENCE_SRC = "/root/reference/src"
 
 HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
@@ -31,6 +32,11 @@ def build(force=False):
                                                           for f in os.listdir(os.path.join(_HERE, "psimag_shim"))
                                                           if f.endswith(".h")]
         stale = not os.path.exists(_LIB) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in srcs)
+        adapter_srcs = srcs[1:] + [os.path.join(_HERE, "..", "tests", "adapter_check.cpp"),
+                                   os.path.join(_HERE, "..", "include", "InternalProductCuda.h"),
+                                   os.path.join(_HERE, "..", "include", "lpp_b200.h")]
+        stale = stale or not os.path.exists(ADAPTER_CHECK) or any(os.path.getmtime(s) > os.path.getmtime(ADAPTER_CHECK)
+                                                                  for s in adapter_srcs)
         if force or stale:
             subprocess.check_call(["make", "-C", _HERE, "_ref"], stdout=subprocess.DEVNULL)
     return _LIB if os.path.exists(_LIB) else None
