@@ -1,0 +1,112 @@
+// host/engine_b200.h -- C++ host layer above the C-ABI (include/lpp_b200.h): the part of Engine (Engine.h:84-98, 133-206,
+// 460-533) that sits on the hot path.  Ground state on construction; spectralFunction() runs the reference's type loop
+// (operator or its conjugate, sum or difference of the two sites), applies the operator on the device
+// (accModifiedState_), runs the "Spectral" Lanczos decomposition on the new sector and records the continued fraction
+// (a, b, Eg, weight, isign) exactly as cf.set(ab, Eg, weight*s2, -s) does at Engine.h:481-489.
+// Header only, no PsimagLite: used by host/lanczos_b200.cpp; inside the reference tree the same calls live behind
+// include/InternalProductCuda.h.
+#ifndef LPP_ENGINE_B200_H
+#define LPP_ENGINE_B200_H
+
+#include <complex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "lpp_b200.h"
+
+namespace lppb200 {
+
+// PsimagLite::ContinuedFraction as Engine uses it: G(z) = weight * sum_l I_l / (z - isign (eps_l - Eg))
+struct ContinuedFraction {
+	int type;
+	std::vector<double> a, b;
+	double Eg, weight;
+	int isign;
+	std::vector<std::complex<double> > operator()(const std::vector<double>& omega, double delta) const
+	{
+		std::vector<double> out(2 * omega.size());
+		if (lpp_cf_eval((int32_t)a.size(), a.data(), b.data(), Eg, weight, isign, (int32_t)omega.size(), omega.data(), delta, out.data()) != 0)
+			throw std::runtime_error(lpp_last_error());
+		std::vector<std::complex<double> > g(omega.size());
+		for (size_t i = 0; i < omega.size(); i++) g[i] = std::complex<double>(out[2 * i], out[2 * i + 1]);
+		return g;
+	}
+};
+
+class Engine {
+public:
+	// Engine.h:84-98: the constructor computes the ground state (computeAllStatesBelow(0), Engine.h:601-657)
+	Engine(const lpp_desc& desc, const lpp_solver_params& lanczos, const lpp_solver_params& spectral)
+	    : desc_(desc), lanczos_(lanczos), spectral_(spectral), h_(nullptr), energy_(0), steps_(0)
+	{
+		check(lpp_create(&desc_, &h_));
+		int32_t ns = 0;
+		check(lpp_ground_state(h_, &lanczos_, nullptr, 1, &energy_, nullptr, nullptr, nullptr, &ns));
+		steps_ = ns;
+	}
+	~Engine() { if (h_) lpp_destroy(h_); }
+	Engine(const Engine&) = delete;
+	Engine& operator=(const Engine&) = delete;
+
+	double energies(size_t) const { return energy_; }
+	int lanczosSteps() const { return steps_; }
+	uint64_t rows() const { uint64_t r = 0; lpp_rows(h_, &r); return r; }
+
+	// Engine.h:133-206 for the fermionic operators c / cdagger of HubbardOneBand (hasNewParts: HubbardOneOrbital.h:212-230)
+	void spectralFunction(std::vector<ContinuedFraction>& cfCollection, int what, int isite, int jsite, int spin) const
+	{
+		if (what != LPP_OP_C && what != LPP_OP_CDAGGER) throw std::runtime_error("spectralFunction: operator must be c or cdagger");
+		const bool isDiagonal = isite == jsite;
+		const int conj = (what == LPP_OP_C) ? LPP_OP_CDAGGER : LPP_OP_C;
+		for (int type = 0; type < 4; type++) {
+			if (isDiagonal && type > 1) continue;
+			const int op = (type & 1) ? what : conj;                       // Engine.h:163
+			const int c = (op == LPP_OP_C) ? -1 : 1;
+			lpp_desc d = desc_;
+			d.nup += (spin == 0) ? c : 0;
+			d.ndown += (spin == 1) ? c : 0;
+			if (d.nup < 0 || d.ndown < 0 || d.nup > d.nsite || d.ndown > d.nsite || (d.nup == 0 && d.ndown == 0)) continue;
+			lpp_handle* dst = nullptr;
+			check(lpp_create(&d, &dst));
+			try {
+				const double isign = (type > 1) ? -1.0 : 1.0;
+				check(lpp_apply_op(h_, dst, op, isite, spin, 0, 1.0, 0));      // Engine.h:509-517
+				check(lpp_apply_op(h_, dst, op, jsite, spin, 0, isign, 1));    // Engine.h:523-531
+				ContinuedFraction cf;
+				cf.a.resize((size_t)spectral_.steps + 1);
+				cf.b.resize((size_t)spectral_.steps + 1);
+				int32_t n = 0;
+				double weight = 0;
+				check(lpp_lanczos_decomposition(dst, &spectral_, nullptr, 1, cf.a.data(), cf.b.data(), &n, &weight));   // Engine.h:474-479
+				cf.a.resize((size_t)n);
+				cf.b.resize((size_t)n);
+				const int s = (type & 1) ? -1 : 1;
+				double s2 = (type > 1) ? -1.0 : 1.0;
+				if (!isDiagonal) s2 *= 0.5;                                   // Engine.h:481-485
+				cf.type = type;
+				cf.Eg = energy_;
+				cf.weight = weight * s2;
+				cf.isign = -s;                                                // cf.set(ab, Eg, weight*s2, -s), Engine.h:489
+				cfCollection.push_back(cf);
+			} catch (...) {
+				lpp_destroy(dst);
+				throw;
+			}
+			lpp_destroy(dst);
+		}
+	}
+
+private:
+	static void check(int status)
+	{
+		if (status != 0) throw std::runtime_error(lpp_last_error());
+	}
+	lpp_desc desc_;
+	lpp_solver_params lanczos_, spectral_;
+	lpp_handle* h_;
+	double energy_;
+	int steps_;
+};
+
+} // namespace lppb200
+#endif

@@ -20,6 +20,7 @@
 #include <string>
 #include <vector>
 #include "../include/lpp_b200.h"
+#include "engine_b200.h"
 
 struct Input {
 	std::map<std::string, std::string> scalars;               // "Label=" lines
@@ -142,10 +143,13 @@ int main(int argc, char** argv)
 	std::string file;
 	int precision = 12;
 	bool parse_only = false;
+	std::string gf, omega_spec;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "-f") && i + 1 < argc) file = argv[++i];
 		else if (!strcmp(argv[i], "-p") && i + 1 < argc) precision = std::atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--parse-only")) parse_only = true;
+		else if (!strcmp(argv[i], "-g") && i + 1 < argc) gf = argv[++i];                 // lanczos -g c | -g cdagger (LanczosOptions.h)
+		else if (!strcmp(argv[i], "--omega") && i + 1 < argc) omega_spec = argv[++i];    // begin,end,step,delta
 	}
 	if (file.empty()) {
 		std::cerr << "USAGE: " << argv[0] << " -f input.inp [-p precision] [--parse-only]\n";
@@ -215,18 +219,46 @@ int main(int argc, char** argv)
 			          << " steps=" << p.steps << "\n";
 			return 0;
 		}
-		lpp_handle* h = nullptr;
-		if (lpp_create(&d, &h) != 0) throw std::runtime_error(lpp_last_error());
-		uint64_t rows = 0;
-		lpp_rows(h, &rows);
-		double energy = 0;
-		int32_t ns = 0;
-		if (lpp_ground_state(h, &p, nullptr, 1, &energy, nullptr, nullptr, nullptr, &ns) != 0)
-			throw std::runtime_error(lpp_last_error());
+		lpp_solver_params ps = p;                       // ParametersForSolver(io, "Spectral"), Engine.h:472
+		ps.steps = geti(in, "SpectralSteps", 200);
+		ps.minsteps = geti(in, "SpectralMinSteps", 4);
+		ps.eps = getd(in, "SpectralEps", 1e-12);
+		ps.reortho = gets(in, "SpectralOptions", "none").find("reortho") != std::string::npos ? 1 : 0;
+		lppb200::Engine engine(d, p, ps);
 		std::cout.precision(precision);
-		std::cout << "#Hilbert=" << rows << " LanczosSteps=" << ns << "\n";
-		std::cout << "Energy=" << energy << "\n";   // LanczosDriver1.h:64-66
-		lpp_destroy(h);
+		std::cout << "#Hilbert=" << engine.rows() << " LanczosSteps=" << engine.lanczosSteps() << "\n";
+		std::cout << "Energy=" << engine.energies(0) << "\n";   // LanczosDriver1.h:64-66
+		if (!gf.empty()) {
+			// LanczosDriver1.h:96-181: TSPSites (one site = diagonal), one continued-fraction collection per pair of sites
+			if (d.model != LPP_MODEL_HUBBARD) throw std::runtime_error("-g is available for Model=HubbardOneBand");
+			const int what = gf == "c" ? LPP_OP_C : (gf == "cdagger" ? LPP_OP_CDAGGER : 0);
+			if (!what) throw std::runtime_error("-g expects c or cdagger");
+			if (!in.vectors.count("TSPSites") || in.vectors["TSPSites"][0].empty()) throw std::runtime_error("TSPSites must have at least one site");
+			std::vector<double> sites = in.vectors["TSPSites"][0];
+			if (sites.size() == 1) sites.push_back(sites[0]);
+			const int site0 = (int)sites[0], site1 = (int)sites[1];
+			const int spin = geti(in, "TSPSpin", 0);
+			std::vector<lppb200::ContinuedFraction> cfs;
+			engine.spectralFunction(cfs, what, site0, site1, spin);
+			std::cout << "#gf(i=" << site0 << ", j=" << site1 << ")\n";
+			for (const auto& cf : cfs) {
+				std::cout << "#CF type=" << cf.type << " isign=" << cf.isign << " weight=" << cf.weight << " Eg=" << cf.Eg << " steps=" << cf.a.size() << "\n";
+				for (size_t k = 0; k < cf.a.size(); k++) std::cout << cf.a[k] << " " << cf.b[k] << "\n";
+			}
+			if (!omega_spec.empty()) {
+				double ob = 0, oe = 0, os = 1, delta = 0.1;
+				if (sscanf(omega_spec.c_str(), "%lf,%lf,%lf,%lf", &ob, &oe, &os, &delta) != 4 || os <= 0) throw std::runtime_error("--omega expects begin,end,step,delta");
+				std::vector<double> omega;
+				for (double w = ob; w < oe + 0.5 * os; w += os) omega.push_back(w);
+				std::vector<std::complex<double> > g(omega.size());
+				for (const auto& cf : cfs) {
+					const std::vector<std::complex<double> > gi = cf(omega, delta);
+					for (size_t k = 0; k < omega.size(); k++) g[k] += gi[k];
+				}
+				std::cout << "#omega ReG ImG\n";       // continuedFractionCollection -b -e -s -d (scripts/sqomega.pl:24-27)
+				for (size_t k = 0; k < omega.size(); k++) std::cout << omega[k] << " " << g[k].real() << " " << g[k].imag() << "\n";
+			}
+		}
 	} catch (std::exception& e) {
 		std::cerr << "lanczos_b200: " << e.what() << "\n";
 		return 2;

@@ -60,10 +60,12 @@ DRIVER_BIN = os.path.join(_HERE, "..", "host", "lanczos_b200")
 def build_driver(force=False):
     """Compile the stand-alone C++ driver (host/lanczos_b200.cpp) against the in-tree shared library."""
     build()
+    hdr = os.path.join(os.path.dirname(DRIVER_SRC), "engine_b200.h")
     if not force and os.path.exists(DRIVER_BIN) and os.path.getmtime(DRIVER_BIN) >= max(
-            os.path.getmtime(DRIVER_SRC), os.path.getmtime(LIB_PATH)):
+            os.path.getmtime(DRIVER_SRC), os.path.getmtime(hdr), os.path.getmtime(LIB_PATH)):
         return DRIVER_BIN
-    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-o", DRIVER_BIN, DRIVER_SRC, "-L" + _HERE, "-llpp_b200",
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(os.path.dirname(_HERE), "include"), "-o", DRIVER_BIN,
+           DRIVER_SRC, "-L" + _HERE, "-llpp_b200",
            "-Wl,-rpath,$ORIGIN/../lanczosplusplus_b200"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

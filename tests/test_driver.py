@@ -35,3 +35,27 @@ def test_driver_energies(lpp):
         assert r.returncode == 0, r.stderr
         e = float(re.search(r"Energy=(\S+)", r.stdout).group(1))
         assert abs(e - ref) < 1e-9, (name, e)
+
+
+@pytest.mark.gpu
+def test_driver_spectral_function_matches_python_engine(lpp):
+    """`lanczos_b200 -g c`: the C++ Engine mirror (host/engine_b200.h, Engine.h:133-206) against the ctypes mirror and its
+    oracle-checked continued fractions (tests/test_gpu_parity.py::test_continued_fraction_parity)."""
+    from tests import cases
+    r = run(lpp, ["-f", os.path.join(ROOT, "tests/inputs/hubbard6_gf.inp"), "-p", "15", "-g", "c", "--omega", "-4,4,0.5,0.1"])
+    assert r.returncode == 0, r.stderr
+    assert "#gf(i=1, j=3)" in r.stdout
+    heads = re.findall(r"#CF type=(\d) isign=(-?\d+) weight=(\S+) Eg=(\S+) steps=(\d+)", r.stdout)
+    assert [int(h[0]) for h in heads] == [0, 1, 2, 3]
+    table = r.stdout.split("#omega ReG ImG\n")[1].strip().splitlines()
+    om = np.array([float(l.split()[0]) for l in table])
+    g = np.array([float(l.split()[1]) + 1j * float(l.split()[2]) for l in table])
+    eng = cases.make_engine(lpp, cases.hubbard_chain(6, 3, 3))
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13, "SpectralSteps": 40, "SpectralEps": 0.0})
+    assert abs(en.energies(0) - float(heads[0][3])) < 1e-10
+    cfs = en.spectralFunction(lpp.OP_C, 1, 3, spin=0)
+    gref = sum(cf(om, 0.1) for _, cf in cfs)
+    for (typ, cf), h in zip(cfs, heads):
+        assert cf.isign == int(h[1]) and abs(cf.weight - float(h[2])) <= 1e-9 * max(1.0, abs(cf.weight))
+    assert np.abs(g - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max())
+    eng.close()
