@@ -52,11 +52,14 @@ public:
 	int lanczosSteps() const { return steps_; }
 	uint64_t rows() const { uint64_t r = 0; lpp_rows(h_, &r); return r; }
 
-	// Engine.h:133-206 for the fermionic operators c / cdagger of HubbardOneBand (hasNewParts: HubbardOneOrbital.h:212-230)
-	void spectralFunction(std::vector<ContinuedFraction>& cfCollection, int what, int isite, int jsite, int spin) const
+	// Engine.h:133-206 for the fermionic operators c / cdagger of HubbardOneBand, FeAsBasedSc (orbital pair orb0, orb1) and
+	// Tj1Orbital (hasNewParts: HubbardOneOrbital.h:212-230, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557)
+	void spectralFunction(std::vector<ContinuedFraction>& cfCollection, int what, int isite, int jsite, int spin, int orb0 = 0,
+	                      int orb1 = 0) const
 	{
 		if (what != LPP_OP_C && what != LPP_OP_CDAGGER) throw std::runtime_error("spectralFunction: operator must be c or cdagger");
-		const bool isDiagonal = isite == jsite;
+		const bool isDiagonal = isite == jsite && orb0 == orb1;
+		const int nmax = desc_.nsite * (desc_.model == LPP_MODEL_FEAS ? desc_.orbitals : 1);
 		const int conj = (what == LPP_OP_C) ? LPP_OP_CDAGGER : LPP_OP_C;
 		for (int type = 0; type < 4; type++) {
 			if (isDiagonal && type > 1) continue;
@@ -65,13 +68,14 @@ public:
 			lpp_desc d = desc_;
 			d.nup += (spin == 0) ? c : 0;
 			d.ndown += (spin == 1) ? c : 0;
-			if (d.nup < 0 || d.ndown < 0 || d.nup > d.nsite || d.ndown > d.nsite || (d.nup == 0 && d.ndown == 0)) continue;
+			if (d.nup < 0 || d.ndown < 0 || d.nup > nmax || d.ndown > nmax || (d.nup == 0 && d.ndown == 0)) continue;
+			if (d.model == LPP_MODEL_TJ && d.nup + d.ndown > d.nsite) continue;           // no double occupancy
 			lpp_handle* dst = nullptr;
 			check(lpp_create(&d, &dst));
 			try {
 				const double isign = (type > 1) ? -1.0 : 1.0;
-				check(lpp_apply_op(h_, dst, op, isite, spin, 0, 1.0, 0));      // Engine.h:509-517
-				check(lpp_apply_op(h_, dst, op, jsite, spin, 0, isign, 1));    // Engine.h:523-531
+				check(lpp_apply_op(h_, dst, op, isite, spin, orb0, 1.0, 0));   // Engine.h:509-517
+				check(lpp_apply_op(h_, dst, op, jsite, spin, orb1, isign, 1)); // Engine.h:523-531
 				ContinuedFraction cf;
 				cf.a.resize((size_t)spectral_.steps + 1);
 				cf.b.resize((size_t)spectral_.steps + 1);

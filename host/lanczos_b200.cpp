@@ -230,7 +230,7 @@ int main(int argc, char** argv)
 		std::cout << "Energy=" << engine.energies(0) << "\n";   // LanczosDriver1.h:64-66
 		if (!gf.empty()) {
 			// LanczosDriver1.h:96-181: TSPSites (one site = diagonal), one continued-fraction collection per pair of sites
-			if (d.model != LPP_MODEL_HUBBARD) throw std::runtime_error("-g is available for Model=HubbardOneBand");
+			if (d.model == LPP_MODEL_HEISENBERG) throw std::runtime_error("-g c is available for the fermionic models");
 			const int what = gf == "c" ? LPP_OP_C : (gf == "cdagger" ? LPP_OP_CDAGGER : 0);
 			if (!what) throw std::runtime_error("-g expects c or cdagger");
 			if (!in.vectors.count("TSPSites") || in.vectors["TSPSites"][0].empty()) throw std::runtime_error("TSPSites must have at least one site");

@@ -617,26 +617,36 @@ LPP_HD int lpp_stored_row(const ModelDev& m, uint64_t r, uint64_t* c, double* v)
 }
 
 // ---------------------------------------------------------------- operator application (Engine.h:416-458) as a gather
-// For destination row r of `dst`: the unique source row of `src` (if any) and the Green-function sign.
-// c:       dst word has the site empty, source = dst | bit      (BasisOneSpin.h:127-134)
-// cdagger: dst word has the site occupied, source = dst ^ bit   (:135-142)
-// n:       same sector, site occupied                            (:143-147)
-LPP_HD bool lpp_apply_op_source(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, uint64_t r,
+// For destination row r of `dst`: the unique source row of `src` (if any) and the Green-function sign doSignGf.
+// c:       dst word has the orbital empty, source = dst | bit      (BasisOneSpin.h:127-134, BasisOneSpinFeAs.h:127-143,
+//          BasisTjMultiOrbLanczos.h:413-433); t-J: the source must not be doubly occupied (:400-411)
+// cdagger: dst word has the orbital occupied, source = dst ^ bit
+// n:       same sector, orbital occupied (HubbardOneBand only)
+// Signs: Hubbard literal BasisHubbardLanczos.h:106-137 (quirk C.3); FeAs BasisFeAsBasedSc.h:170-178 with
+// BasisOneSpinFeAs.h:227-239; t-J BasisTjMultiOrbLanczos.h:163-192: parity of the same-species electrons below the orbital,
+// times the parity of all up electrons for a down operator.
+LPP_HD bool lpp_apply_op_source(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, int orb, uint64_t r,
                                 uint64_t* src_row, double* sign)
 {
-	uint64_t i1 = r % dst.n1, i2 = r / dst.n1;
-	word_t b1 = dst.b1[i1], b2 = dst.b2[i2];
-	word_t bra = spin == 0 ? b1 : b2;
-	word_t ms = lpp_bit(site);
+	const LppRowKets k = lpp_row_kets(dst, r);
+	const word_t b1 = k.k1, b2 = k.k2;
+	const word_t bra = spin == 0 ? b1 : b2;
+	const int pos = site * dst.orbitals + orb;
+	const word_t ms = lpp_bit(pos);
 	word_t ket;
 	if (op == 1) { if (bra & ms) return false; ket = bra | ms; }
 	else if (op == 3) { if (!(bra & ms)) return false; ket = bra ^ ms; }
 	else { if (!(bra & ms)) return false; ket = bra; }
-	word_t k1 = spin == 0 ? ket : b1, k2 = spin == 0 ? b2 : ket;
-	uint64_t s1 = spin == 0 ? lpp_rank_onespin(src, 0, ket) : i1;
-	uint64_t s2 = spin == 0 ? i2 : lpp_rank_onespin(src, 1, ket);
-	*sign = (op == 1 || op == 3) ? (double)lpp_hubbard_sign_gf(k1, k2, site, spin) : 1.0;
-	*src_row = s1 + s2 * src.n1;
+	const word_t k1 = spin == 0 ? ket : b1, k2 = spin == 0 ? b2 : ket;
+	if (src.model == LPP_MODEL_TJ && (k1 & k2)) return false;
+	if (src.model == LPP_MODEL_HUBBARD) {
+		*sign = (op == 1 || op == 3) ? (double)lpp_hubbard_sign_gf(k1, k2, site, spin) : 1.0;
+	} else {
+		int sg = lpp_sign_below(spin == 0 ? k1 : k2, pos);
+		if (spin == 1 && (lpp_popc(k1) & 1)) sg = -sg;
+		*sign = (double)sg;
+	}
+	*src_row = lpp_rank_pair(src, k1, k2);
 	return true;
 }
 

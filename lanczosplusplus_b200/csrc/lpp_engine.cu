@@ -1262,9 +1262,11 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
                             double factor, int32_t accumulate)
 {
 	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
-	if (src->md.model != LPP_MODEL_HUBBARD || dst->md.model != LPP_MODEL_HUBBARD || orb != 0)
-		return fail(LPP_ERR_ARG, "lpp_apply_op supports HubbardOneBand bases (c, cdagger, n)");
-	if (op != LPP_OP_C && op != LPP_OP_CDAGGER && op != LPP_OP_N) return fail(LPP_ERR_ARG, "unsupported operator");
+	const int model = src->md.model;
+	if (model != dst->md.model || model == LPP_MODEL_HEISENBERG)
+		return fail(LPP_ERR_ARG, "lpp_apply_op: HubbardOneBand (c, cdagger, n), FeAsBasedSc and Tj1Orbital (c, cdagger) bases");
+	if (orb < 0 || orb >= src->md.orbitals) return fail(LPP_ERR_ARG, "bad orbital");
+	if (op != LPP_OP_C && op != LPP_OP_CDAGGER && !(op == LPP_OP_N && model == LPP_MODEL_HUBBARD)) return fail(LPP_ERR_ARG, "unsupported operator");
 	if (site < 0 || site >= src->md.nsite || spin < 0 || spin > 1) return fail(LPP_ERR_ARG, "bad site/spin");
 	if (!src->gs) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
 	if (src->desc.nranks != dst->desc.nranks || src->desc.rank != dst->desc.rank || src->device != dst->device)
@@ -1275,6 +1277,7 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	int eu = src->md.nup + (spin == 0 ? dup : 0), ed = src->md.ndn + (spin == 1 ? dup : 0);
 	if (dst->md.nup != eu || dst->md.ndn != ed || dst->md.nsite != src->md.nsite)
 		return fail(LPP_ERR_ARG, "destination sector does not match operator (hasNewParts, HubbardOneOrbital.h:212-230)");
+	if (model == LPP_MODEL_FEAS && dst->md.orbitals != src->md.orbitals) return fail(LPP_ERR_ARG, "orbital count differs");
 	CK(cudaSetDevice(dst->device));
 	if (!dst->modified) {
 		CKR(dev_alloc(dst, &dst->modified, dst->nloc));
@@ -1284,7 +1287,7 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	CK(cudaStreamSynchronize(src->stream));
 	// source vector is indexed globally inside the kernel: shift the local pointer by the shard's first row
 	const double* srcv = src->gs - src->row0;
-	lpp_launch_apply_op(src->md, dst->md, op, site, spin, factor, srcv, dst->modified, dst->row0, dst->nloc, dst->stream);
+	lpp_launch_apply_op(src->md, dst->md, op, site, spin, orb, factor, srcv, dst->modified, dst->row0, dst->nloc, dst->stream);
 	dst->launches += 1;
 	CK(cudaStreamSynchronize(dst->stream));
 	CK(cudaGetLastError());

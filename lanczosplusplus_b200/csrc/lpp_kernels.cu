@@ -611,7 +611,7 @@ void lpp_launch_finalize_sum(const double* partials, int n, double* out, cudaStr
 // c:       dst word has the site empty, source = dst | bit      (BasisOneSpin.h:127-134)
 // cdagger: dst word has the site occupied, source = dst ^ bit   (:135-142)
 // n:       same sector, site occupied                            (:143-147)
-__global__ void __launch_bounds__(LPP_TPB) k_apply_op(ModelDev src, ModelDev dst, int op, int site, int spin, double factor,
+__global__ void __launch_bounds__(LPP_TPB) k_apply_op(ModelDev src, ModelDev dst, int op, int site, int spin, int orb, double factor,
                                                      const double* __restrict__ srcv, double* __restrict__ z,
                                                      uint64_t dst_row0, uint64_t dst_nloc)
 {
@@ -619,14 +619,14 @@ __global__ void __launch_bounds__(LPP_TPB) k_apply_op(ModelDev src, ModelDev dst
 	if (t >= dst_nloc) return;
 	uint64_t srow;
 	double sg;
-	if (!lpp_apply_op_source(src, dst, op, site, spin, dst_row0 + t, &srow, &sg)) return;
+	if (!lpp_apply_op_source(src, dst, op, site, spin, orb, dst_row0 + t, &srow, &sg)) return;
 	z[t] += factor * sg * srcv[srow];
 }
 
-void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, double factor,
+void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, int orb, double factor,
                          const double* srcv, double* z, uint64_t dst_row0, uint64_t dst_nloc, cudaStream_t s)
 {
-	k_apply_op<<<(unsigned)((dst_nloc + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(src, dst, op, site, spin, factor, srcv, z,
+	k_apply_op<<<(unsigned)((dst_nloc + LPP_TPB - 1) / LPP_TPB), LPP_TPB, 0, s>>>(src, dst, op, site, spin, orb, factor, srcv, z,
 	                                                                            dst_row0, dst_nloc);
 }
 

@@ -81,7 +81,7 @@ void lpp_launch_scale(double* v, double coef, uint64_t n, cudaStream_t s);
 void lpp_launch_finalize_sum(const double* partials, int n, double* out, cudaStream_t s);
 
 // operator application (Engine.h:416-458), gather form on the destination basis
-void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, double factor,
+void lpp_launch_apply_op(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, int orb, double factor,
                          const double* srcv, double* z, uint64_t dst_row0, uint64_t dst_nloc, cudaStream_t s);
 
 // two-layout exchange helpers (multi-GPU)

@@ -289,25 +289,29 @@ class Engine:
     def energies(self, ind=0):
         return self.energy
 
-    def spectralFunction(self, op, isite, jsite, spin=0):
-        """Engine.h:133-206 for fermionic c/cdagger on Hubbard bases: list of (type, ContinuedFraction)."""
+    def spectralFunction(self, op, isite, jsite, spin=0, orbs=(0, 0)):
+        """Engine.h:133-206 for the fermionic c/cdagger of HubbardOneBand, FeAsBasedSc (orbital pair) and Tj1Orbital:
+        list of (type, ContinuedFraction)."""
         if spin != 0 and self.mat.nranks > 1:
             raise LppError("row-sharded spectral functions support spin 0")
         out = []
-        is_diag = isite == jsite
+        is_diag = isite == jsite and orbs[0] == orbs[1]
         op2 = {OP_C: OP_CDAGGER, OP_CDAGGER: OP_C}[op]
+        nmax = self.mat.nsite * self.mat.orbitals
         for typ in range(4):
             if is_diag and typ > 1:
                 continue
             lop = op if (typ & 1) else op2  # Engine.h:163
             dn = -1 if lop == OP_C else 1
             nup, ndown = self.mat.nup + (dn if spin == 0 else 0), self.mat.ndown + (dn if spin == 1 else 0)
-            if nup < 0 or ndown < 0 or nup > self.mat.nsite or ndown > self.mat.nsite or (nup == 0 and ndown == 0):
-                continue  # hasNewPartsCorCdagger, HubbardOneOrbital.h:212-230
+            if nup < 0 or ndown < 0 or nup > nmax or ndown > nmax or (nup == 0 and ndown == 0):
+                continue  # hasNewPartsCorCdagger: HubbardOneOrbital.h:212-230, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557
+            if self.mat.model == TJ and nup + ndown > self.mat.nsite:
+                continue  # no double occupancy, TjMultiOrb.h:553
             dst = self.mat.sector(nup, ndown)
-            self.mat.apply_op(dst, lop, isite, spin, 1.0, accumulate=False)           # Engine.h:509-517
+            self.mat.apply_op(dst, lop, isite, spin, 1.0, accumulate=False, orb=orbs[0])   # Engine.h:509-517
             isign = -1.0 if typ > 1 else 1.0
-            self.mat.apply_op(dst, lop, jsite, spin, isign, accumulate=True)           # Engine.h:523-531
+            self.mat.apply_op(dst, lop, jsite, spin, isign, accumulate=True, orb=orbs[1])   # Engine.h:523-531
             solver = LanczosSolver(dst, ParametersForSolver(self.io, "Spectral"))
             a, b, weight = solver.decomposition(use_modified=True)                     # Engine.h:474-479
             s = -1 if (typ & 1) else 1

@@ -1391,26 +1391,69 @@ static int hubbard_dosign_gf(word_t a, word_t b, int ind, int sector)
 	return s;
 }
 
-/* Engine.h:416-458 accModifiedState_ for Hubbard with c / cdagger / n (BasisOneSpin.h:121-151,
- * BasisHubbardLanczos.h:162-182, 64-bit indices instead of int).  z (dst basis) += factor*sign*src. */
-void orc_apply_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, double factor,
-                  const double* srcv, double* z)
+/* BasisOneSpinFeAs.h:227-239: parity of the occupied orbitals below site*orbitals + orb */
+static int feas_dosign_gf1(word_t a, int ind, int orb, int orbitals)
+{
+	int sum = feas_nbyket(a, 0, ind * orbitals);
+	sum += feas_nbyket(a, ind * orbitals, ind * orbitals + orb);
+	return (sum & 1) ? -1 : 1;
+}
+
+/* BasisTjMultiOrbLanczos.h:163-192 */
+static int tj_dosign_gf(word_t a, word_t b, int ind, int sector)
+{
+	if (sector == 0) {
+		if (ind == 0) return 1;
+		word_t mask = a & ((((word_t)1 << 1) - 1) ^ (((word_t)1 << ind) - 1));
+		int s = (popc(mask) & 1) ? -1 : 1;
+		if (a & 1) s = -s;
+		return s;
+	}
+	int s = (popc(a) & 1) ? -1 : 1;
+	if (ind == 0) return s;
+	word_t mask = b & ((((word_t)1 << 1) - 1) ^ (((word_t)1 << ind) - 1));
+	s *= (popc(mask) & 1) ? -1 : 1;
+	if (b & 1) s = -s;
+	return s;
+}
+
+/* Engine.h:416-458 accModifiedState_ with c / cdagger (/ n for Hubbard): getBraIndex of the new basis
+ * (BasisHubbardLanczos.h:162-182 with BasisOneSpin.h:121-151; BasisFeAsBasedSc.h:276-289 with BasisOneSpinFeAs.h:127-143;
+ * BasisTjMultiOrbLanczos.h:302-318,398-433), doSignGf of the source basis, 64-bit indices instead of int.
+ * z (dst basis) += factor*sign*src. */
+void orc_apply_op_orb(const orc_model* src, const orc_model* dst, int op, int site, int spin, int orb, double factor,
+                      const double* srcv, double* z)
 {
 	size_t n = orc_rows(src);
-	word_t ms = ((word_t)1) << site;
+	int pos = site * src->orbitals + orb;
+	word_t ms = ((word_t)1) << pos;
 	for (size_t r = 0; r < n; r++) {
-		word_t k1 = src->b1[r % src->n1];
-		word_t k2 = src->b2[r / src->n1];
+		word_t k1, k2;
+		row_kets(src, r, &k1, &k2);
 		word_t ket = spin == 0 ? k1 : k2;
 		word_t bra;
 		word_t si = ket & ms;
 		if (op == ORC_OP_C) { if (!si) continue; bra = ket ^ ms; }
 		else if (op == ORC_OP_CDAGGER) { if (si) continue; bra = ket ^ ms; }
 		else { if (!si) continue; bra = ket; }
+		if (src->model == ORC_TJ && (spin == 0 ? (bra & k2) : (k1 & bra))) continue;   /* isDoublyOccupied */
 		size_t idx = spin == 0 ? perfect_index(dst, bra, k2) : perfect_index(dst, k1, bra);
-		double mysign = (op == ORC_OP_C || op == ORC_OP_CDAGGER) ? hubbard_dosign_gf(k1, k2, site, spin) : 1;
+		double mysign = 1;
+		if (op == ORC_OP_C || op == ORC_OP_CDAGGER) {
+			if (src->model == ORC_HUBBARD) mysign = hubbard_dosign_gf(k1, k2, site, spin);
+			else if (src->model == ORC_FEAS) {
+				if (spin == 0) mysign = feas_dosign_gf1(k1, site, orb, src->orbitals);
+				else mysign = ((popc(k1) & 1) ? -1 : 1) * feas_dosign_gf1(k2, site, orb, src->orbitals);
+			} else mysign = tj_dosign_gf(k1, k2, site, spin);
+		}
 		z[idx] += factor * mysign * 1.0 * srcv[r];
 	}
+}
+
+void orc_apply_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, double factor,
+                  const double* srcv, double* z)
+{
+	orc_apply_op_orb(src, dst, op, site, spin, 0, factor, srcv, z);
 }
 
 int orc_num_threads(void)

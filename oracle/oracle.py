@@ -82,6 +82,8 @@ def lib():
                                   C.c_void_p, C.c_double, C.c_void_p]
         L.orc_apply_op.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                    C.c_void_p]
+        L.orc_apply_op_orb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
+                                       C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -232,9 +234,9 @@ class OracleModel:
                                     z.ctypes.data if want_vector else None, a.ctypes.data, b.ctypes.data)
         return e.value, z, a[:ns].copy(), b[:ns].copy()
 
-    def apply_op(self, dst, op, site, spin, factor, srcv, z):
+    def apply_op(self, dst, op, site, spin, factor, srcv, z, orb=0):
         srcv = _f64(srcv)
-        lib().orc_apply_op(self.h, dst.h, op, site, spin, factor, srcv.ctypes.data, z.ctypes.data)
+        lib().orc_apply_op_orb(self.h, dst.h, op, site, spin, orb, factor, srcv.ctypes.data, z.ctypes.data)
         return z
 
 

@@ -156,13 +156,13 @@ void hc_matvec(const HostModel* h, double* x, const double* y)
 }
 
 // z (dst basis) += factor * O |srcv> using the gather form
-void hc_apply_op(const HostModel* src, const HostModel* dst, int op, int site, int spin, double factor, const double* srcv,
+void hc_apply_op(const HostModel* src, const HostModel* dst, int op, int site, int spin, int orb, double factor, const double* srcv,
                  double* z)
 {
 	for (uint64_t r = 0; r < dst->m.rows; r++) {
 		uint64_t srow;
 		double sg;
-		if (!lpp_apply_op_source(src->m, dst->m, op, site, spin, r, &srow, &sg)) continue;
+		if (!lpp_apply_op_source(src->m, dst->m, op, site, spin, orb, r, &srow, &sg)) continue;
 		z[r] += factor * sg * srcv[srow];
 	}
 }

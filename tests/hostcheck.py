@@ -37,7 +37,7 @@ def lib():
         L.hc_crs.restype = C.c_int64
         L.hc_crs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hc_matvec.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.hc_apply_op.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.hc_apply_op.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.hc_splitmix.restype = C.c_double
         L.hc_splitmix.argtypes = [C.c_uint64, C.c_uint64]
         _lib = L
@@ -102,7 +102,7 @@ class HostModel:
         lib().hc_matvec(self.h, x.ctypes.data, y.ctypes.data)
         return x
 
-    def apply_op(self, dst, op, site, spin, factor, srcv, z):
+    def apply_op(self, dst, op, site, spin, factor, srcv, z, orb=0):
         srcv = _f(srcv)
-        lib().hc_apply_op(self.h, dst.h, op, site, spin, factor, srcv.ctypes.data, z.ctypes.data)
+        lib().hc_apply_op(self.h, dst.h, op, site, spin, orb, factor, srcv.ctypes.data, z.ctypes.data)
         return z

@@ -313,22 +313,26 @@ def test_engine_matches_reference_fixture(lpp, name):
     e.close()
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(cases.SMALL_CASES) if cases.SMALL_CASES[n]["model"] == cases.HUBBARD])
+_ALL = dict(cases.SMALL_CASES, **cases.TJ_CASES)
+
+
+@pytest.mark.parametrize("name", [n for n in sorted(_ALL) if _ALL[n]["model"] != cases.HEISENBERG])
 def test_apply_op_matches_reference_fixture(lpp, name):
-    """accModifiedState_ on the device against the reference's getBraIndex / doSignGf results (both spins, c and cdagger)."""
+    """accModifiedState_ on the device against the reference's getBraIndex / doSignGf results (both spins, c and cdagger;
+    HubbardOneBand, FeAsBasedSc per orbital, Tj1Orbital)."""
     from tests import golden_util as gu
-    case = cases.SMALL_CASES[name]
+    case = _ALL[name]
     g = gu.load(name, case)
     e = cases.make_engine(lpp, case)
     e.set_groundstate(geo.splitmix64_vector(e.rows(), gu.SRC_SEED))
     seen = 0
     for rec in gu.ops(g):
         dst = e.sector(rec["nup"], rec["ndown"])
-        e.apply_op(dst, rec["op"], rec["site"], rec["spin"], 1.0, accumulate=False)
+        e.apply_op(dst, rec["op"], rec["site"], rec["spin"], 1.0, accumulate=False, orb=rec["orb"])
         assert np.array_equal(dst.get_vector(1), g[rec["key"]]), rec      # +-source elements: exact
         dst.close()
         seen += 1
-    assert seen >= 8
+    assert seen >= (4 if name in ("tj6_full", "tj5_no_dn", "hub_empty_dn") else 8)
     e.close()
 
 
@@ -443,3 +447,41 @@ def test_reortho_full_space_reproduces_all_eigenvalues(lpp, oracle):
         assert np.abs(distinct - r).min() <= 1e-8
     assert len(ritz) >= 0.5 * len(distinct)
     e.close()
+
+
+@pytest.mark.parametrize("name,orbs,steps", [("feas3", (0, 1), 8), ("feas4", (1, 1), 30), ("tj8_V", (0, 0), 30), ("tj6_pbc", (0, 0), 10)])
+def test_continued_fraction_other_models(lpp, oracle, name, orbs, steps):
+    """spectralFunction for FeAsBasedSc (orbital pair) and Tj1Orbital: modified state, weights, tridiagonal coefficients and
+    G(omega) against the oracle pipeline (apply_op -> decomposition -> continued fraction), same ground-state vector on both sides."""
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 77)
+    e0, z0, _, _ = o.ground_state(init, 300, 1e-13, 4)
+    eng = cases.make_engine(lpp, case, kernel=lpp.KERNEL_AUTO)
+    # `steps` stays well below the dimension of the smallest new sector: once the Krylov space closes the late coefficients are noise
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13, "SpectralSteps": steps, "SpectralEps": 0.0}, init=init)
+    assert abs(en.energies(0) - e0) < 1e-10
+    eng.set_groundstate(z0)
+    en.energy = e0
+    omega = np.linspace(-6, 6, 49)
+    isite, jsite = 0, case["nsite"] - 1
+    for spin in (0, 1):
+        cfs = en.spectralFunction(lpp.OP_C, isite, jsite, spin=spin, orbs=orbs)
+        assert len(cfs) >= 2
+        for typ, cf in cfs:
+            lop = oracle.OP_C if (typ & 1) else oracle.OP_CDAGGER
+            dn = -1 if lop == oracle.OP_C else 1
+            od = cases.make_oracle(oracle, dict(case, nup=case["nup"] + (dn if spin == 0 else 0),
+                                                ndown=case["ndown"] + (dn if spin == 1 else 0)))
+            phi = np.zeros(od.rows())
+            o.apply_op(od, lop, isite, spin, 1.0, z0, phi, orb=orbs[0])
+            o.apply_op(od, lop, jsite, spin, -1.0 if typ > 1 else 1.0, z0, phi, orb=orbs[1])
+            a, b = od.decomposition(phi, steps=steps, eps=0.0)
+            weight = (phi @ phi) * (-1.0 if typ > 1 else 1.0) * 0.5
+            assert abs(cf.weight - weight) <= 1e-12 * max(1.0, abs(weight))
+            n = min(len(a), 8)
+            assert relerr(cf.a[:n], a[:n]) <= 1e-10 and relerr(cf.b[:n], b[:n]) <= 1e-10
+            s = -1 if (typ & 1) else 1
+            gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
+            assert np.abs(cf(omega, 0.1) - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max()), (name, spin, typ)
+    eng.close()

@@ -95,6 +95,33 @@ def test_apply_op_matches_oracle(oracle):
             assert np.array_equal(z0, z1)
 
 
+@pytest.mark.parametrize("name", ["feas3", "feas4_interorb_otfquirk", "tj6_pbc", "tj8_V", "tj6_full"])
+def test_apply_op_other_models_match_oracle(oracle, name):
+    """c / cdagger for FeAsBasedSc (every orbital) and Tj1Orbital through the product's gather form vs the oracle's scatter."""
+    src_case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    os_, hs = cases.make_oracle(oracle, src_case), HostModel(src_case)
+    v = geo.splitmix64_vector(os_.rows(), 5)
+    n, no = src_case["nsite"], src_case["orbitals"]
+    done = 0
+    for op, dn in ((oracle.OP_C, -1), (oracle.OP_CDAGGER, 1)):
+        for spin in (0, 1):
+            nu, nd = src_case["nup"] + (dn if spin == 0 else 0), src_case["ndown"] + (dn if spin == 1 else 0)
+            if min(nu, nd) < 0 or max(nu, nd) > n * no or (nu == 0 and nd == 0):
+                continue
+            if src_case["model"] == cases.TJ and nu + nd > n:
+                continue
+            dst_case = dict(src_case, nup=nu, ndown=nd)
+            od, hd = cases.make_oracle(oracle, dst_case), HostModel(dst_case)
+            for site in range(n):
+                for orb in range(no):
+                    z0, z1 = np.zeros(od.rows()), np.zeros(od.rows())
+                    os_.apply_op(od, op, site, spin, 0.7, v, z0, orb=orb)
+                    hs.apply_op(hd, op, site, spin, 0.7, v, z1, orb=orb)
+                    assert np.array_equal(z0, z1), (op, spin, site, orb)
+                    done += 1
+    assert done > 0
+
+
 def test_splitmix_matches_numpy():
     v = geo.splitmix64_vector(64, 1234, offset=10**12)
     for i in range(64):

@@ -49,7 +49,7 @@ def make_reference(case):
 
 def op_list(case):
     """(op, site, spin, orb) tuples exercised per model (fermionic c / cdagger; both spins: quirk C.3 lives in spin 1)."""
-    if case["model"] in (cases.HEISENBERG, cases.TJ):
+    if case["model"] == cases.HEISENBERG:
         return []
     n = case["nsite"]
     sites = sorted({0, n // 2, n - 1})
