@@ -100,6 +100,26 @@ public:
 		}
 	}
 
+	// Engine.h:262-331 with bra = ket = ground state: result[i * nsite + j] = <O_j gs | O_i gs> (c: <cdagger_j c_i>)
+	std::vector<double> twoPoint(int what, int spin, int orb0 = 0, int orb1 = 0) const
+	{
+		std::vector<double> result((size_t)desc_.nsite * desc_.nsite, 0.0);
+		if (what == LPP_OP_N) {
+			check(lpp_two_point(h_, h_, what, spin, orb0, orb1, result.data()));
+			return result;
+		}
+		const int c = (what == LPP_OP_C) ? -1 : 1;
+		lpp_desc d = desc_;
+		d.nup += (spin == 0) ? c : 0;
+		d.ndown += (spin == 1) ? c : 0;
+		lpp_handle* dst = nullptr;
+		check(lpp_create(&d, &dst));
+		const int rc = lpp_two_point(h_, dst, what, spin, orb0, orb1, result.data());
+		lpp_destroy(dst);
+		check(rc);
+		return result;
+	}
+
 private:
 	static void check(int status)
 	{

@@ -147,6 +147,10 @@ int lpp_ground_state(lpp_handle* h, const lpp_solver_params* p, const double* in
  * accumulate == 0 zeroes dst.modified first. */
 int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb, double factor,
                  int32_t accumulate);
+/* Engine::twoPoint (Engine.h:262-331) with bra = ket = ground state: result[i*nsite + j] = <O_{j,spin,orb_j} gs | O_{i,spin,orb_i} gs>
+ * for the operators of lpp_apply_op (c: the one-body density matrix <cdagger_j c_i>; n: <n_j n_i>); dst is a handle on the
+ * sector the operator leads to (src itself for n).  Modified states and the Gram matrix stay on the device. */
+int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t spin, int32_t orb_i, int32_t orb_j, double* result);
 /* copy the handle's ground-state / modified vector to the host (parity tests) */
 int lpp_get_vector(lpp_handle* h, int32_t which /*0 = ground state, 1 = modified*/, double* out_host);
 int lpp_set_groundstate(lpp_handle* h, const double* z_host);

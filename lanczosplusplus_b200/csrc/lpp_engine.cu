@@ -1294,6 +1294,61 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	return 0;
 }
 
+// Engine::twoPoint (Engine.h:262-331) for the operators lpp_apply_op knows: m_i = O_{i, spin, orb_i} |src.groundstate> on the
+// sector of `dst` for every site i, result[i * nsite + j] = <m_j(orb_j) | m_i(orb_i)> (bra = ket = ground state)
+extern "C" int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t spin, int32_t orb_i, int32_t orb_j, double* result)
+{
+	if (!src || !dst || !result) return fail(LPP_ERR_ARG, "null argument");
+	const int nsite = src->md.nsite;
+	CK(cudaSetDevice(dst->device));
+	const uint64_t n = dst->nloc, stride = std::max<uint64_t>(n, 1);
+	const int nsets = (orb_i == orb_j) ? 1 : 2;                     // second set of modified states when the orbitals differ
+	double* vecs = nullptr;
+	if (cudaMalloc((void**)&vecs, sizeof(double) * stride * nsite * nsets) != cudaSuccess) {
+		cudaGetLastError();
+		return fail(LPP_ERR_CUDA, "two_point: out of device memory for nsite modified states");
+	}
+	double* keep = dst->modified;
+	int rc = 0;
+	for (int set = 0; set < nsets && rc == 0; set++)
+		for (int i = 0; i < nsite && rc == 0; i++) {
+			dst->modified = vecs + (uint64_t)(set * nsite + i) * stride;   // lpp_apply_op writes into the handle's modified vector
+			rc = lpp_apply_op(src, dst, op, i, spin, set == 0 ? orb_i : orb_j, 1.0, 0);
+		}
+	dst->modified = keep;
+	if (rc != 0) { cudaFree(vecs); return rc; }
+	const int nt = (nsite + 3) / 4, npb = lpp_vec_blocks(n * 2);
+	int rcp = ensure_partials(dst, npb * 16);
+	if (rcp != 0) { cudaFree(vecs); return rcp; }
+	const double* vi = vecs;
+	const double* vj = vecs + (uint64_t)(nsets - 1) * nsite * stride;
+	for (int ti = 0; ti < nt && rc == 0; ti++)
+		for (int tj = 0; tj < nt && rc == 0; tj++) {
+			// tile (ti, tj): rows from the orb_i set of modified states, columns from the orb_j set
+			lpp_launch_gram_tile(vi, vj, stride, n, nsite, ti, tj, dst->partials, dst->stream);
+			dst->launches += 1;
+			double sums[16];
+			for (int q = 0; q < 16 && rc == 0; q += 4) {                  // scal_dev holds 8 values: reduce the 16 sums in four rounds
+				lpp_launch_finalize_sums(dst->partials + (uint64_t)q * npb, npb, 4, dst->scal_dev, dst->stream);
+				cudaStream_t cs = dst->stream;
+				if (dst->desc.nranks > 1) {
+					if (!dst->comm) { rc = fail(LPP_ERR_STATE, "nranks>1 but no communicator"); break; }
+					if (g_nccl.AllReduce(dst->scal_dev, dst->scal_dev, 4, kNcclFloat64, kNcclSum, dst->comm, cs) != 0) { rc = fail(LPP_ERR_NCCL, "all-reduce failed"); break; }
+				}
+				if (cudaMemcpyAsync(dst->scal_host, dst->scal_dev, sizeof(double) * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
+				    cudaStreamSynchronize(cs) != cudaSuccess) { rc = fail(LPP_ERR_CUDA, "two_point reduction failed"); break; }
+				for (int k = 0; k < 4; k++) sums[q + k] = dst->scal_host[k];
+			}
+			for (int a = 0; a < 4; a++)
+				for (int b = 0; b < 4; b++) {
+					const int i = ti * 4 + a, j = tj * 4 + b;
+					if (i < nsite && j < nsite) result[i * nsite + j] = sums[a * 4 + b];
+				}
+		}
+	cudaFree(vecs);
+	return rc;
+}
+
 extern "C" int lpp_get_vector(lpp_handle* h, int32_t which, double* out_host)
 {
 	if (!h || !out_host) return fail(LPP_ERR_ARG, "null argument");

@@ -568,6 +568,42 @@ __global__ void __launch_bounds__(1024) k_finalize_sums(const double* __restrict
 	s = lpp_block_sum(s);
 	if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
+// Engine::twoPoint (Engine.h:262-331): result(i, j) = <m_j | m_i> for the modified states m_i = O_i |gs>.  One CTA column
+// accumulates a 4 x 4 tile of the Gram matrix over a grid-stride range of elements (8 vectors read per pass).
+__global__ void __launch_bounds__(LPP_TPB) k_gram_tile(const double* __restrict__ veci, const double* __restrict__ vecj, uint64_t stride,
+                                                      uint64_t n, int nvec, int ti, int tj, double* __restrict__ partials)
+{
+	double acc[4][4];
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+	for (uint64_t e = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; e < n; e += (uint64_t)gridDim.x * LPP_TPB) {
+		double vi[4], vj[4];
+#pragma unroll
+		for (int a = 0; a < 4; a++) {
+			vi[a] = (ti * 4 + a < nvec) ? veci[(uint64_t)(ti * 4 + a) * stride + e] : 0.0;
+			vj[a] = (tj * 4 + a < nvec) ? vecj[(uint64_t)(tj * 4 + a) * stride + e] : 0.0;
+		}
+#pragma unroll
+		for (int a = 0; a < 4; a++)
+#pragma unroll
+			for (int b = 0; b < 4; b++) acc[a][b] = fma(vi[a], vj[b], acc[a][b]);
+	}
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+#pragma unroll
+		for (int b = 0; b < 4; b++) {
+			const double t = lpp_block_sum(acc[a][b]);
+			if (threadIdx.x == 0) partials[(uint64_t)(a * 4 + b) * gridDim.x + blockIdx.x] = t;
+		}
+}
+void lpp_launch_gram_tile(const double* veci, const double* vecj, uint64_t stride, uint64_t n, int nvec, int ti, int tj, double* partials,
+                          cudaStream_t s)
+{
+	k_gram_tile<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(veci, vecj, stride, n, nvec, ti, tj, partials);
+}
+
 void lpp_launch_reortho_dots(const double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s)
 {
 	k_reortho_dots<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(x, r, n, partials);

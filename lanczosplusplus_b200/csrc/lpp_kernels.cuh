@@ -37,6 +37,8 @@ struct RoVecs {              // a block of saved Lanczos vectors and the project
 };
 void lpp_launch_reortho_dots(const double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
 void lpp_launch_reortho_axpy_norm(double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_gram_tile(const double* veci, const double* vecj, uint64_t stride, uint64_t n, int nvec, int ti, int tj, double* partials,
+                          cudaStream_t s);
 void lpp_launch_finalize_sums(const double* partials, int n, int nv, double* out, cudaStream_t s);
 void lpp_launch_build_colex(const uint64_t* binom, int nsite, int npart, uint64_t n, word_t* out, cudaStream_t s);
 void lpp_launch_build_feas(const ModelDev& m, int spin, uint64_t n, word_t* out, cudaStream_t s);

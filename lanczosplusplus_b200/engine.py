@@ -289,6 +289,20 @@ class Engine:
     def energies(self, ind=0):
         return self.energy
 
+    def twoPoint(self, op, spin=0, orbs=(0, 0)):
+        """Engine.h:262-331 with bra = ket = ground state: matrix result(i, j) = <O_j gs | O_i gs> (c: <cdagger_j c_i>)."""
+        if op == OP_N:
+            dst, own = self.mat, False
+        else:
+            dn = -1 if op == OP_C else 1
+            dst, own = self.mat.sector(self.mat.nup + (dn if spin == 0 else 0), self.mat.ndown + (dn if spin == 1 else 0)), True
+        n = self.mat.nsite
+        out = np.zeros((n, n))
+        check(_lib.lib().lpp_two_point(self.mat.h, dst.h, op, spin, orbs[0], orbs[1], out.ctypes.data))
+        if own:
+            dst.close()
+        return out
+
     def spectralFunction(self, op, isite, jsite, spin=0, orbs=(0, 0)):
         """Engine.h:133-206 for the fermionic c/cdagger of HubbardOneBand, FeAsBasedSc (orbital pair) and Tj1Orbital:
         list of (type, ContinuedFraction)."""

@@ -1450,6 +1450,28 @@ void orc_apply_op_orb(const orc_model* src, const orc_model* dst, int op, int si
 	}
 }
 
+/* Engine::twoPoint (Engine.h:262-331) with bra = ket = gs: result(isite, jsite) = modifVector2 * modifVector1 */
+void orc_two_point(const orc_model* src, const orc_model* dst, int op, int spin, int orb_i, int orb_j, const double* gs,
+                   double* result)
+{
+	int nsite = src->nsite;
+	size_t nd = orc_rows(dst);
+	double* m1 = (double*)malloc(sizeof(double) * (nd ? nd : 1));
+	double* m2 = (double*)malloc(sizeof(double) * (nd ? nd : 1));
+	for (int isite = 0; isite < nsite; isite++) {
+		memset(m1, 0, sizeof(double) * nd);
+		orc_apply_op_orb(src, dst, op, isite, spin, orb_i, 1.0, gs, m1);
+		for (int jsite = 0; jsite < nsite; jsite++) {
+			memset(m2, 0, sizeof(double) * nd);
+			orc_apply_op_orb(src, dst, op, jsite, spin, orb_j, 1.0, gs, m2);
+			double s = 0;
+			for (size_t k = 0; k < nd; k++) s += m2[k] * m1[k];
+			result[isite * nsite + jsite] = s;
+		}
+	}
+	free(m1); free(m2);
+}
+
 void orc_apply_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, double factor,
                   const double* srcv, double* z)
 {

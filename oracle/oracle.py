@@ -84,6 +84,7 @@ def lib():
                                    C.c_void_p]
         L.orc_apply_op_orb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p,
                                        C.c_void_p]
+        L.orc_two_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
         _lib = L
     return _lib
@@ -238,6 +239,14 @@ class OracleModel:
         srcv = _f64(srcv)
         lib().orc_apply_op_orb(self.h, dst.h, op, site, spin, orb, factor, srcv.ctypes.data, z.ctypes.data)
         return z
+
+
+def two_point(src, dst, op, spin, gs, orbs=(0, 0)):
+    """Engine::twoPoint with bra = ket = gs: nsite x nsite matrix <O_j gs | O_i gs>."""
+    gs = _f64(gs)
+    out = np.zeros((src.nsite, src.nsite))
+    lib().orc_two_point(src.h, dst.h, op, spin, orbs[0], orbs[1], gs.ctypes.data, out.ctypes.data)
+    return out
 
 
 def crs_matvec(rowptr, colind, vals, x, y):

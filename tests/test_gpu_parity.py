@@ -485,3 +485,27 @@ def test_continued_fraction_other_models(lpp, oracle, name, orbs, steps):
             gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
             assert np.abs(cf(omega, 0.1) - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max()), (name, spin, typ)
     eng.close()
+
+
+@pytest.mark.parametrize("name,orbs", [("c1_hub8", (0, 0)), ("hub_rand7", (0, 0)), ("feas4", (0, 1)), ("tj8_V", (0, 0))])
+def test_two_point_matches_oracle(lpp, oracle, name, orbs):
+    """Engine::twoPoint (Engine.h:262-331) on the device: <cdagger_j c_i> for both spins and <n_j n_i> (Hubbard) against the
+    oracle; the trace of the one-body density matrix is the electron number of that species and orbital."""
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 5)
+    e0, z0, _, _ = o.ground_state(init, 300, 1e-13, 4)
+    eng = cases.make_engine(lpp, case)
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13}, init=init)
+    eng.set_groundstate(z0)
+    for spin in (0, 1):
+        od = cases.make_oracle(oracle, dict(case, nup=case["nup"] - (1 if spin == 0 else 0), ndown=case["ndown"] - (1 if spin == 1 else 0)))
+        ref = oracle.two_point(o, od, oracle.OP_C, spin, z0, orbs)
+        got = en.twoPoint(lpp.OP_C, spin=spin, orbs=orbs)
+        assert np.abs(got - ref).max() <= 1e-12
+        if orbs[0] == orbs[1] and case["orbitals"] == 1:
+            assert abs(np.trace(got) - (case["nup"] if spin == 0 else case["ndown"])) <= 1e-10
+    if case["model"] == cases.HUBBARD:
+        ref = oracle.two_point(o, o, oracle.OP_N, 0, z0)
+        assert np.abs(en.twoPoint(lpp.OP_N, spin=0) - ref).max() <= 1e-12
+    eng.close()
