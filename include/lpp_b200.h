@@ -142,6 +142,12 @@ int lpp_lanczos_decomposition(lpp_handle* h, const lpp_solver_params* p, const d
 int lpp_ground_state(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int32_t want_vector,
                      double* energy, double* z_host, double* a, double* b, int32_t* nsteps);
 
+/* lanczosSolver.computeAllStatesBelow(eigs, zs, initial, excitedPlusOne) (Engine.h:601-657 with excited > 0): the lowest nstates
+ * Ritz values of one decomposition (convergence watched on state nstates-1) and, when z_host != NULL, their vectors
+ * (nstates x rows, state k at z_host + k*rows).  State 0 stays in the handle as the ground state. */
+int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int32_t nstates, double* energies,
+                     double* z_host, int32_t* nsteps);
+
 /* Engine::accModifiedState_ (Engine.h:416-458) for c / cdagger / n on Hubbard-type bases
  * (BasisHubbardLanczos.h:106-137,162-182; 64-bit indices): dst.modified (+)= factor * O_{site,spin} |src.groundstate>.
  * accumulate == 0 zeroes dst.modified first. */

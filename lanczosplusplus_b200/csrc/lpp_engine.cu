@@ -115,6 +115,7 @@ struct lpp_handle {
 	double* modified = nullptr;
 	double* partials = nullptr;
 	int partials_cap = 0;
+	int conv_index = 0;           // which Ritz value the convergence test of the Krylov loop watches (0 = lowest)
 	double* scal_dev = nullptr;
 	double* scal_host = nullptr;
 	// comm
@@ -676,7 +677,11 @@ extern "C" int lpp_matvec_host(lpp_handle* h, int32_t kernel, double* x, const d
 
 // ------------------------------------------------------------------ tridiagonal eigen-solvers (host)
 // lowest eigenvalue by Sturm-sequence bisection (used every Lanczos step for the convergence test)
-static double tridiag_lowest(int n, const double* a, const double* b)
+static double tridiag_kth(int n, const double* a, const double* b, int k);
+static double tridiag_lowest(int n, const double* a, const double* b) { return tridiag_kth(n, a, b, 0); }
+
+// k-th lowest eigenvalue (k = 0 .. n-1) of the symmetric tridiagonal (a, b) by Sturm-sequence bisection
+static double tridiag_kth(int n, const double* a, const double* b, int k)
 {
 	if (n == 1) return a[0];
 	double lo = a[0], hi = a[0];
@@ -700,7 +705,7 @@ static double tridiag_lowest(int n, const double* a, const double* b)
 	for (int it = 0; it < 200; it++) {
 		double mid = 0.5 * (lo + hi);
 		if (mid <= lo || mid >= hi) break;
-		if (count_below(mid) >= 1) hi = mid; else lo = mid;
+		if (count_below(mid) >= k + 1) hi = mid; else lo = mid;
 	}
 	return 0.5 * (lo + hi);
 }
@@ -1188,9 +1193,13 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 		nj = (bj < 1e-10) ? 1.0 : bj;
 		std::swap(x, y);
 		if (check_convergence && p->eps > 0) {
-			double enew = tridiag_lowest(j + 1, a, b);
-			if (fabs(enew - eold) < p->eps && (j >= p->minsteps || h->rows <= 4)) { j++; break; }
-			eold = enew;
+			// LanczosSolver::computeAllStatesBelow watches the highest requested state; until the tridiagonal has that many
+			// rows there is nothing to compare
+			if (j >= h->conv_index) {
+				double enew = tridiag_kth(j + 1, a, b, h->conv_index);
+				if (fabs(enew - eold) < p->eps && (j >= p->minsteps || h->rows <= 4)) { j++; break; }
+				eold = enew;
+			}
 		}
 	}
 	*nsteps = j;
@@ -1253,6 +1262,47 @@ extern "C" int lpp_ground_state(lpp_handle* h, const lpp_solver_params* p, const
 	}
 	if (a) std::copy(aa.begin(), aa.begin() + ns, a);
 	if (b) std::copy(bb.begin(), bb.begin() + ns, b);
+	if (nsteps) *nsteps = ns;
+	return 0;
+}
+
+// LanczosSolver::computeAllStatesBelow(eigs, zs, initial, excitedPlusOne) (Engine.h:626): the lowest `nstates` Ritz pairs of one
+// decomposition whose convergence test watches state nstates-1.  Vectors are rebuilt by replaying the recurrence once per state
+// (nothing is saved unless p->reortho); state 0 stays in the handle as the ground state.  Without reorthogonalisation the higher
+// Ritz values of a long run can be ghost copies of converged ones (the same holds for the reference): use Options=reortho.
+extern "C" int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int32_t nstates, double* energies,
+                                double* z_host, int32_t* nsteps)
+{
+	if (!h || !p || !energies || nstates < 1) return fail(LPP_ERR_ARG, "bad argument");
+	if ((uint64_t)nstates > h->rows) return fail(LPP_ERR_ARG, "more states requested than the sector has rows");
+	CK(cudaSetDevice(h->device));
+	int cap = (int)std::min<uint64_t>((uint64_t)p->steps, h->rows);
+	if (cap < nstates) return fail(LPP_ERR_ARG, "LanczosSteps smaller than the number of states requested");
+	std::vector<double> aa(cap + 1), bb(cap + 1);
+	CKR(load_init(h, p, init_host, 0));
+	int ns = 0;
+	h->conv_index = nstates - 1;
+	int rc = lanczos_loop(h, p, p->steps, true, nullptr, nullptr, aa.data(), bb.data(), &ns, nullptr, nullptr);
+	h->conv_index = 0;
+	if (rc != 0) return rc;
+	if (ns < nstates) return fail(LPP_ERR_STATE, "the Krylov space closed before the requested number of states");
+	std::vector<double> d(aa.begin(), aa.begin() + ns), e(ns, 0.0), zz((size_t)ns * ns);
+	for (int i = 0; i + 1 < ns; i++) e[i] = bb[i];
+	if (tridiag_full(ns, d, e, zz.data()) != 0) return fail(LPP_ERR_STATE, "tridiagonal QL did not converge");
+	for (int k = 0; k < nstates; k++) energies[k] = d[k];
+	if (z_host) {
+		if (!h->gs) CKR(dev_alloc(h, &h->gs, h->nloc));
+		std::vector<double> coef(ns), a2(ns + 1), b2(ns + 1);
+		for (int k = nstates - 1; k >= 0; k--) {                       // state 0 last: it stays in h->gs
+			for (int j = 0; j < ns; j++) coef[j] = zz[(size_t)j * ns + k];
+			CK(cudaMemsetAsync(h->gs, 0, sizeof(double) * h->nloc, h->stream));
+			CKR(load_init(h, p, init_host, 0));
+			int ns2 = 0;
+			CKR(lanczos_loop(h, p, ns, false, coef.data(), h->gs, a2.data(), b2.data(), &ns2, nullptr, nullptr));
+			CK(cudaStreamSynchronize(h->stream));
+			CK(cudaMemcpy(z_host + (uint64_t)k * h->rows + h->row0, h->gs, sizeof(double) * h->nloc, cudaMemcpyDeviceToHost));
+		}
+	}
 	if (nsteps) *nsteps = ns;
 	return 0;
 }

@@ -251,6 +251,25 @@ class LanczosSolver:
         return e.value, z, a[:ns.value].copy(), b[:ns.value].copy()
 
 
+def _states_below(solver, init, excited_plus_one, want_vectors):
+    p = solver._p()
+    eigs = np.zeros(excited_plus_one)
+    init = _f64(init)
+    zs = np.zeros((excited_plus_one, solver.mat.rows())) if want_vectors else None
+    ns = C.c_int32()
+    check(_lib.lib().lpp_states_below(solver.mat.h, C.byref(p), None if init is None else init.ctypes.data, excited_plus_one,
+                                      eigs.ctypes.data, None if zs is None else zs.ctypes.data, C.byref(ns)))
+    return eigs, zs, ns.value
+
+
+def _computeAllStatesBelow(self, init=None, excited_plus_one=1, want_vectors=True):
+    """-> (eigs, zs, steps): lanczosSolver.computeAllStatesBelow(eigs, zs, initial, excitedPlusOne), Engine.h:626."""
+    return _states_below(self, init, excited_plus_one, want_vectors)
+
+
+LanczosSolver.computeAllStatesBelow = _computeAllStatesBelow
+
+
 def tridiag_eig(a, b, vectors=False):
     n = len(a)
     a = _f64(a)

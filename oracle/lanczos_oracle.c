@@ -1229,6 +1229,69 @@ static void one_step_reortho(orc_mv_fn mv, void* ctx, int64_t n, double* x, doub
 	*b_out = b;
 }
 
+static double tridiag_kth(int n, const double* a, const double* b, int k)
+{
+	double* d = (double*)malloc(sizeof(double) * n);
+	double* e = (double*)malloc(sizeof(double) * (n > 0 ? n : 1));
+	memcpy(d, a, sizeof(double) * n);
+	memcpy(e, b, sizeof(double) * n);
+	orc_tridiag_eig(n, d, e, NULL);
+	double r = d[k];
+	free(d); free(e);
+	return r;
+}
+
+/* LanczosSolver::computeAllStatesBelow (Engine.h:626; PARITY UNPINNED, PsimagLite absent): one decomposition with every
+ * vector saved and reorthogonalised, convergence watched on Ritz value nstates-1, then the lowest nstates Ritz pairs;
+ * z (nstates x rows) may be NULL.  Returns the step count. */
+int orc_states_below(const orc_model* m, const double* init, int steps, double eps, int minsteps, int nstates,
+                     double* energies, double* z)
+{
+	mv_model_ctx c = {m, 0};
+	int64_t n = (int64_t)orc_rows(m);
+	double* x = (double*)calloc(n, sizeof(double));
+	double* y = (double*)malloc(sizeof(double) * n);
+	double nrm = 0;
+	for (int64_t i = 0; i < n; i++) nrm += init[i] * init[i];
+	nrm = sqrt(nrm);
+	for (int64_t i = 0; i < n; i++) y[i] = init[i] / nrm;
+	if (steps > n) steps = (int)n;
+	double** saved = (double**)calloc(steps > 0 ? steps : 1, sizeof(double*));
+	double* a = (double*)calloc(steps + 1, sizeof(double));
+	double* b = (double*)calloc(steps + 1, sizeof(double));
+	double eold = 100.0;
+	int j = 0;
+	for (; j < steps; j++) {
+		saved[j] = (double*)malloc(sizeof(double) * n);
+		memcpy(saved[j], y, sizeof(double) * n);
+		one_step_reortho(mv_model, &c, n, x, y, saved, j + 1, &a[j], &b[j]);
+		if (eps > 0 && j >= nstates - 1) {
+			double enew = tridiag_kth(j + 1, a, b, nstates - 1);
+			if (fabs(enew - eold) < eps && (j >= minsteps || n <= 4)) { j++; break; }
+			eold = enew;
+		}
+	}
+	int ns = j;
+	double* d = (double*)malloc(sizeof(double) * ns);
+	double* e = (double*)calloc(ns > 0 ? ns : 1, sizeof(double));
+	double* zz = (double*)malloc(sizeof(double) * (size_t)ns * ns);
+	memcpy(d, a, sizeof(double) * ns);
+	for (int i = 0; i + 1 < ns; i++) e[i] = b[i];
+	orc_tridiag_eig(ns, d, e, zz);
+	for (int k = 0; k < nstates && k < ns; k++) {
+		energies[k] = d[k];
+		if (!z) continue;
+		for (int64_t i = 0; i < n; i++) z[(size_t)k * n + i] = 0;
+		for (int q = 0; q < ns; q++) {
+			double cq = zz[(size_t)q * ns + k];
+			for (int64_t i = 0; i < n; i++) z[(size_t)k * n + i] += cq * saved[q][i];
+		}
+	}
+	for (int k = 0; k < steps; k++) free(saved[k]);
+	free(saved); free(x); free(y); free(a); free(b); free(d); free(e); free(zz);
+	return ns;
+}
+
 /* decomposition with every Lanczos vector saved and full reorthogonalisation; returns the step count */
 int orc_lanczos_decomposition_reortho(const orc_model* m, const double* init, int steps, double eps, int minsteps,
                                       double* a, double* b)

@@ -72,6 +72,8 @@ def lib():
         L.orc_lanczos_decomposition_reortho.restype = C.c_int
         L.orc_lanczos_decomposition_reortho.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p,
                                                         C.c_void_p]
+        L.orc_states_below.restype = C.c_int
+        L.orc_states_below.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_lanczos_decomposition_crs.restype = C.c_int
         L.orc_lanczos_decomposition_crs.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
@@ -222,6 +224,15 @@ class OracleModel:
         ns = lib().orc_lanczos_decomposition_reortho(self.h, init.ctypes.data, steps, eps, minsteps, a.ctypes.data,
                                                      b.ctypes.data)
         return a[:ns].copy(), b[:ns].copy()
+
+    def states_below(self, init, nstates, steps=200, eps=1e-12, minsteps=4):
+        """Lowest nstates Ritz pairs with full reorthogonalisation (computeAllStatesBelow, Engine.h:626)."""
+        n = self.rows()
+        init = _f64(init)
+        eigs = np.zeros(nstates)
+        zs = np.zeros((nstates, n))
+        ns = lib().orc_states_below(self.h, init.ctypes.data, steps, eps, minsteps, nstates, eigs.ctypes.data, zs.ctypes.data)
+        return eigs, zs, ns
 
     def ground_state(self, init, steps=200, eps=1e-12, minsteps=4, want_vector=True, faithful=False):
         n = self.rows()

@@ -509,3 +509,31 @@ def test_two_point_matches_oracle(lpp, oracle, name, orbs):
         ref = oracle.two_point(o, o, oracle.OP_N, 0, z0)
         assert np.abs(en.twoPoint(lpp.OP_N, spin=0) - ref).max() <= 1e-12
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["hub_rand7", "feas4", "tj7_rand"])
+def test_states_below_excited_states(lpp, oracle, name):
+    """computeAllStatesBelow with excited > 0 (Engine.h:601-657): the lowest four Ritz pairs with Options=reortho against the
+    oracle and, for the energies, against a dense diagonalisation of the stored Hamiltonian (distinct eigenvalues)."""
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    o = cases.make_oracle(oracle, case)
+    n = o.rows()
+    init = geo.splitmix64_vector(n, 31)
+    e0, z0, _ = o.states_below(init, 4, steps=300, eps=1e-12)
+    eng = cases.make_engine(lpp, case)
+    solver = lpp.LanczosSolver(eng, lpp.ParametersForSolver(steps=300, eps=1e-12, options="reortho"))
+    e1, z1, steps = solver.computeAllStatesBelow(init, 4)
+    assert np.abs(e1 - e0).max() <= 1e-9 * max(1.0, np.abs(e0).max())
+    import scipy.sparse as sp
+    rp, ci, v = o.crs()
+    H = sp.csr_matrix((v, ci, rp), shape=(n, n))
+    distinct = np.unique(np.round(np.linalg.eigvalsh(H.toarray()), 8))
+    assert np.abs(e1 - distinct[:4]).max() <= 1e-7
+    for k in range(4):
+        assert abs(np.linalg.norm(z1[k]) - 1.0) <= 1e-8
+        r = H @ z1[k] - e1[k] * z1[k]
+        assert np.linalg.norm(r) <= 1e-5                                  # Ritz residual of a converged pair
+        for q in range(k):
+            assert abs(z1[k] @ z1[q]) <= 1e-7
+    assert np.abs(eng.get_vector(0) - z1[0]).max() == 0.0                  # state 0 stays in the handle
+    eng.close()
