@@ -880,7 +880,11 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 	if (h->md.model != LPP_MODEL_HUBBARD) return 0;          // FeAs two-spin terms need arbitrary remote elements
 	if (resolve_kernel(h, kernel) != LPP_KERNEL_TILED) return 0;
 	CKR(ensure_tiled(h));
-	if (!lpp_tiled_two_layout_ok(h->tiled)) return 0;
+	const int tl = lpp_tiled_two_layout_ok(h->tiled);
+	if (tl == 0) return 0;
+	// blocked up sweep (tl == 2): two-layout pays off with the peer-memory exchange only; handles that borrowed a communicator
+	// (new sectors of the continued-fraction path) exchange over NCCL send/recv and keep the gather scheme
+	if (tl == 2 && h->comm_borrowed) return 0;
 	const int G = h->desc.nranks, me = h->desc.rank;
 	const uint64_t n1 = h->md.n1, n2 = h->md.n2;
 	h->cols.nranks = G;

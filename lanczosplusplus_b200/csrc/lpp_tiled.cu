@@ -386,7 +386,7 @@ k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0,
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			acc[r] = 0.0;
-			xold[r] = live[r] ? xrow[r][u] : 0.0;        // issued early, consumed after the gathers
+			xold[r] = (live[r] && a.beta != 0.0) ? xrow[r][u] : 0.0;   // issued early, consumed after the gathers
 		}
 		int k = 0;
 		for (; k < next; k++) {                          // hops leaving the block (only when the up basis is split)
@@ -417,7 +417,7 @@ k_sweep_up_blocks(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0,
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			if (!live[r]) continue;
-			double xn = xold[r] + a.alpha * acc[r];
+			double xn = a.beta * xold[r] + a.alpha * acc[r];
 			xrow[r][u] = xn;
 			contrib += ys[i * R + r] * xn;
 		}
@@ -476,7 +476,7 @@ k_sweep_up_pipe(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0, u
 		for (int j = 0; j < NE; j++) en[j] = (j < width) ? tcol[(uint64_t)j * n1] : TE_HOLE;
 		mnext = up.meta[u];
 #pragma unroll
-		for (int r = 0; r < R; r++) xn_old[r] = live[r] ? xrow[r][u] : 0.0;
+		for (int r = 0; r < R; r++) xn_old[r] = (live[r] && a.beta != 0.0) ? xrow[r][u] : 0.0;
 	};
 	uint32_t i = threadIdx.x;
 	if (i < bsize) prefetch(i);                          // overlaps with the cp.async staging
@@ -532,7 +532,7 @@ k_sweep_up_pipe(ModelDev m, SpinPlan up, MagTable mt, SpmvArgs a, uint64_t d0, u
 #pragma unroll
 		for (int r = 0; r < R; r++) {
 			if (!live[r]) continue;
-			double xn = xold[r] + a.alpha * acc[r];
+			double xn = a.beta * xold[r] + a.alpha * acc[r];
 			xrow[r][u] = xn;
 			contrib += ys[i * R + r] * xn;
 		}
@@ -1879,12 +1879,14 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 #undef RUNL
 	} else if (p->v2) {
 		const unsigned gridB = (unsigned)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
-#define RUNB(R_, N_) k_sweep_up_pipe<R_, N_><<<gridB, PBP_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b)
+		SpmvArgs ab = a;
+		ab.beta = 1.0;                                  // sweep A already applied beta
+#define RUNB(R_, N_) k_sweep_up_pipe<R_, N_><<<gridB, PBP_THREADS, p->smemB, s>>>(m, p->up, p->mt, ab, p->d0, p->dcount, dot_in_b)
 		if (p->pipeB) {
 			if (p->R == 2) { if (p->NE == 16) RUNB(2, 16); else if (p->NE == 24) RUNB(2, 24); else RUNB(2, 32); }
 			else { if (p->NE == 16) RUNB(1, 16); else if (p->NE == 24) RUNB(1, 24); else RUNB(1, 32); }
-		} else if (p->R == 2) k_sweep_up_blocks<2><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
-		else k_sweep_up_blocks<1><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, p->d0, p->dcount, dot_in_b);
+		} else if (p->R == 2) k_sweep_up_blocks<2><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, ab, p->d0, p->dcount, dot_in_b);
+		else k_sweep_up_blocks<1><<<gridB, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, ab, p->d0, p->dcount, dot_in_b);
 #undef RUNB
 	} else if (p->up_in_smem) {
 		k_sweep_up_smem<<<(unsigned)p->dcount, PB_THREADS, p->up_smem_bytes, s>>>(m, up, a, p->d0, dot_in_b);
@@ -1911,9 +1913,24 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 // two-layout multi-GPU entry points: the up sweep runs on the rank's ROW shard (all up states, local down range),
 // the down sweep (+ diagonal) on the rank's COLUMN shard (all down states, local up range).
 // ---------------------------------------------------------------------------------------------------------------
-int lpp_tiled_two_layout_ok(const TiledPlan* p) { return (p->v2 && (p->leanB || p->packedB) && !p->has_twospin) ? 1 : 0; }
+// any v2 up sweep works on a row shard: the one-block kernels (lean / packed) and the blocked ones (an up segment larger than
+// shared memory, e.g. 48 620 up states of the 18-site chain)
+// returns 1 for the one-block kernels, 2 for the blocked ones (the caller decides: with peer memory the blocked two-layout
+// run of config 5 takes 17.6 ms per iteration against 41.9 ms for the gather scheme; over NCCL send/recv it is slower, 54.7 ms
+// against 34.8 ms), 0 when the plan cannot be sharded that way
+int lpp_tiled_two_layout_ok(const TiledPlan* p)
+{
+	static const bool blocked_ok = !(getenv("LPP_TWO_LAYOUT_BLOCKED") && getenv("LPP_TWO_LAYOUT_BLOCKED")[0] == '0');
+	if (!p->v2 || p->has_twospin) return 0;
+	if (p->leanB || p->packedB) return 1;
+	return blocked_ok ? 2 : 0;
+}
 
-int lpp_tiled_up_rows_blocks(const TiledPlan* p, uint64_t nrows) { return (int)((nrows + p->R - 1) / p->R); }
+int lpp_tiled_up_rows_blocks(const TiledPlan* p, uint64_t nrows)
+{
+	const uint64_t pairs = (nrows + p->R - 1) / p->R;
+	return (int)((p->leanB || p->packedB) ? pairs : pairs * p->up.nblocks);
+}
 
 // x = beta x + alpha (T_up (x) 1) y on `nrows` local rows; x, y are the local row blocks (row r at r*Nup)
 int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, uint64_t nrows, cudaStream_t s)
@@ -1928,8 +1945,19 @@ int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, 
 		if (p->packedE16 && p->packedNG == 12) { if (uni) RUNP(true, true, 12); else RUNP(false, true, 12); }
 		else if (p->packedE16) { if (uni) RUNP(true, true, 8); else RUNP(false, true, 8); }
 		else { if (uni) RUNP(true, false, 8); else RUNP(false, false, 8); }
-	} else if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
-	else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+	} else if (p->leanB) {
+		if (p->R == 2) { if (p->mt.nmag == 1) RUNL(2, true); else RUNL(2, false); }
+		else { if (p->mt.nmag == 1) RUNL(1, true); else RUNL(1, false); }
+	} else {
+		// blocked up sweep on the row shard (same kernels as lpp_tiled_spmv, local rows 0 .. nrows)
+#define RUNB(R_, N_) k_sweep_up_pipe<R_, N_><<<gridL, PBP_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, 0, nrows, want_dot)
+		if (p->pipeB) {
+			if (p->R == 2) { if (p->NE == 16) RUNB(2, 16); else if (p->NE == 24) RUNB(2, 24); else RUNB(2, 32); }
+			else { if (p->NE == 16) RUNB(1, 16); else if (p->NE == 24) RUNB(1, 24); else RUNB(1, 32); }
+		} else if (p->R == 2) k_sweep_up_blocks<2><<<gridL, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, 0, nrows, want_dot);
+		else k_sweep_up_blocks<1><<<gridL, PB_THREADS, p->smemB, s>>>(m, p->up, p->mt, a, 0, nrows, want_dot);
+#undef RUNB
+	}
 #undef RUNP
 #undef RUNL
 	cudaError_t e = cudaGetLastError();

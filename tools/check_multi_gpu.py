@@ -15,7 +15,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for name, kw in (("hubbard 4x3", dict(model=lpp.HUBBARD, nsite=12, nup=6, ndown=6, hop=geo.square(4, 3, -1.0), U=np.full(12, 4.0), V=np.zeros(12))),
+for name, kw in (("hubbard 18-chain 9 up 2 down (blocked up sweep)", dict(model=lpp.HUBBARD, nsite=18, nup=9, ndown=2, hop=geo.chain(18, -1.0), U=np.full(18, 4.0), V=np.zeros(18))),
+                 ("hubbard 4x3", dict(model=lpp.HUBBARD, nsite=12, nup=6, ndown=6, hop=geo.square(4, 3, -1.0), U=np.full(12, 4.0), V=np.zeros(12))),
                  ("feas 2x3", dict(model=lpp.FEAS, nsite=6, nup=4, ndown=4, orbitals=2,
                                    hop=geo.with_orbitals(geo.square(2, 3, -1.0, False, False), 2, 1.0, 0.5),
                                    U=np.array([4.0, 3.0, -0.8, -0.4]), V=np.zeros(24), D=np.array([0.0]))),
@@ -25,6 +26,12 @@ for name, kw in (("hubbard 4x3", dict(model=lpp.HUBBARD, nsite=12, nup=6, ndown=
         D.attach(sharded, dist)
         p = lpp.ParametersForSolver(steps=60, eps=0.0, seed=1234)
         a, b, _ = lpp.LanczosSolver(sharded, p).decomposition(None)
+        torch.cuda.synchronize()
+        import time
+        t0 = time.perf_counter()
+        a, b, _ = lpp.LanczosSolver(sharded, p).decomposition(None)
+        torch.cuda.synchronize()
+        ms_iter = 1e3 * (time.perf_counter() - t0) / len(a)
         single = lpp.InternalProductCuda(device=local, kernel=kernel, **kw)
         a1, b1, _ = lpp.LanczosSolver(single, p).decomposition(None)
         err = max(np.abs(a[:25] - a1[:25]).max(), np.abs(b[:25] - b1[:25]).max())
@@ -33,7 +40,7 @@ for name, kw in (("hubbard 4x3", dict(model=lpp.HUBBARD, nsite=12, nup=6, ndown=
         good = err < 1e-10 and abs(e - e1) < 1e-9
         ok = ok and good
         if rank == 0:
-            print("%-14s kernel %d ranks %d: max|d(a,b)| %.2e  E %.12f vs %.12f  %s" % (name, kernel, world, err, e, e1, "OK" if good else "FAIL"), flush=True)
+            print("%-14s kernel %d ranks %d: max|d(a,b)| %.2e  E %.12f vs %.12f  %.3f ms/iteration  %s" % (name, kernel, world, err, e, e1, ms_iter, "OK" if good else "FAIL"), flush=True)
         sharded.close()
         single.close()
 dist.barrier()
