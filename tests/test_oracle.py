@@ -144,3 +144,39 @@ def test_continued_fraction_matches_resolvent(oracle):
     amp = (vd.T @ phi) ** 2
     ref = np.array([(amp / (o + 0.1j - (wd - eg))).sum() for o in omega])
     assert np.abs(g - ref).max() < 1e-8
+
+
+def test_reortho_removes_ghost_ritz_values(oracle):
+    """<prefix>Options=reortho in the oracle (one_step_reortho): the plain recurrence on the Heisenberg 12-ring repeats its lowest
+    Ritz value after 120 steps, the reorthogonalised one lands on distinct eigenvalues of the stored Hamiltonian."""
+    m = cases.make_oracle(oracle, cases.SMALL_CASES["heis12"])
+    n = m.rows()
+    init = geo.splitmix64_vector(n, 99)
+    a0, b0 = m.decomposition(init, steps=120, eps=0.0)
+    a1, b1 = m.decomposition_reortho(init, steps=120, eps=0.0)
+    assert np.abs(a0[:20] - a1[:20]).max() < 1e-12 and np.abs(b0[:20] - b1[:20]).max() < 1e-12
+    plain, ro = oracle.tridiag_eig(a0, b0), oracle.tridiag_eig(a1, b1)
+    exact = np.unique(np.round(np.linalg.eigvalsh(crs_matrix(m).toarray()), 9))
+    assert abs(plain[1] - plain[0]) < 1e-8                       # ghost copy of the ground state
+    assert np.all(np.diff(ro[:4]) > 1e-6)
+    for r in ro[:4]:
+        assert np.abs(exact - r).min() < 1e-9
+
+
+def test_states_below_and_two_point_in_the_oracle(oracle):
+    """computeAllStatesBelow (excited states) and Engine::twoPoint restated in the oracle, against dense linear algebra."""
+    case = cases.SMALL_CASES["hub_rand7"]
+    m = cases.make_oracle(oracle, case)
+    n = m.rows()
+    H = crs_matrix(m).toarray()
+    w, v = np.linalg.eigh(H)
+    eigs, zs, _ = m.states_below(geo.splitmix64_vector(n, 31), 3, steps=300, eps=1e-12)
+    assert np.abs(eigs - w[:3]).max() < 1e-9
+    for k in range(3):
+        assert abs(abs(zs[k] @ v[:, k]) - 1.0) < 1e-7
+    # one-body density matrix of the ground state: Hermitian, trace = number of up electrons, eigenvalues in [0, 1]
+    dst = cases.make_oracle(oracle, dict(case, nup=case["nup"] - 1))
+    rho = oracle.two_point(m, dst, oracle.OP_C, 0, v[:, 0])
+    assert np.abs(rho - rho.T).max() < 1e-12 and abs(np.trace(rho) - case["nup"]) < 1e-12
+    occ = np.linalg.eigvalsh(rho)
+    assert occ.min() > -1e-12 and occ.max() < 1 + 1e-12
