@@ -59,7 +59,7 @@ struct TiledPlan {
 	std::vector<uint32_t> tilesA_host;
 	uint32_t* tilesA = nullptr;   // (block, panel) pairs intersecting the local rows: block ids only, panel-major grid
 	uint32_t ntilesA_blocks = 0, npanels = 0;
-	int has_twospin = 0;
+	int has_twospin = 0, tsRows = 0;
 	uint32_t* ts_up = nullptr;    // two-spin tables [site][state] (two orbitals), see k_sweep_twospin_tab
 	uint32_t* ts_dn = nullptr;
 	double u2half = 0, u3 = 0;
@@ -1259,6 +1259,64 @@ __global__ void __launch_bounds__(256) k_sweep_twospin_tab(ModelDev m, const uin
 	}
 }
 
+// sweep C by rows: one CTA per down state d, site loop outside, so that all gathers of one (d, site) pair fall into ONE source
+// row of y (the row of d with the two orbitals of that site exchanged): 64 KB for 8 008 up states, L1 resident while the CTA
+// walks it.  k_sweep_twospin_tab (256 up states x 8 down states per CTA) touches 8 different source rows per site and pulls a
+// 32-byte sector from L2 for every 8-byte operand.  Thread t owns up states t, t + TSR_THREADS, ... (TSR_KC per pass).
+// Experiment, off by default: parity-tested (LPP_TWOSPIN_ROWS=1) but slower on config 4 (1.6 ms against 1.2 ms).
+#define TSR_THREADS 512
+#define TSR_KC 16
+__global__ void __launch_bounds__(TSR_THREADS) k_sweep_twospin_rows(ModelDev m, const uint32_t* __restrict__ tu, const uint32_t* __restrict__ td,
+                                                                  double u2half, double u3, int all_pairs, SpmvArgs a, uint64_t dcount)
+{
+	__shared__ uint32_t s_ed[64];
+	const uint64_t n1 = m.n1;
+	const uint64_t dl = blockIdx.x, d = a.row0 / n1 + dl;
+	if (threadIdx.x < (unsigned)m.nsite) s_ed[threadIdx.x] = td[(uint64_t)threadIdx.x * m.n2 + d];
+	__syncthreads();
+	double contrib = 0.0;
+	for (uint64_t base = 0; base < n1; base += (uint64_t)TSR_THREADS * TSR_KC) {
+		double acc[TSR_KC];
+#pragma unroll
+		for (int k = 0; k < TSR_KC; k++) acc[k] = 0.0;
+		for (int i = 0; i < m.nsite; i++) {
+			const uint32_t ed = s_ed[i];
+			if (!(ed & TS_VALID)) continue;                                 // CTA-uniform
+			const uint32_t od = (ed >> 25) & 1u;
+			const double* __restrict__ yrow = a.y + (uint64_t)(ed & 0xffffffu) * n1;
+			const uint32_t* __restrict__ tui = tu + (uint64_t)i * n1;
+#pragma unroll
+			for (int k = 0; k < TSR_KC; k++) {
+				const uint64_t u = base + (uint64_t)k * TSR_THREADS + threadIdx.x;
+				if (u >= n1) continue;
+				const uint32_t eu = __ldg(tui + u);
+				if (!(eu & TS_VALID)) continue;
+				const uint32_t ou = (eu >> 25) & 1u;
+				double coef;
+				if (od != ou) coef = u2half;
+				else if (all_pairs || ou == 1u) coef = -u3;
+				else continue;
+				// orb1 = 1 - ou: doSign(., i, orb1, i, orb2) is the (0,1) sign when orb1 = 0, the (1,0) sign otherwise
+				const uint32_t neg = ((ou ? (eu >> 26) : (eu >> 27)) ^ (ou ? (ed >> 26) : (ed >> 27))) & 1u;
+				acc[k] += (neg ? -coef : coef) * yrow[eu & 0xffffffu];
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < TSR_KC; k++) {
+			const uint64_t u = base + (uint64_t)k * TSR_THREADS + threadIdx.x;
+			if (u >= n1) continue;
+			const uint64_t t = dl * n1 + u;
+			const double xn = a.x[t] + a.alpha * acc[k];
+			a.x[t] = xn;
+			contrib += a.y[a.row0 + t] * xn;
+		}
+	}
+	if (a.dot_partials) {
+		double sum = tiled_block_sum(contrib);
+		if (threadIdx.x == 0) a.dot_partials[blockIdx.x] = sum;
+	}
+}
+
 // =====================================================================================================
 // plan construction
 // =====================================================================================================
@@ -1761,7 +1819,10 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		p->u3 = Uh[3];
 	}
 	// the last sweep owns the dot-product partial sums
-	if (p->has_twospin && p->ts_up) p->dot_blocks = (int)(((m.n1 + 255) / 256) * ((p->dcount + TS_ROWS - 1) / TS_ROWS));
+	// opt-in (LPP_TWOSPIN_ROWS=1): measured 1.6 ms against 1.2 ms for k_sweep_twospin_tab on config 4
+	{ const char* envt = getenv("LPP_TWOSPIN_ROWS"); p->tsRows = (envt && envt[0] == '1') && m.nsite <= 64; }
+	if (p->has_twospin && p->ts_up && p->tsRows) p->dot_blocks = (int)p->dcount;
+	else if (p->has_twospin && p->ts_up) p->dot_blocks = (int)(((m.n1 + 255) / 256) * ((p->dcount + TS_ROWS - 1) / TS_ROWS));
 	else if (p->has_twospin) p->dot_blocks = (int)((nloc + 255) / 256);
 	else if (p->v2 && (p->leanB || p->packedB)) p->dot_blocks = (int)((p->dcount + p->R - 1) / p->R);
 	else if (p->v2) p->dot_blocks = (int)(((p->dcount + p->R - 1) / p->R) * p->up.nblocks);
@@ -1895,7 +1956,10 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 		k_sweep_up_global<<<(unsigned)(nbx * p->dcount), 256, 0, s>>>(m, up, a, p->d0, nbx, dot_in_b);
 	}
 	launches++;
-	if (p->has_twospin && p->ts_up) {
+	if (p->has_twospin && p->ts_up && p->tsRows) {
+		k_sweep_twospin_rows<<<(unsigned)p->dcount, TSR_THREADS, 0, s>>>(m, p->ts_up, p->ts_dn, p->u2half, p->u3, m.u3_all_pairs, a, p->dcount);
+		launches++;
+	} else if (p->has_twospin && p->ts_up) {
 		// m.U lives on the device; the two couplings were read once at plan creation
 		const dim3 g((unsigned)((m.n1 + 255) / 256), (unsigned)((p->dcount + TS_ROWS - 1) / TS_ROWS), 1);
 		k_sweep_twospin_tab<<<g, 256, 0, s>>>(m, p->ts_up, p->ts_dn, p->u2half, p->u3, m.u3_all_pairs, a, p->dcount);

@@ -261,6 +261,23 @@ def test_staged_down_kernel(lpp, oracle, rows, pc, nb, monkeypatch):
         e.close()
 
 
+def test_twospin_rows_kernel(lpp, oracle, monkeypatch):
+    """k_sweep_twospin_rows (opt-in, LPP_TWOSPIN_ROWS=1): FeAs on-site two-spin terms with one CTA per down state."""
+    monkeypatch.setenv("LPP_TWOSPIN_ROWS", "1")
+    for name in ("feas3", "feas4", "feas4_interorb_otfquirk", "feas_2x2"):
+        case = cases.SMALL_CASES[name]
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        e = cases.make_engine(lpp, case)
+        y = geo.splitmix64_vector(o.rows(), 42)
+        x0 = geo.splitmix64_vector(o.rows(), 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+        assert relerr(x, xref) <= 1e-13, name
+        e.close()
+
+
 def test_large_up_basis_c5_structure(lpp, oracle):
     """Config-5 structure at a size one GPU and the oracle handle quickly: 18-site open chain, 9 up electrons (48 620 up
     states: an up segment no longer fits in shared memory, so the blocked up-sweep path runs), 2 down; dim 7 438 860."""
