@@ -121,6 +121,7 @@ struct lpp_handle {
 	// comm
 	ncclComm_t comm = nullptr;
 	bool comm_borrowed = false;    // lpp_comm_share: the communicator belongs to another handle
+	bool p2p_requested = false;    // lpp_p2p_export was called: the launcher is setting up the peer-memory exchange
 	// LPP_PHASES=1: CUDA-event breakdown of the sharded iteration (printed by lpp_destroy)
 	cudaStream_t copy_stream2 = nullptr;
 	cudaEvent_t ev_copy2 = nullptr;
@@ -883,8 +884,9 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 	const int tl = lpp_tiled_two_layout_ok(h->tiled);
 	if (tl == 0) return 0;
 	// blocked up sweep (tl == 2): two-layout pays off with the peer-memory exchange only; handles that borrowed a communicator
-	// (new sectors of the continued-fraction path) exchange over NCCL send/recv and keep the gather scheme
-	if (tl == 2 && h->comm_borrowed) return 0;
+	// (new sectors of the continued-fraction path) and were not given peer mappings exchange over NCCL send/recv and keep the
+	// gather scheme
+	if (tl == 2 && h->comm_borrowed && !h->p2p_requested) return 0;
 	const int G = h->desc.nranks, me = h->desc.rank;
 	const uint64_t n1 = h->md.n1, n2 = h->md.n2;
 	h->cols.nranks = G;
@@ -1461,6 +1463,7 @@ extern "C" int lpp_p2p_export(lpp_handle* h, int32_t kernel, uint8_t handles[128
 {
 	if (!h || !handles) return fail(LPP_ERR_ARG, "null argument");
 	CK(cudaSetDevice(h->device));
+	h->p2p_requested = true;
 	CKR(ensure_two_layout(h, kernel));
 	if (h->two_layout != 1) return fail(LPP_ERR_STATE, "two-layout sharding does not apply to this handle");
 	cudaIpcMemHandle_t a, b;

@@ -32,10 +32,12 @@ def attach(engine, dist):
     """Give a row-sharded InternalProductCuda its NCCL communicator."""
     from .engine import comm_unique_id
     engine.comm_init(broadcast_unique_id(dist, comm_unique_id))
+    engine._dist = dist                       # new-sector handles (engine.sector) repeat the peer-memory exchange through it
     if os.environ.get("LPP_P2P", "1") != "0":
         mine = engine.p2p_export()
         parts = [None] * dist.get_world_size()
         dist.all_gather_object(parts, mine)
         if all(p is not None for p in parts):
             engine.p2p_import(b"".join(parts))
+            engine._has_p2p = True
     return engine

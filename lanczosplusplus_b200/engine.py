@@ -85,6 +85,17 @@ class InternalProductCuda:
         if self.nranks > 1 and getattr(self, "_has_comm", False):
             check(_lib.lib().lpp_comm_share(s.h, self.h))      # same ranks, same device: borrow the communicator
             s._has_comm = True
+            dist = getattr(self, "_dist", None)
+            if dist is not None and getattr(self, "_has_p2p", False):
+                # peer-memory exchange for the new sector as well (every rank creates the same sector at the same point of
+                # Engine::spectralFunction, so this is a collective): 128 bytes of IPC handles per rank
+                mine = s.p2p_export()
+                parts = [None] * dist.get_world_size()
+                dist.all_gather_object(parts, mine)
+                if all(q is not None for q in parts):
+                    s.p2p_import(b"".join(parts))
+                    s._has_p2p = True
+                s._dist = dist
         return s
 
     # --- InternalProductOnTheFly interface

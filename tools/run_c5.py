@@ -28,13 +28,15 @@ ap.add_argument("--site", type=int, default=8)
 ap.add_argument("--steps", type=int, default=200)         # SpectralSteps
 ap.add_argument("--gs-steps", type=int, default=300)
 ap.add_argument("--compare", action="store_true")
+ap.add_argument("--ndown", type=int, default=-1)          # default: half filling; fewer down electrons keep 18-site runs small
 args = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = args.sites
-kw = dict(model=lpp.HUBBARD, nsite=n, nup=n // 2, ndown=n // 2, hop=geo.chain(n, -1.0, False), U=np.full(n, 4.0), V=np.zeros(n))
+ndown = n // 2 if args.ndown < 0 else args.ndown
+kw = dict(model=lpp.HUBBARD, nsite=n, nup=n // 2, ndown=ndown, hop=geo.chain(n, -1.0, False), U=np.full(n, 4.0), V=np.zeros(n))
 io = {"LanczosSteps": args.gs_steps, "LanczosEps": 1e-12, "SpectralSteps": args.steps, "SpectralEps": 0.0}
 
 t0 = time.perf_counter()
@@ -49,7 +51,7 @@ cfs = en.spectralFunction(lpp.OP_C, args.site, args.site, spin=0)
 torch.cuda.synchronize()
 t3 = time.perf_counter()
 omega = np.linspace(-6.0, 6.0, 25)
-out = {"config": "HubbardOneOrbital %d-site open chain t=-1 U=4, %d up %d down" % (n, n // 2, n // 2), "rows": eng.rows(),
+out = {"config": "HubbardOneOrbital %d-site open chain t=-1 U=4, %d up %d down" % (n, n // 2, ndown), "rows": eng.rows(),
        "ranks": world, "energy": en.energy, "gs_lanczos_steps": len(en.a), "setup_s": t1 - t0, "ground_state_s": t2 - t1,
        "gs_s_per_iteration": (t2 - t1) / (2 * max(len(en.a), 1)),   # decomposition + replay for the eigenvector
        "cf_s": t3 - t2, "cf_s_per_iteration": (t3 - t2) / (args.steps * max(len(cfs), 1)), "cf": []}
