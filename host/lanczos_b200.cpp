@@ -8,7 +8,7 @@
 //   hubbardU / potentialV / MagneticField / AnisotropyD vectors   Orbitals= FeAsMode=INT_PAPER33
 //   TargetElectronsUp= TargetElectronsDown= TargetSzPlusConst= HeisenbergTwiceS=1
 //   SolverOptions= (InternalProductCuda | InternalProductStored)  LanczosSteps= LanczosEps= LanczosMinSteps= LanczosOptions=reortho Threads=(ignored)
-// Usage: lanczos_b200 -f input.inp [-p precision] [--parse-only]
+// Usage: lanczos_b200 -f input.inp [-p precision] [--parse-only] [-g c|cdagger [--omega begin,end,step,delta]] [-c c|cdagger|n]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -143,13 +143,14 @@ int main(int argc, char** argv)
 	std::string file;
 	int precision = 12;
 	bool parse_only = false;
-	std::string gf, omega_spec;
+	std::string gf, omega_spec, cicj;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "-f") && i + 1 < argc) file = argv[++i];
 		else if (!strcmp(argv[i], "-p") && i + 1 < argc) precision = std::atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--parse-only")) parse_only = true;
 		else if (!strcmp(argv[i], "-g") && i + 1 < argc) gf = argv[++i];                 // lanczos -g c | -g cdagger (LanczosOptions.h)
 		else if (!strcmp(argv[i], "--omega") && i + 1 < argc) omega_spec = argv[++i];    // begin,end,step,delta
+		else if (!strcmp(argv[i], "-c") && i + 1 < argc) cicj = argv[++i];               // lanczos -c c | -c n: two-point matrix
 	}
 	if (file.empty()) {
 		std::cerr << "USAGE: " << argv[0] << " -f input.inp [-p precision] [--parse-only]\n";
@@ -228,6 +229,23 @@ int main(int argc, char** argv)
 		std::cout.precision(precision);
 		std::cout << "#Hilbert=" << engine.rows() << " LanczosSteps=" << engine.lanczosSteps() << "\n";
 		std::cout << "Energy=" << engine.energies(0) << "\n";   // LanczosDriver1.h:64-66
+		if (!cicj.empty()) {
+			// LanczosDriver1.h:183-199 -> Engine::twoPoint (Engine.h:262-331): result(i, j) = <O_j gs | O_i gs>, spin TSPSpin
+			if (d.model == LPP_MODEL_HEISENBERG) throw std::runtime_error("-c is available for the fermionic models");
+			const int what = cicj == "c" ? LPP_OP_C : (cicj == "cdagger" ? LPP_OP_CDAGGER : (cicj == "n" ? LPP_OP_N : 0));
+			if (!what) throw std::runtime_error("-c expects c, cdagger or n");
+			if (what == LPP_OP_N && d.model != LPP_MODEL_HUBBARD) throw std::runtime_error("-c n is available for Model=HubbardOneBand");
+			const int spin = geti(in, "TSPSpin", 0);
+			const std::vector<double> m = engine.twoPoint(what, spin);
+			std::cout << "spins=" << spin << " " << spin << "\norbs=0 0\n" << d.nsite << " " << d.nsite << "\n";
+			double sum = 0;
+			for (int i = 0; i < d.nsite; i++) {
+				for (int j = 0; j < d.nsite; j++) std::cout << m[(size_t)i * d.nsite + j] << " ";
+				std::cout << "\n";
+				sum += m[(size_t)i * d.nsite + i];
+			}
+			std::cout << "MatrixDiagonal = " << sum << "\n";          // Engine.h:330
+		}
 		if (!gf.empty()) {
 			// LanczosDriver1.h:96-181: TSPSites (one site = diagonal), one continued-fraction collection per pair of sites
 			if (d.model == LPP_MODEL_HEISENBERG) throw std::runtime_error("-g c is available for the fermionic models");

@@ -59,3 +59,14 @@ def test_driver_spectral_function_matches_python_engine(lpp):
         assert cf.isign == int(h[1]) and abs(cf.weight - float(h[2])) <= 1e-9 * max(1.0, abs(cf.weight))
     assert np.abs(g - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max())
     eng.close()
+
+
+@pytest.mark.gpu
+def test_driver_two_point_matrix(lpp):
+    """`lanczos_b200 -c c`: Engine::twoPoint through the C++ mirror; the trace of <cdagger_j c_i> is the number of up electrons."""
+    r = run(lpp, ["-f", os.path.join(ROOT, "tests/inputs/hubbard6_gf.inp"), "-p", "14", "-c", "c"])
+    assert r.returncode == 0, r.stderr
+    assert abs(float(re.search(r"MatrixDiagonal = (\S+)", r.stdout).group(1)) - 3.0) < 1e-9
+    rows = r.stdout.split("6 6\n")[1].strip().splitlines()[:6]
+    m = np.array([[float(x) for x in line.split()] for line in rows])
+    assert np.abs(m - m.T).max() < 1e-10 and np.linalg.eigvalsh(m).min() > -1e-10
