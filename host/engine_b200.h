@@ -52,26 +52,43 @@ public:
 	int lanczosSteps() const { return steps_; }
 	uint64_t rows() const { uint64_t r = 0; lpp_rows(h_, &r); return r; }
 
-	// Engine.h:133-206 for the fermionic operators c / cdagger of HubbardOneBand, FeAsBasedSc (orbital pair orb0, orb1) and
-	// Tj1Orbital (hasNewParts: HubbardOneOrbital.h:212-230, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557)
+	// Engine.h:133-206: c / cdagger of HubbardOneBand, FeAsBasedSc (orbital pair orb0, orb1) and Tj1Orbital; sz / splus / sminus
+	// of HubbardOneBand and Heisenberg (hasNewParts: HubbardOneOrbital.h:212-257, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557,
+	// Heisenberg.h:218-240)
 	void spectralFunction(std::vector<ContinuedFraction>& cfCollection, int what, int isite, int jsite, int spin, int orb0 = 0,
 	                      int orb1 = 0) const
 	{
-		if (what != LPP_OP_C && what != LPP_OP_CDAGGER) throw std::runtime_error("spectralFunction: operator must be c or cdagger");
+		const bool fermionic = what == LPP_OP_C || what == LPP_OP_CDAGGER;       // LabeledOperator::isFermionic
+		int conj;                                                                // LabeledOperator::transposeConjugate
+		switch (what) {
+		case LPP_OP_C: conj = LPP_OP_CDAGGER; break;
+		case LPP_OP_CDAGGER: conj = LPP_OP_C; break;
+		case LPP_OP_SPLUS: conj = LPP_OP_SMINUS; break;
+		case LPP_OP_SMINUS: conj = LPP_OP_SPLUS; break;
+		case LPP_OP_SZ: conj = LPP_OP_SZ; break;
+		default: throw std::runtime_error("spectralFunction: operator must be c, cdagger, sz, splus or sminus");
+		}
 		const bool isDiagonal = isite == jsite && orb0 == orb1;
 		const int nmax = desc_.nsite * (desc_.model == LPP_MODEL_FEAS ? desc_.orbitals : 1);
-		const int conj = (what == LPP_OP_C) ? LPP_OP_CDAGGER : LPP_OP_C;
 		for (int type = 0; type < 4; type++) {
 			if (isDiagonal && type > 1) continue;
 			const int op = (type & 1) ? what : conj;                       // Engine.h:163
-			const int c = (op == LPP_OP_C) ? -1 : 1;
 			lpp_desc d = desc_;
-			d.nup += (spin == 0) ? c : 0;
-			d.ndown += (spin == 1) ? c : 0;
-			if (d.nup < 0 || d.ndown < 0 || d.nup > nmax || d.ndown > nmax || (d.nup == 0 && d.ndown == 0)) continue;
+			if (op == LPP_OP_C || op == LPP_OP_CDAGGER) {
+				const int c = (op == LPP_OP_C) ? -1 : 1;
+				d.nup += (spin == 0) ? c : 0;
+				d.ndown += (spin == 1) ? c : 0;
+				if (d.nup == 0 && d.ndown == 0) continue;
+			} else if (op == LPP_OP_SPLUS || op == LPP_OP_SMINUS) {
+				const int c = (op == LPP_OP_SPLUS) ? 1 : -1;
+				d.nup += c;
+				if (d.model == LPP_MODEL_HUBBARD) d.ndown -= c;
+			}
+			if (d.nup < 0 || d.ndown < 0 || d.nup > nmax || d.ndown > nmax) continue;
 			if (d.model == LPP_MODEL_TJ && d.nup + d.ndown > d.nsite) continue;           // no double occupancy
-			lpp_handle* dst = nullptr;
-			check(lpp_create(&d, &dst));
+			const bool same = op == LPP_OP_SZ;                             // needsNewBasis() is false
+			lpp_handle* dst = h_;
+			if (!same) check(lpp_create(&d, &dst));
 			try {
 				const double isign = (type > 1) ? -1.0 : 1.0;
 				check(lpp_apply_op(h_, dst, op, isite, spin, orb0, 1.0, 0));   // Engine.h:509-517
@@ -86,6 +103,7 @@ public:
 				cf.b.resize((size_t)n);
 				const int s = (type & 1) ? -1 : 1;
 				double s2 = (type > 1) ? -1.0 : 1.0;
+				if (!fermionic) s2 *= s;                                      // Engine.h:482
 				if (!isDiagonal) s2 *= 0.5;                                   // Engine.h:481-485
 				cf.type = type;
 				cf.Eg = energy_;
@@ -93,10 +111,10 @@ public:
 				cf.isign = -s;                                                // cf.set(ab, Eg, weight*s2, -s), Engine.h:489
 				cfCollection.push_back(cf);
 			} catch (...) {
-				lpp_destroy(dst);
+				if (!same) lpp_destroy(dst);
 				throw;
 			}
-			lpp_destroy(dst);
+			if (!same) lpp_destroy(dst);
 		}
 	}
 

@@ -248,9 +248,9 @@ int main(int argc, char** argv)
 		}
 		if (!gf.empty()) {
 			// LanczosDriver1.h:96-181: TSPSites (one site = diagonal), one continued-fraction collection per pair of sites
-			if (d.model == LPP_MODEL_HEISENBERG) throw std::runtime_error("-g c is available for the fermionic models");
-			const int what = gf == "c" ? LPP_OP_C : (gf == "cdagger" ? LPP_OP_CDAGGER : 0);
-			if (!what) throw std::runtime_error("-g expects c or cdagger");
+			const int what = gf == "c" ? LPP_OP_C : gf == "cdagger" ? LPP_OP_CDAGGER : gf == "sz" ? LPP_OP_SZ : gf == "splus" ? LPP_OP_SPLUS
+			               : gf == "sminus" ? LPP_OP_SMINUS : 0;
+			if (!what) throw std::runtime_error("-g expects c, cdagger, sz, splus or sminus");
 			if (!in.vectors.count("TSPSites") || in.vectors["TSPSites"][0].empty()) throw std::runtime_error("TSPSites must have at least one site");
 			std::vector<double> sites = in.vectors["TSPSites"][0];
 			if (sites.size() == 1) sites.push_back(sites[0]);

@@ -53,7 +53,7 @@ typedef enum {
 } lpp_kernel;
 
 /* Operator ids of LabeledOperator::Label (LabeledOperator.h:10-17). */
-typedef enum { LPP_OP_C = 1, LPP_OP_CDAGGER = 3, LPP_OP_N = 4 } lpp_op;
+typedef enum { LPP_OP_C = 1, LPP_OP_SZ = 2, LPP_OP_CDAGGER = 3, LPP_OP_N = 4, LPP_OP_SPLUS = 5, LPP_OP_SMINUS = 6 } lpp_op;
 
 /* One (model, symmetry sector).  Replaces the model constructor + createBasis():
  * HubbardOneOrbital.h:41-49,117-122 ; FeBasedSc.h:132-140,249-254 ; Heisenberg.h:38-60.
@@ -148,8 +148,10 @@ int lpp_ground_state(lpp_handle* h, const lpp_solver_params* p, const double* in
 int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const double* init_host, int32_t nstates, double* energies,
                      double* z_host, int32_t* nsteps);
 
-/* Engine::accModifiedState_ (Engine.h:416-458) for c / cdagger / n on Hubbard-type bases
- * (BasisHubbardLanczos.h:106-137,162-182; 64-bit indices): dst.modified (+)= factor * O_{site,spin} |src.groundstate>.
+/* Engine::accModifiedState_ (Engine.h:416-458): dst.modified (+)= factor * O_{site,spin,orb} |src.groundstate>, 64-bit indices.
+ * HubbardOneBand: c, cdagger, n, sz, splus, sminus (BasisHubbardLanczos.h:106-257); FeAsBasedSc (per orbital) and Tj1Orbital: c,
+ * cdagger; Heisenberg S=1/2: sz, n, splus, sminus (BasisHeisenberg.h:123-139,230-280).  dst is a handle on the sector hasNewParts
+ * gives (src itself for sz / n).
  * accumulate == 0 zeroes dst.modified first. */
 int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb, double factor,
                  int32_t accumulate);

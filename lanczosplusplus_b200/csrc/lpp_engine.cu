@@ -1319,20 +1319,26 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 {
 	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
 	const int model = src->md.model;
-	if (model != dst->md.model || model == LPP_MODEL_HEISENBERG)
-		return fail(LPP_ERR_ARG, "lpp_apply_op: HubbardOneBand (c, cdagger, n), FeAsBasedSc and Tj1Orbital (c, cdagger) bases");
+	if (model != dst->md.model) return fail(LPP_ERR_ARG, "source and destination models differ");
 	if (orb < 0 || orb >= src->md.orbitals) return fail(LPP_ERR_ARG, "bad orbital");
-	if (op != LPP_OP_C && op != LPP_OP_CDAGGER && !(op == LPP_OP_N && model == LPP_MODEL_HUBBARD)) return fail(LPP_ERR_ARG, "unsupported operator");
 	if (site < 0 || site >= src->md.nsite || spin < 0 || spin > 1) return fail(LPP_ERR_ARG, "bad site/spin");
+	const bool fermion = op == LPP_OP_C || op == LPP_OP_CDAGGER;
+	const bool spinop = op == LPP_OP_SZ || op == LPP_OP_SPLUS || op == LPP_OP_SMINUS;
+	if (model == LPP_MODEL_HUBBARD) { if (!fermion && !spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "unsupported operator"); }
+	else if (model == LPP_MODEL_HEISENBERG) { if (!spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "Heisenberg: sz, splus, sminus, n"); }
+	else if (!fermion) return fail(LPP_ERR_ARG, "FeAsBasedSc / Tj1Orbital: c and cdagger");
 	if (!src->gs) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
 	if (src->desc.nranks != dst->desc.nranks || src->desc.rank != dst->desc.rank || src->device != dst->device)
 		return fail(LPP_ERR_ARG, "source and destination must share device and sharding");
-	if (src->desc.nranks > 1 && spin != 0)
-		return fail(LPP_ERR_ARG, "row-sharded operator application is local for spin-up operators only");
-	int dup = (op == LPP_OP_C) ? -1 : (op == LPP_OP_CDAGGER ? 1 : 0);
-	int eu = src->md.nup + (spin == 0 ? dup : 0), ed = src->md.ndn + (spin == 1 ? dup : 0);
-	if (dst->md.nup != eu || dst->md.ndn != ed || dst->md.nsite != src->md.nsite)
-		return fail(LPP_ERR_ARG, "destination sector does not match operator (hasNewParts, HubbardOneOrbital.h:212-230)");
+	if (src->desc.nranks > 1 && (spin != 0 || op == LPP_OP_SPLUS || op == LPP_OP_SMINUS || model == LPP_MODEL_HEISENBERG))
+		return fail(LPP_ERR_ARG, "row-sharded operator application is local for spin-up c/cdagger and for sz/n only");
+	// hasNewParts: HubbardOneOrbital.h:212-257, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557, Heisenberg.h:218-240
+	int eu = src->md.nup, ed = src->md.ndn;
+	if (fermion) { const int dup = (op == LPP_OP_C) ? -1 : 1; if (spin == 0) eu += dup; else ed += dup; }
+	else if (op == LPP_OP_SPLUS) { eu += 1; if (model == LPP_MODEL_HUBBARD) ed -= 1; }
+	else if (op == LPP_OP_SMINUS) { eu -= 1; if (model == LPP_MODEL_HUBBARD) ed += 1; }
+	if (dst->md.nup != eu || (model != LPP_MODEL_HEISENBERG && dst->md.ndn != ed) || dst->md.nsite != src->md.nsite)
+		return fail(LPP_ERR_ARG, "destination sector does not match operator (hasNewParts)");
 	if (model == LPP_MODEL_FEAS && dst->md.orbitals != src->md.orbitals) return fail(LPP_ERR_ARG, "orbital count differs");
 	CK(cudaSetDevice(dst->device));
 	if (!dst->modified) {

@@ -16,7 +16,7 @@ from ._lib import Desc, LppError, SolverParams, Timing, check
 
 HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TABLE, KERNEL_TILED, KERNEL_STORED = 0, 1, 2, 3, 4
-OP_C, OP_CDAGGER, OP_N = 1, 3, 4
+OP_C, OP_SZ, OP_CDAGGER, OP_N, OP_SPLUS, OP_SMINUS = 1, 2, 3, 4, 5, 6
 MODEL_NAMES = {"HubbardOneBand": HUBBARD, "FeAsBasedSc": FEAS, "Heisenberg": HEISENBERG, "Tj1Orbital": TJ, "TjMultiOrb": TJ}
 
 
@@ -334,24 +334,37 @@ class Engine:
         return out
 
     def spectralFunction(self, op, isite, jsite, spin=0, orbs=(0, 0)):
-        """Engine.h:133-206 for the fermionic c/cdagger of HubbardOneBand, FeAsBasedSc (orbital pair) and Tj1Orbital:
-        list of (type, ContinuedFraction)."""
+        """Engine.h:133-206: list of (type, ContinuedFraction).  Fermionic c/cdagger for HubbardOneBand, FeAsBasedSc (orbital
+        pair) and Tj1Orbital; sz / splus / sminus for HubbardOneBand and Heisenberg (S(q, omega) building blocks)."""
         if spin != 0 and self.mat.nranks > 1:
             raise LppError("row-sharded spectral functions support spin 0")
         out = []
         is_diag = isite == jsite and orbs[0] == orbs[1]
-        op2 = {OP_C: OP_CDAGGER, OP_CDAGGER: OP_C}[op]
+        fermionic = op in (OP_C, OP_CDAGGER)                                 # LabeledOperator::isFermionic
+        op2 = {OP_C: OP_CDAGGER, OP_CDAGGER: OP_C, OP_SPLUS: OP_SMINUS, OP_SMINUS: OP_SPLUS, OP_SZ: OP_SZ}[op]   # transposeConjugate
         nmax = self.mat.nsite * self.mat.orbitals
         for typ in range(4):
             if is_diag and typ > 1:
                 continue
             lop = op if (typ & 1) else op2  # Engine.h:163
-            dn = -1 if lop == OP_C else 1
-            nup, ndown = self.mat.nup + (dn if spin == 0 else 0), self.mat.ndown + (dn if spin == 1 else 0)
-            if nup < 0 or ndown < 0 or nup > nmax or ndown > nmax or (nup == 0 and ndown == 0):
+            nup, ndown = self.mat.nup, self.mat.ndown
+            if lop in (OP_C, OP_CDAGGER):
+                dn = -1 if lop == OP_C else 1
+                nup, ndown = nup + (dn if spin == 0 else 0), ndown + (dn if spin == 1 else 0)
+            elif lop in (OP_SPLUS, OP_SMINUS):      # HubbardOneOrbital.h:232-257 ; Heisenberg.h:218-240 (parts = (2S, Sz + const))
+                c = 1 if lop == OP_SPLUS else -1
+                nup += c
+                if self.mat.model == HUBBARD:
+                    ndown -= c
+            if nup < 0 or ndown < 0 or nup > nmax or ndown > nmax:
+                continue
+            if lop in (OP_C, OP_CDAGGER) and nup == 0 and ndown == 0:
                 continue  # hasNewPartsCorCdagger: HubbardOneOrbital.h:212-230, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557
             if self.mat.model == TJ and nup + ndown > self.mat.nsite:
                 continue  # no double occupancy, TjMultiOrb.h:553
+            if lop == OP_SZ:                        # needsNewBasis() is false: the sector is its own destination
+                self._spectral_same_sector(out, typ, lop, isite, jsite, spin, orbs, is_diag)
+                continue
             dst = self.mat.sector(nup, ndown)
             self.mat.apply_op(dst, lop, isite, spin, 1.0, accumulate=False, orb=orbs[0])   # Engine.h:509-517
             isign = -1.0 if typ > 1 else 1.0
@@ -360,7 +373,19 @@ class Engine:
             a, b, weight = solver.decomposition(use_modified=True)                     # Engine.h:474-479
             s = -1 if (typ & 1) else 1
             s2 = -1.0 if typ > 1 else 1.0
+            if not fermionic:
+                s2 *= s                                                                # Engine.h:482
             s2 *= 1.0 if is_diag else 0.5                                              # Engine.h:481-485
             out.append((typ, ContinuedFraction(a, b, self.energy, weight * s2, -s)))   # Engine.h:489
             dst.close()
         return out
+
+    def _spectral_same_sector(self, out, typ, lop, isite, jsite, spin, orbs, is_diag):
+        self.mat.apply_op(self.mat, lop, isite, spin, 1.0, accumulate=False, orb=orbs[0])
+        isign = -1.0 if typ > 1 else 1.0
+        self.mat.apply_op(self.mat, lop, jsite, spin, isign, accumulate=True, orb=orbs[1])
+        solver = LanczosSolver(self.mat, ParametersForSolver(self.io, "Spectral"))
+        a, b, weight = solver.decomposition(use_modified=True)
+        s = -1 if (typ & 1) else 1
+        s2 = (-1.0 if typ > 1 else 1.0) * s * (1.0 if is_diag else 0.5)               # not fermionic: s2 *= s
+        out.append((typ, ContinuedFraction(a, b, self.energy, weight * s2, -s)))

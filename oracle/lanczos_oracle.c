@@ -37,7 +37,7 @@
 typedef uint64_t word_t;
 
 enum { ORC_HUBBARD = 0, ORC_FEAS = 1, ORC_HEISENBERG = 2, ORC_TJ = 3 };
-enum { ORC_OP_C = 1, ORC_OP_CDAGGER = 3, ORC_OP_N = 4 }; /* LabeledOperator.h:10-17 */
+enum { ORC_OP_C = 1, ORC_OP_SZ = 2, ORC_OP_CDAGGER = 3, ORC_OP_N = 4, ORC_OP_SPLUS = 5, ORC_OP_SMINUS = 6 }; /* LabeledOperator.h:10-17 */
 
 typedef struct {
 	int model;
@@ -1484,9 +1484,66 @@ static int tj_dosign_gf(word_t a, word_t b, int ind, int sector)
  * (BasisHubbardLanczos.h:162-182 with BasisOneSpin.h:121-151; BasisFeAsBasedSc.h:276-289 with BasisOneSpinFeAs.h:127-143;
  * BasisTjMultiOrbLanczos.h:302-318,398-433), doSignGf of the source basis, 64-bit indices instead of int.
  * z (dst basis) += factor*sign*src. */
+/* accModifiedState_ for the spin operators: getBraIndex of BasisHubbardLanczos.h:162-257 (sz -> getBraIndexSz, splus/sminus ->
+ * getBraIndexSplusSminus, sign doSignSpSm :151-160) and of BasisHeisenberg.h:123-139,230-280 (sz value 1 - 2 n_up, n value
+ * n_up or 1 - n_up, splus/sminus flip the site; doSignSpSm is the BasisBase default 1) */
+static void apply_spin_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, double factor,
+                          const double* srcv, double* z)
+{
+	size_t n = orc_rows(src);
+	word_t ms = ((word_t)1) << site;
+	for (size_t r = 0; r < n; r++) {
+		word_t k1, k2;
+		row_kets(src, r, &k1, &k2);
+		long idx = -1;
+		double value = 1, mysign = 1;
+		if (src->model == ORC_HEISENBERG) {
+			int nup = (k1 & ms) ? 1 : 0;
+			if (op == ORC_OP_SZ) { idx = (long)r; value = 1 - 2 * nup; }
+			else if (op == ORC_OP_N) { idx = (long)r; value = (spin == 0) ? nup : 1 - nup; }
+			else {
+				if (nup) { if (op == ORC_OP_SPLUS) continue; }
+				else { if (op == ORC_OP_SMINUS) continue; }
+				idx = (long)perfect_index(dst, k1 ^ ms, 0);
+			}
+		} else { /* Hubbard */
+			int b1 = (k1 & ms) ? 1 : 0, b2 = (k2 & ms) ? 1 : 0;
+			if (op == ORC_OP_SZ) {
+				if (!b1 && !b2) continue;
+				if (b1 && b2) continue;
+				value = b1 ? 1 : -1;
+				idx = (long)perfect_index(dst, k1, k2);
+			} else {
+				int up_first = (op == ORC_OP_SPLUS);           /* spin = SPIN_UP for S+, SPIN_DOWN for S- */
+				word_t brar1, brar2;
+				if (up_first) {
+					if (b1) continue;                          /* cdagger up: needs the up orbital empty */
+					brar1 = k1 ^ ms;
+					if (!b2) continue;                         /* c down: needs the down orbital occupied */
+					brar2 = k2 ^ ms;
+					idx = (long)perfect_index(dst, brar1, brar2);
+				} else {
+					if (b2) continue;                          /* cdagger down */
+					brar1 = k2 ^ ms;
+					if (!b1) continue;                         /* c up */
+					brar2 = k1 ^ ms;
+					idx = (long)perfect_index(dst, brar2, brar1);
+				}
+				mysign = do_sign(k1, site) * do_sign(k2, site);   /* doSignSpSm */
+			}
+		}
+		if (idx < 0) continue;
+		z[idx] += factor * mysign * value * srcv[r];
+	}
+}
+
 void orc_apply_op_orb(const orc_model* src, const orc_model* dst, int op, int site, int spin, int orb, double factor,
                       const double* srcv, double* z)
 {
+	if (op == ORC_OP_SZ || op == ORC_OP_SPLUS || op == ORC_OP_SMINUS || src->model == ORC_HEISENBERG) {
+		apply_spin_op(src, dst, op, site, spin, factor, srcv, z);
+		return;
+	}
 	size_t n = orc_rows(src);
 	int pos = site * src->orbitals + orb;
 	word_t ms = ((word_t)1) << pos;

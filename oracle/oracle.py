@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liblpp_oracle.so")
 
 HUBBARD, FEAS, HEISENBERG, TJ = 0, 1, 2, 3
-OP_C, OP_CDAGGER, OP_N = 1, 3, 4
+OP_C, OP_SZ, OP_CDAGGER, OP_N, OP_SPLUS, OP_SMINUS = 1, 2, 3, 4, 5, 6
 
 
 def build(force=False):

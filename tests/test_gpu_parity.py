@@ -333,10 +333,10 @@ def test_engine_matches_reference_fixture(lpp, name):
 _ALL = dict(cases.SMALL_CASES, **cases.TJ_CASES)
 
 
-@pytest.mark.parametrize("name", [n for n in sorted(_ALL) if _ALL[n]["model"] != cases.HEISENBERG])
+@pytest.mark.parametrize("name", sorted(_ALL))
 def test_apply_op_matches_reference_fixture(lpp, name):
-    """accModifiedState_ on the device against the reference's getBraIndex / doSignGf results (both spins, c and cdagger;
-    HubbardOneBand, FeAsBasedSc per orbital, Tj1Orbital)."""
+    """accModifiedState_ on the device against the reference's getBraIndex / doSignGf / doSignSpSm results: c, cdagger on both
+    spins (HubbardOneBand, FeAsBasedSc per orbital, Tj1Orbital), sz / splus / sminus (HubbardOneBand, Heisenberg), n (Heisenberg)."""
     from tests import golden_util as gu
     case = _ALL[name]
     g = gu.load(name, case)
@@ -344,10 +344,12 @@ def test_apply_op_matches_reference_fixture(lpp, name):
     e.set_groundstate(geo.splitmix64_vector(e.rows(), gu.SRC_SEED))
     seen = 0
     for rec in gu.ops(g):
-        dst = e.sector(rec["nup"], rec["ndown"])
+        same = rec["op"] in (2, 4)                                        # sz / n stay in the sector: the handle is its own destination
+        dst = e if same else e.sector(rec["nup"], rec["ndown"])
         e.apply_op(dst, rec["op"], rec["site"], rec["spin"], 1.0, accumulate=False, orb=rec["orb"])
         assert np.array_equal(dst.get_vector(1), g[rec["key"]]), rec      # +-source elements: exact
-        dst.close()
+        if not same:
+            dst.close()
         seen += 1
     assert seen >= (4 if name in ("tj6_full", "tj5_no_dn", "hub_empty_dn") else 8)
     e.close()
@@ -553,4 +555,45 @@ def test_states_below_excited_states(lpp, oracle, name):
         for q in range(k):
             assert abs(z1[k] @ z1[q]) <= 1e-7
     assert np.abs(eng.get_vector(0) - z1[0]).max() == 0.0                  # state 0 stays in the handle
+    eng.close()
+
+
+@pytest.mark.parametrize("name,op", [("c1_hub8", "sz"), ("c1_hub8", "splus"), ("heis12", "sz"), ("heis12", "sminus")])
+def test_spin_operator_continued_fractions(lpp, oracle, name, op):
+    """spectralFunction with the spin operators (the S(q, omega) building blocks): type loop with transposeConjugate, the
+    non-fermionic sign s2 *= s (Engine.h:482), sz without a new basis; against the oracle pipeline."""
+    case = cases.SMALL_CASES[name]
+    OP = {"sz": lpp.OP_SZ, "splus": lpp.OP_SPLUS, "sminus": lpp.OP_SMINUS}[op]
+    conj = {lpp.OP_SZ: lpp.OP_SZ, lpp.OP_SPLUS: lpp.OP_SMINUS, lpp.OP_SMINUS: lpp.OP_SPLUS}
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 13)
+    e0, z0, _, _ = o.ground_state(init, 300, 1e-13, 4)
+    eng = cases.make_engine(lpp, case)
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13, "SpectralSteps": 25, "SpectralEps": 0.0}, init=init)
+    eng.set_groundstate(z0)
+    en.energy = e0
+    omega = np.linspace(-5, 5, 41)
+    isite, jsite = 1, 4
+    cfs = en.spectralFunction(OP, isite, jsite, spin=0)
+    assert len(cfs) == 4
+    for typ, cf in cfs:
+        lop = OP if (typ & 1) else conj[OP]
+        nup, ndown = case["nup"], case["ndown"]
+        if lop in (lpp.OP_SPLUS, lpp.OP_SMINUS):
+            c = 1 if lop == lpp.OP_SPLUS else -1
+            nup += c
+            if case["model"] == cases.HUBBARD:
+                ndown -= c
+        od = o if lop == lpp.OP_SZ else cases.make_oracle(oracle, dict(case, nup=nup, ndown=ndown))
+        phi = np.zeros(od.rows())
+        o.apply_op(od, lop, isite, 0, 1.0, z0, phi)
+        o.apply_op(od, lop, jsite, 0, -1.0 if typ > 1 else 1.0, z0, phi)
+        a, b = od.decomposition(phi, steps=25, eps=0.0)
+        s = -1 if (typ & 1) else 1
+        weight = (phi @ phi) * (-1.0 if typ > 1 else 1.0) * s * 0.5
+        assert abs(cf.weight - weight) <= 1e-12 * max(1.0, abs(weight)), (name, op, typ)
+        n = min(len(a), 8)
+        assert relerr(cf.a[:n], a[:n]) <= 1e-10 and relerr(cf.b[:n], b[:n]) <= 1e-10
+        gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
+        assert np.abs(cf(omega, 0.1) - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max()), (name, op, typ)
     eng.close()

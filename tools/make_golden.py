@@ -48,18 +48,40 @@ def make_reference(case):
 
 
 def op_list(case):
-    """(op, site, spin, orb) tuples exercised per model (fermionic c / cdagger; both spins: quirk C.3 lives in spin 1)."""
-    if case["model"] == cases.HEISENBERG:
-        return []
+    """(op, site, spin, orb) tuples exercised per model: fermionic c / cdagger on both spins (quirk C.3 lives in spin 1) and,
+    for HubbardOneBand and Heisenberg, the spin operators sz / splus / sminus (/ n)."""
     n = case["nsite"]
     sites = sorted({0, n // 2, n - 1})
     out = []
-    for op in (ref.OP_C, ref.OP_CDAGGER):
+    if case["model"] != cases.HEISENBERG:
+        for op in (ref.OP_C, ref.OP_CDAGGER):
+            for spin in (0, 1):
+                for site in sites:
+                    for orb in range(case["orbitals"]):
+                        out.append((op, site, spin, orb))
+    if case["model"] in (cases.HUBBARD, cases.HEISENBERG):
+        for op in (ref.OP_SZ, ref.OP_SPLUS, ref.OP_SMINUS):
+            for site in sites[:2]:
+                out.append((op, site, 0, 0))
+    if case["model"] == cases.HEISENBERG:
         for spin in (0, 1):
-            for site in sites:
-                for orb in range(case["orbitals"]):
-                    out.append((op, site, spin, orb))
+            out.append((ref.OP_N, sites[-1], spin, 0))
     return out
+
+
+def new_sector_of(r, case, op, spin, orb):
+    """(reference handle of the destination sector, nup, ndown) or None when hasNewParts says there is none."""
+    if op in (ref.OP_SZ, ref.OP_N):
+        return r, case["nup"], case["ndown"]
+    if case["model"] == cases.HEISENBERG:          # parts() = (twiceS, szPlusConst): Heisenberg.h:218-240
+        sz = case["nup"] + (1 if op == ref.OP_SPLUS else -1)
+        if sz < 0 or sz > case["nsite"]:
+            return None
+        return r.new_sector(1, sz), sz, 0
+    has, (nu, nd) = r.has_new_parts(op, spin, orb)
+    if not has or max(nu, nd) > case["nsite"] * case["orbitals"]:
+        return None
+    return r.new_sector(nu, nd), nu, nd
 
 
 def generate(name, case):
@@ -90,12 +112,10 @@ def generate(name, case):
     src = geo.splitmix64_vector(n, SRC_SEED)
     ops = []
     for (op, site, spin, orb) in op_list(case):
-        has, (nu, nd) = r.has_new_parts(op, spin, orb)
-        if not has:
+        sec = new_sector_of(r, case, op, spin, orb)
+        if sec is None:
             continue
-        if max(nu, nd) > case["nsite"] * case["orbitals"]:
-            continue
-        dst = r.new_sector(nu, nd)
+        dst, nu, nd = sec
         if dst.rows() == 0:
             continue
         z = np.zeros(dst.rows())
