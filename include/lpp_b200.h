@@ -159,6 +159,11 @@ int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int
  * for the operators of lpp_apply_op (c: the one-body density matrix <cdagger_j c_i>; n: <n_j n_i>); dst is a handle on the
  * sector the operator leads to (src itself for n).  Modified states and the Gram matrix stay on the device. */
 int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t spin, int32_t orb_i, int32_t orb_j, double* result);
+/* Engine::measure (Engine.h:208-249) for <gs| op_0[site_0]; ...; op_{n-1}[site_{n-1}] |gs> with ModelBase::rahulMethod semantics
+ * (ModelBase.h:89-141, RahulOperator.h:26-50): labels 0 identity, 1 n, 2 sz, 3 c (cdagger when transposes[i] != 0); dofs 0 up,
+ * 1 down; sites are bit positions in the one-spin word (site*orbitals + orb).  The operators must conserve the sector. */
+int lpp_measure(lpp_handle* h, int32_t nops, const int32_t* labels, const int32_t* dofs, const int32_t* transposes,
+                const int32_t* sites, double* result);
 /* copy the handle's ground-state / modified vector to the host (parity tests) */
 int lpp_get_vector(lpp_handle* h, int32_t which /*0 = ground state, 1 = modified*/, double* out_host);
 int lpp_set_groundstate(lpp_handle* h, const double* z_host);

@@ -682,6 +682,47 @@ LPP_HD bool lpp_apply_op_source(const ModelDev& src, const ModelDev& dst, int op
 	return true;
 }
 
+// ---------------------------------------------------------------- Engine::measure (Engine.h:208-249) -> ModelBase::rahulMethod
+// A product of one-site operators applied to a basis state, right to left (ModelBase.h:89-141 with RahulOperator.h:26-50):
+// label 0 identity, 1 n, 2 sz (value -1/2 when the orbital is occupied, +1/2 otherwise), 3 c (cdagger when transpose != 0);
+// dof 0 acts on the up word, 1 on the down word; fermionic operators carry the parity of the orbitals below `site` in their own
+// (updated) word and, for dof 1, the parity of all up electrons.  `site` is the bit position in the word.
+#define LPP_MAX_MEASURE_OPS 8
+struct LppMeasureOps {
+	int n;
+	int label[LPP_MAX_MEASURE_OPS], dof[LPP_MAX_MEASURE_OPS], transpose[LPP_MAX_MEASURE_OPS], site[LPP_MAX_MEASURE_OPS];
+};
+// returns false when the product annihilates the state; otherwise the target words and the accumulated factor
+LPP_HD bool lpp_rahul_apply(const LppMeasureOps& ops, word_t k1, word_t k2, word_t* o1, word_t* o2, double* value)
+{
+	double v = 1.0;
+	bool nonzero = false;
+	for (int jj = 0; jj < ops.n; jj++) {
+		const int j = ops.n - jj - 1;
+		const word_t mask = lpp_bit(ops.site[j]);
+		word_t& ketp = (ops.dof[j] == 0) ? k1 : k2;
+		const bool bit = (ketp & mask) != 0;
+		double result = 1.0;
+		bool newbit = bit;
+		switch (ops.label[j]) {
+		case 0: nonzero = true; break;
+		case 1: nonzero = bit; break;
+		case 2: result = bit ? -0.5 : 0.5; nonzero = true; break;
+		default: newbit = !bit; nonzero = (bit && !ops.transpose[j]) || (!bit && ops.transpose[j]); break;
+		}
+		if (!nonzero) return false;
+		if (newbit != bit) ketp ^= mask;
+		if (ops.label[j] == 3) {
+			if (ops.dof[j] != 0 && (lpp_popc(k1) & 1)) result = -result;
+			result *= (double)lpp_sign_below(ketp, ops.site[j]);
+		}
+		v *= result;
+	}
+	if (!nonzero) return false;
+	*o1 = k1; *o2 = k2; *value = v;
+	return true;
+}
+
 // counter-based initial vector, identical to lanczosplusplus_b200/geometry.py::splitmix64_vector
 LPP_HD double lpp_splitmix_uniform(uint64_t seed, uint64_t idx)
 {

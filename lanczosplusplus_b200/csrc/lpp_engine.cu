@@ -1411,6 +1411,35 @@ extern "C" int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32
 	return rc;
 }
 
+// Engine::measure (Engine.h:208-249) with bra = ket = ground state: <gs| op_0[site_0] ... op_{n-1}[site_{n-1}] |gs> through
+// ModelBase::rahulMethod semantics (the rightmost operator acts first)
+extern "C" int lpp_measure(lpp_handle* h, int32_t nops, const int32_t* labels, const int32_t* dofs, const int32_t* transposes,
+                           const int32_t* sites, double* result)
+{
+	if (!h || !labels || !dofs || !transposes || !sites || !result) return fail(LPP_ERR_ARG, "null argument");
+	if (nops < 1 || nops > LPP_MAX_MEASURE_OPS) return fail(LPP_ERR_ARG, "between 1 and 8 operators");
+	if (h->md.model == LPP_MODEL_HEISENBERG) return fail(LPP_ERR_ARG, "lpp_measure: fermionic models (up / down words)");
+	if (!h->gs) return fail(LPP_ERR_STATE, "handle holds no ground-state vector");
+	LppMeasureOps ops;
+	memset(&ops, 0, sizeof(ops));
+	ops.n = nops;
+	bool diagonal = true;
+	for (int i = 0; i < nops; i++) {
+		if (labels[i] < 0 || labels[i] > 3 || dofs[i] < 0 || dofs[i] > 1 || sites[i] < 0 || sites[i] >= h->md.nbits)
+			return fail(LPP_ERR_ARG, "bad operator label / dof / site");
+		ops.label[i] = labels[i]; ops.dof[i] = dofs[i]; ops.transpose[i] = transposes[i] ? 1 : 0; ops.site[i] = sites[i];
+		diagonal = diagonal && labels[i] != 3;
+	}
+	if (h->desc.nranks > 1 && !diagonal) return fail(LPP_ERR_ARG, "row-sharded measure supports identity / n / sz products");
+	CK(cudaSetDevice(h->device));
+	const int npb = lpp_vec_blocks(h->nloc * 2);
+	CKR(ensure_partials(h, npb));
+	lpp_launch_measure(h->md, ops, h->gs, h->gs, h->row0, h->nloc, h->partials, h->stream);
+	h->launches += 1;
+	CKR(reduce_scalar(h, npb, result));
+	return 0;
+}
+
 extern "C" int lpp_get_vector(lpp_handle* h, int32_t which, double* out_host)
 {
 	if (!h || !out_host) return fail(LPP_ERR_ARG, "null argument");

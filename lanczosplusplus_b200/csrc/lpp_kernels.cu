@@ -598,6 +598,29 @@ __global__ void __launch_bounds__(LPP_TPB) k_gram_tile(const double* __restrict_
 			if (threadIdx.x == 0) partials[(uint64_t)(a * 4 + b) * gridDim.x + blockIdx.x] = t;
 		}
 }
+// <bra| prod ops |ket> without materialising the intermediate vector: every source row contributes bra[target] * factor * ket[row]
+__global__ void __launch_bounds__(LPP_TPB) k_measure(ModelDev m, LppMeasureOps ops, const double* __restrict__ bra, const double* __restrict__ ket,
+                                                    uint64_t row0, uint64_t nloc, double* __restrict__ partials)
+{
+	double s = 0.0;
+	for (uint64_t t = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; t < nloc; t += (uint64_t)gridDim.x * LPP_TPB) {
+		const LppRowKets k = lpp_row_kets(m, row0 + t);
+		word_t o1, o2;
+		double v;
+		if (!lpp_rahul_apply(ops, k.k1, k.k2, &o1, &o2, &v)) continue;
+		if (m.model == LPP_MODEL_TJ && (o1 & o2)) continue;            // left the no-double-occupancy space
+		const uint64_t target = (o1 == k.k1 && o2 == k.k2) ? row0 + t : lpp_rank_pair(m, o1, o2);
+		s += bra[target - row0] * v * ket[t];
+	}
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+void lpp_launch_measure(const ModelDev& m, const LppMeasureOps& ops, const double* bra, const double* ket, uint64_t row0, uint64_t nloc,
+                        double* partials, cudaStream_t s)
+{
+	k_measure<<<lpp_vec_blocks(nloc * 2), LPP_TPB, 0, s>>>(m, ops, bra, ket, row0, nloc, partials);
+}
+
 void lpp_launch_gram_tile(const double* veci, const double* vecj, uint64_t stride, uint64_t n, int nvec, int ti, int tj, double* partials,
                           cudaStream_t s)
 {

@@ -37,6 +37,8 @@ struct RoVecs {              // a block of saved Lanczos vectors and the project
 };
 void lpp_launch_reortho_dots(const double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
 void lpp_launch_reortho_axpy_norm(double* x, const RoVecs& r, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_measure(const ModelDev& m, const LppMeasureOps& ops, const double* bra, const double* ket, uint64_t row0, uint64_t nloc,
+                        double* partials, cudaStream_t s);
 void lpp_launch_gram_tile(const double* veci, const double* vecj, uint64_t stride, uint64_t n, int nvec, int ti, int tj, double* partials,
                           cudaStream_t s);
 void lpp_launch_finalize_sums(const double* partials, int n, int nv, double* out, cudaStream_t s);

@@ -319,6 +319,21 @@ class Engine:
     def energies(self, ind=0):
         return self.energy
 
+    RAHUL_LABELS = {"identity": 0, "n": 1, "sz": 2, "c": 3}
+
+    def measure(self, ops):
+        """Engine.h:208-249 for <gs|op_0[site_0];...|gs>: ops = [(label, dof, site[, transpose]), ...] with the labels of
+        RahulOperator.h:56-63 ("c", "identity", "sz", "n"); the rightmost operator acts first (ModelBase::rahulMethod)."""
+        n = len(ops)
+        lab = np.array([self.RAHUL_LABELS[o[0]] for o in ops], dtype=np.int32)
+        dof = np.array([o[1] for o in ops], dtype=np.int32)
+        site = np.array([o[2] for o in ops], dtype=np.int32)
+        tr = np.array([1 if (len(o) > 3 and o[3]) else 0 for o in ops], dtype=np.int32)
+        out = C.c_double()
+        check(_lib.lib().lpp_measure(self.mat.h, n, lab.ctypes.data, dof.ctypes.data, tr.ctypes.data, site.ctypes.data,
+                                     C.byref(out)))
+        return out.value
+
     def twoPoint(self, op, spin=0, orbs=(0, 0)):
         """Engine.h:262-331 with bra = ket = ground state: matrix result(i, j) = <O_j gs | O_i gs> (c: <cdagger_j c_i>)."""
         if op == OP_N:

@@ -308,6 +308,30 @@ int ref_apply_op(void* hsrc, void* hdst, int op, int site, int spin, int orb, do
 	REF_CATCH(-1)
 }
 
+// psiNew = prod ops |psi> through the reference's own ModelBase::rahulMethod (ModelBase.h:89-141); labels 0 identity, 1 n, 2 sz,
+// 3 c (RahulOperator.h:56-63), the operator list in the order Engine::measure builds it (Engine.h:217-234)
+int ref_rahul(void* h, int nops, const int* labels, const int* dofs, const int* transposes, const int* sites, const double* psi,
+              double* psiNew)
+{
+	REF_TRY
+	RefModel* r = static_cast<RefModel*>(h);
+	ModelBaseType* m = r->parent ? r->parent->model.get() : r->model.get();
+	static const char* names[4] = {"identity", "n", "sz", "c"};
+	ModelBaseType::VectorRahulOperatorType vops;
+	ModelBaseType::VectorSizeType vsites(nops);
+	for (int i = 0; i < nops; i++) {
+		if (labels[i] < 0 || labels[i] > 3) throw std::runtime_error("ref_rahul: bad label");
+		vops.push_back(ModelBaseType::RahulOperatorType(names[labels[i]], dofs[i], transposes[i] != 0));
+		vsites[i] = sites[i];
+	}
+	const SizeType n = r->basis->size();
+	std::vector<double> in(psi, psi + n), out(n, 0.0);
+	m->rahulMethod(out, vops, vsites, in, *r->basis);
+	std::memcpy(psiNew, out.data(), sizeof(double) * n);
+	return 0;
+	REF_CATCH(-1)
+}
+
 // hasNewParts (HubbardOneOrbital.h:88-107 and siblings): returns 1 and the new sector, 0 when the operator keeps the sector
 int ref_has_new_parts(void* h, int op, int spin, int orb, int nup, int ndown, int* new_up, int* new_down)
 {

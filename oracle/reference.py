@@ -72,6 +72,7 @@ def lib():
                                    C.c_void_p]
         L.ref_has_new_parts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                         C.POINTER(C.c_int)]
+        L.ref_rahul.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
@@ -161,6 +162,17 @@ class ReferenceModel:
         if lib().ref_apply_op(self.h, dst.h, op, site, spin, orb, factor, srcv.ctypes.data, z.ctypes.data) != 0:
             raise RuntimeError("reference: " + lib().ref_last_error().decode())
         return z
+
+    def rahul(self, ops, psi):
+        """psiNew = prod ops |psi> by ModelBase::rahulMethod; ops = [(label 0..3, dof, site, transpose), ...]."""
+        a = np.array(ops, dtype=np.int32).reshape(-1, 4)
+        lab, dof, site, tr = (np.ascontiguousarray(a[:, k]) for k in (0, 1, 2, 3))
+        psi = _f64(psi)
+        out = np.zeros(self.rows())
+        if lib().ref_rahul(self.h, len(a), lab.ctypes.data, dof.ctypes.data, tr.ctypes.data, site.ctypes.data, psi.ctypes.data,
+                           out.ctypes.data) != 0:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+        return out
 
     def has_new_parts(self, op, spin, orb=0):
         a, b = C.c_int(0), C.c_int(0)

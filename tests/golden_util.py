@@ -32,6 +32,10 @@ def ops(g):
     return json.loads(str(g["ops"]))
 
 
+def measures(g):
+    return json.loads(str(g["measure"])) if "measure" in g.files else {}
+
+
 def check_crs(g, rowptr, colind, values, tol=1e-14):
     """CRS structure bit-exact against the reference's stored Hamiltonian; values to `tol`."""
     assert int(g["nnz"]) == colind.size

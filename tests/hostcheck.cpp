@@ -110,6 +110,24 @@ void hc_row_words(const HostModel* h, int spin, uint64_t* out)
 }
 uint64_t hc_rank_pair(const HostModel* h, uint64_t k1, uint64_t k2) { return lpp_rank_pair(h->m, k1, k2); }
 
+// Engine::measure pieces on the host: psiNew = prod ops |psi> (scatter, as ModelBase::rahulMethod) with the product's lpp_rahul_apply
+void hc_rahul(const HostModel* h, int nops, const int* labels, const int* dofs, const int* transposes, const int* sites, const double* psi,
+              double* psiNew)
+{
+	LppMeasureOps ops;
+	memset(&ops, 0, sizeof(ops));
+	ops.n = nops;
+	for (int i = 0; i < nops; i++) { ops.label[i] = labels[i]; ops.dof[i] = dofs[i]; ops.transpose[i] = transposes[i]; ops.site[i] = sites[i]; }
+	for (uint64_t r = 0; r < h->m.rows; r++) {
+		const LppRowKets k = lpp_row_kets(h->m, r);
+		word_t o1, o2;
+		double v;
+		if (!lpp_rahul_apply(ops, k.k1, k.k2, &o1, &o2, &v)) continue;
+		if (h->m.model == LPP_MODEL_TJ && (o1 & o2)) continue;
+		psiNew[lpp_rank_pair(h->m, o1, o2)] += v * psi[r];
+	}
+}
+
 void hc_destroy(HostModel* h) { delete h; }
 uint64_t hc_rows(const HostModel* h) { return h->m.rows; }
 uint64_t hc_basis_size(const HostModel* h, int spin) { return spin ? h->m.n2 : h->m.n1; }

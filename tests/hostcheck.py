@@ -26,6 +26,7 @@ def lib():
         L.hc_row_words.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hc_rank_pair.restype = C.c_uint64
         L.hc_rank_pair.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.hc_rahul.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hc_destroy.argtypes = [C.c_void_p]
         L.hc_rows.restype = C.c_uint64
         L.hc_rows.argtypes = [C.c_void_p]
@@ -84,6 +85,15 @@ class HostModel:
     def row_words(self, spin):
         out = np.zeros(self.rows(), dtype=np.uint64)
         lib().hc_row_words(self.h, spin, out.ctypes.data)
+        return out
+
+    def rahul(self, ops, psi):
+        a = np.array(ops, dtype=np.int32).reshape(-1, 4)
+        lab, dof, site, tr = (np.ascontiguousarray(a[:, k]) for k in (0, 1, 2, 3))
+        psi = _f(psi)
+        out = np.zeros(self.rows())
+        lib().hc_rahul(self.h, len(a), lab.ctypes.data, dof.ctypes.data, tr.ctypes.data, site.ctypes.data, psi.ctypes.data,
+                       out.ctypes.data)
         return out
 
     def rank_pair(self, k1, k2):

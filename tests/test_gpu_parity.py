@@ -597,3 +597,25 @@ def test_spin_operator_continued_fractions(lpp, oracle, name, op):
         gref = oracle.cf_eval(a, b, e0, weight, -s, omega, 0.1)
         assert np.abs(cf(omega, 0.1) - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max()), (name, op, typ)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["c1_hub8", "hub_rand7", "feas4", "tj8_V"])
+def test_measure_matches_reference_fixture(lpp, name):
+    """Engine::measure on the device (lpp_measure): <v| prod ops |v> for the fixture's vector v against the values the reference's
+    ModelBase::rahulMethod gave; physical checks on a ground state (densities sum to the electron numbers)."""
+    from tests import golden_util as gu
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    g = gu.load(name, case)
+    eng = cases.make_engine(lpp, case)
+    eng.set_groundstate(geo.splitmix64_vector(eng.rows(), gu.SRC_SEED))
+    en = lpp.Engine.__new__(lpp.Engine)
+    en.mat, en.io = eng, {}
+    label = {0: "identity", 1: "n", 2: "sz", 3: "c"}
+    for key, rec in gu.measures(g).items():
+        got = en.measure([(label[o[0]], o[1], o[2], o[3]) for o in rec["ops"]])
+        assert abs(got - rec["value"]) <= 1e-12 * max(1.0, abs(rec["value"])), (name, key)
+    en2 = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13}, init=geo.splitmix64_vector(eng.rows(), 1))
+    nb = case["nsite"] * case["orbitals"]
+    assert abs(sum(en2.measure([("n", 0, s)]) for s in range(nb)) - case["nup"]) <= 1e-9
+    assert abs(sum(en2.measure([("n", 1, s)]) for s in range(nb)) - case["ndown"]) <= 1e-9
+    eng.close()

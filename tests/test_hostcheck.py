@@ -143,6 +143,24 @@ def test_spin_operators_match_reference_fixture(name):
     assert seen >= 3
 
 
+@pytest.mark.parametrize("name", ["c1_hub8", "hub_rand7", "hub6_pbc_V", "feas4", "feas_2x2", "tj8_V", "tj_3x3"])
+def test_measure_products_match_reference_rahul_method(name):
+    """Engine::measure: the product's lpp_rahul_apply (compiled for the host) against the reference's own ModelBase::rahulMethod
+    (fixtures): the modified vectors element by element, the expectation values to rounding."""
+    from tests import golden_util as gu
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
+    g = gu.load(name, case)
+    h = HostModel(case)
+    src = geo.splitmix64_vector(h.rows(), gu.SRC_SEED)
+    meas = gu.measures(g)
+    assert len(meas) >= 4
+    for key, rec in meas.items():
+        psi_new = h.rahul(rec["ops"], src)
+        assert abs(src @ psi_new - rec["value"]) <= 1e-12 * max(1.0, abs(rec["value"])), key
+        if "rahul_" + key in g.files:
+            assert np.array_equal(psi_new, g["rahul_" + key]), key
+
+
 def test_splitmix_matches_numpy():
     v = geo.splitmix64_vector(64, 1234, offset=10**12)
     for i in range(64):

@@ -84,6 +84,22 @@ def new_sector_of(r, case, op, spin, orb):
     return r.new_sector(nu, nd), nu, nd
 
 
+def measure_list(case):
+    """operator products for Engine::measure / ModelBase::rahulMethod: (label 0 identity 1 n 2 sz 3 c, dof, bit position, transpose).
+    t-J gets the diagonal ones only: the reference asserts when a product leaves the no-double-occupancy space."""
+    if case["model"] == cases.HEISENBERG:
+        return {}
+    nb = case["nsite"] * case["orbitals"]
+    s0, s1 = 0, nb - 1
+    out = {"n_up": [(1, 0, s0, 0)], "nn": [(1, 0, s0, 0), (1, 1, s1, 0)], "szsz": [(2, 0, s0, 0), (2, 1, s1, 0)],
+           "id_n": [(0, 0, s0, 0), (1, 1, s0, 0)]}
+    if case["model"] != cases.TJ:
+        out.update({"hop_up": [(3, 0, s0, 1), (3, 0, s1, 0)], "hop_dn": [(3, 1, s1, 1), (3, 1, s0, 0)],
+                    "pair": [(3, 0, s0, 1), (3, 0, s1, 0), (3, 1, s1, 1), (3, 1, s0, 0)],
+                    "same_site": [(3, 0, s0, 1), (3, 0, s0, 0)]})
+    return out
+
+
 def generate(name, case):
     r = make_reference(case)
     n = r.rows()
@@ -124,6 +140,15 @@ def generate(name, case):
         out[key] = z
         ops.append(dict(key=key, op=op, site=site, spin=spin, orb=orb, nup=nu, ndown=nd))
     out["ops"] = np.array(json.dumps(ops))
+    meas = {}
+    for key, oplist in measure_list(case).items():
+        if any(o[0] == 3 for o in oplist) and (case["nup"] == 0 or case["ndown"] == 0):
+            continue
+        psi_new = r.rahul(oplist, src)
+        meas[key] = dict(ops=[list(map(int, o)) for o in oplist], value=float(src @ psi_new))
+        if key in ("hop_up", "pair", "nn"):
+            out["rahul_" + key] = psi_new
+    out["measure"] = np.array(json.dumps(meas))
     return out
 
 
