@@ -138,6 +138,18 @@ public:
 		return result;
 	}
 
+	// Engine.h:208-249 with bra = ket = ground state: <gs| op_0[site_0]; ...; op_{n-1}[site_{n-1}] |gs>, ModelBase::rahulMethod
+	// semantics; labels 0 identity, 1 n, 2 sz, 3 c (cdagger when transpose), dof 0 up / 1 down, site = bit position
+	struct MeasureOp { int label, dof, site, transpose; };
+	double measure(const std::vector<MeasureOp>& ops) const
+	{
+		std::vector<int32_t> l, d, t, s;
+		for (const MeasureOp& o : ops) { l.push_back(o.label); d.push_back(o.dof); t.push_back(o.transpose); s.push_back(o.site); }
+		double r = 0;
+		check(lpp_measure(h_, (int32_t)ops.size(), l.data(), d.data(), t.data(), s.data(), &r));
+		return r;
+	}
+
 private:
 	static void check(int status)
 	{
