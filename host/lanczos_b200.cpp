@@ -21,6 +21,7 @@
 #include <vector>
 #include "../include/lpp_b200.h"
 #include "engine_b200.h"
+#include "comb_io.h"
 
 struct Input {
 	std::map<std::string, std::string> scalars;               // "Label=" lines
@@ -259,6 +260,23 @@ int main(int argc, char** argv)
 			std::vector<lppb200::ContinuedFraction> cfs;
 			engine.spectralFunction(cfs, what, site0, site1, spin);
 			std::cout << "#gf(i=" << site0 << ", j=" << site1 << ")\n";
+			{   // <basename of the input>0.comb, LanczosDriver1.h:147-181
+				lppb200::CombFile comb;
+				comb.site0 = site0;
+				comb.site1 = site1;
+				for (const auto& cf : cfs) {
+					std::ostringstream key;
+					key << spin << "," << cf.type << ",0,0";                 // Engine.h:199-202
+					comb.indexToCf.push_back(key.str());
+					lppb200::CombFraction f;
+					f.a = cf.a; f.b = cf.b; f.weight = cf.weight; f.Eg = cf.Eg; f.isign = cf.isign;
+					comb.cfs.push_back(f);
+				}
+				std::string base = file.substr(file.find_last_of('/') == std::string::npos ? 0 : file.find_last_of('/') + 1);
+				const std::string out = base + "0.comb";
+				lppb200::writeComb(out, comb);
+				std::cerr << "lanczos_b200: Written to " << out << "\n";
+			}
 			for (const auto& cf : cfs) {
 				std::cout << "#CF type=" << cf.type << " isign=" << cf.isign << " weight=" << cf.weight << " Eg=" << cf.Eg << " steps=" << cf.a.size() << "\n";
 				for (size_t k = 0; k < cf.a.size(); k++) std::cout << cf.a[k] << " " << cf.b[k] << "\n";

@@ -73,6 +73,23 @@ def build_driver(force=False):
     return DRIVER_BIN
 
 
+def build_cf_collection(force=False):
+    """Compile host/cf_collection.cpp (the evaluator for .comb files) against the in-tree shared library."""
+    build()
+    src = os.path.join(os.path.dirname(DRIVER_SRC), "cf_collection.cpp")
+    hdr = os.path.join(os.path.dirname(DRIVER_SRC), "comb_io.h")
+    exe = os.path.join(os.path.dirname(DRIVER_SRC), "cf_collection")
+    if not force and os.path.exists(exe) and os.path.getmtime(exe) >= max(os.path.getmtime(src), os.path.getmtime(hdr),
+                                                                         os.path.getmtime(LIB_PATH)):
+        return exe
+    cmd = ["/usr/bin/g++", "-O2", "-std=c++17", "-o", exe, src, "-L" + _HERE, "-llpp_b200",
+           "-Wl,-rpath,$ORIGIN/../lanczosplusplus_b200"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise LppError("g++ failed:\n" + r.stdout)
+    return exe
+
+
 class Desc(C.Structure):
     _fields_ = [("model", C.c_int32), ("nsite", C.c_int32), ("orbitals", C.c_int32), ("nup", C.c_int32),
                 ("ndown", C.c_int32), ("feas_u3_all_pairs", C.c_int32),

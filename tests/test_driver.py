@@ -9,9 +9,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(lpp, args):
+def run(lpp, args, cwd=None):
     exe = lpp._lib.build_driver()
-    return subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    return subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=cwd)
 
 
 def test_parses_reference_style_inputs(lpp):
@@ -38,13 +38,21 @@ def test_driver_energies(lpp):
 
 
 @pytest.mark.gpu
-def test_driver_spectral_function_matches_python_engine(lpp):
+def test_driver_spectral_function_matches_python_engine(lpp, tmp_path):
     """`lanczos_b200 -g c`: the C++ Engine mirror (host/engine_b200.h, Engine.h:133-206) against the ctypes mirror and its
     oracle-checked continued fractions (tests/test_gpu_parity.py::test_continued_fraction_parity)."""
     from tests import cases
-    r = run(lpp, ["-f", os.path.join(ROOT, "tests/inputs/hubbard6_gf.inp"), "-p", "15", "-g", "c", "--omega", "-4,4,0.5,0.1"])
+    r = run(lpp, ["-f", os.path.join(ROOT, "tests/inputs/hubbard6_gf.inp"), "-p", "15", "-g", "c", "--omega", "-4,4,0.5,0.1"],
+            cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr
     assert "#gf(i=1, j=3)" in r.stdout
+    # the .comb file of LanczosDriver1.h:147-181 next to the run, evaluated by the continuedFractionCollection stand-in
+    comb_path = str(tmp_path / "hubbard6_gf.inp0.comb")
+    assert os.path.exists(comb_path)
+    ev = subprocess.run([lpp._lib.build_cf_collection(), "-f", comb_path, "-b", "-4", "-e", "4", "-s", "0.5", "-d", "0.1"],
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert ev.returncode == 0, ev.stderr
+    comb_rows = np.array([[float(x) for x in line.split()] for line in ev.stdout.strip().splitlines()])
     heads = re.findall(r"#CF type=(\d) isign=(-?\d+) weight=(\S+) Eg=(\S+) steps=(\d+)", r.stdout)
     assert [int(h[0]) for h in heads] == [0, 1, 2, 3]
     table = r.stdout.split("#omega ReG ImG\n")[1].strip().splitlines()
@@ -58,6 +66,7 @@ def test_driver_spectral_function_matches_python_engine(lpp):
     for (typ, cf), h in zip(cfs, heads):
         assert cf.isign == int(h[1]) and abs(cf.weight - float(h[2])) <= 1e-9 * max(1.0, abs(cf.weight))
     assert np.abs(g - gref).max() <= 1e-8 * max(1.0, np.abs(gref).max())
+    assert np.abs(comb_rows[:, 1] + 1j * 0 - g.imag).max() <= 1e-9 and np.abs(comb_rows[:, 2] - g.real).max() <= 1e-9
     eng.close()
 
 
