@@ -1390,17 +1390,12 @@ extern "C" int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32
 			lpp_launch_gram_tile(vi, vj, stride, n, nsite, ti, tj, dst->partials, dst->stream);
 			dst->launches += 1;
 			double sums[16];
+			double* const all_partials = dst->partials;
 			for (int q = 0; q < 16 && rc == 0; q += 4) {                  // scal_dev holds 8 values: reduce the 16 sums in four rounds
-				lpp_launch_finalize_sums(dst->partials + (uint64_t)q * npb, npb, 4, dst->scal_dev, dst->stream);
-				cudaStream_t cs = dst->stream;
-				if (dst->desc.nranks > 1) {
-					if (!dst->comm) { rc = fail(LPP_ERR_STATE, "nranks>1 but no communicator"); break; }
-					if (g_nccl.AllReduce(dst->scal_dev, dst->scal_dev, 4, kNcclFloat64, kNcclSum, dst->comm, cs) != 0) { rc = fail(LPP_ERR_NCCL, "all-reduce failed"); break; }
-				}
-				if (cudaMemcpyAsync(dst->scal_host, dst->scal_dev, sizeof(double) * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess ||
-				    cudaStreamSynchronize(cs) != cudaSuccess) { rc = fail(LPP_ERR_CUDA, "two_point reduction failed"); break; }
-				for (int k = 0; k < 4; k++) sums[q + k] = dst->scal_host[k];
+				dst->partials = all_partials + (uint64_t)q * npb;         // reduce_scalars sums rows [0, 4) of h->partials (and all-reduces)
+				rc = reduce_scalars(dst, npb, 4, sums + q);
 			}
+			dst->partials = all_partials;
 			for (int a = 0; a < 4; a++)
 				for (int b = 0; b < 4; b++) {
 					const int i = ti * 4 + a, j = tj * 4 + b;
