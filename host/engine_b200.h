@@ -82,7 +82,7 @@ public:
 			} else if (op == LPP_OP_SPLUS || op == LPP_OP_SMINUS) {
 				const int c = (op == LPP_OP_SPLUS) ? 1 : -1;
 				d.nup += c;
-				if (d.model == LPP_MODEL_HUBBARD) d.ndown -= c;
+				if (d.model != LPP_MODEL_HEISENBERG) d.ndown -= c;
 			}
 			if (d.nup < 0 || d.ndown < 0 || d.nup > nmax || d.ndown > nmax) continue;
 			if (d.model == LPP_MODEL_TJ && d.nup + d.ndown > d.nsite) continue;           // no double occupancy

@@ -628,12 +628,12 @@ LPP_HD int lpp_stored_row(const ModelDev& m, uint64_t r, uint64_t* c, double* v)
 // Spin operators (not fermionic: mysign = 1 except doSignSpSm for S+-), gather form of
 //   HubbardOneBand: getBraIndexSz / getBraIndexSplusSminus (BasisHubbardLanczos.h:221-257) with doSignSpSm (:151-160)
 //   Heisenberg S=1/2: getBraIndex_ / getBraIndexSplusSminus (BasisHeisenberg.h:230-280): sz value 1 - 2 bit, n value bit (spin 0) or 1 - bit
-// op: 2 sz, 4 n (Heisenberg), 5 splus, 6 sminus
-LPP_HD bool lpp_apply_spin_op_source(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, uint64_t r, word_t b1, word_t b2,
-                                     uint64_t* src_row, double* sign)
+// op: 2 sz (Hubbard, Heisenberg), 4 n (Heisenberg), 5 splus, 6 sminus (all four models)
+LPP_HD bool lpp_apply_spin_op_source(const ModelDev& src, const ModelDev& dst, int op, int site, int spin, int orb, uint64_t r, word_t b1,
+                                     word_t b2, uint64_t* src_row, double* sign)
 {
-	const word_t ms = lpp_bit(site);
 	if (dst.model == LPP_MODEL_HEISENBERG) {
+		const word_t ms = lpp_bit(site);
 		const bool up = (b1 & ms) != 0;
 		if (op == 2) { *src_row = r; *sign = up ? -1.0 : 1.0; return true; }
 		if (op == 4) { if ((spin == 0) != up) return false; *src_row = r; *sign = 1.0; return true; }
@@ -644,13 +644,21 @@ LPP_HD bool lpp_apply_spin_op_source(const ModelDev& src, const ModelDev& dst, i
 		*sign = 1.0;
 		return true;
 	}
-	if (dst.model != LPP_MODEL_HUBBARD) return false;
+	// two-species bases: HubbardOneBand (BasisHubbardLanczos.h:221-257), FeAsBasedSc per orbital (BasisFeAsBasedSc.h:291-303,
+	// 356-379 with doSignSpSm :202-211), Tj1Orbital (BasisTjMultiOrbLanczos.h:213-242; doSignSpSm is the BasisBase default 1)
+	const int pos = site * dst.orbitals + orb;
+	const word_t ms = lpp_bit(pos);
 	const bool nu = (b1 & ms) != 0, nd = (b2 & ms) != 0;
-	if (op == 2) { if (nu == nd) return false; *src_row = r; *sign = nu ? 1.0 : -1.0; return true; }
+	if (op == 2) {
+		if (dst.model != LPP_MODEL_HUBBARD || nu == nd) return false;
+		*src_row = r; *sign = nu ? 1.0 : -1.0;
+		return true;
+	}
+	if (op != 5 && op != 6) return false;
 	word_t k1, k2;
 	if (op == 5) { if (!nu || nd) return false; k1 = b1 ^ ms; k2 = b2 | ms; }   // source: up empty, down occupied
 	else { if (nu || !nd) return false; k1 = b1 | ms; k2 = b2 ^ ms; }
-	*sign = (double)(lpp_sign_below(k1, site) * lpp_sign_below(k2, site));    // doSignSpSm of the source words
+	*sign = (dst.model == LPP_MODEL_TJ) ? 1.0 : (double)(lpp_sign_below(k1, pos) * lpp_sign_below(k2, pos));   // doSignSpSm of the source words
 	*src_row = lpp_rank_pair(src, k1, k2);
 	return true;
 }
@@ -661,7 +669,7 @@ LPP_HD bool lpp_apply_op_source(const ModelDev& src, const ModelDev& dst, int op
 	const LppRowKets k = lpp_row_kets(dst, r);
 	const word_t b1 = k.k1, b2 = k.k2;
 	if (op == 2 || op == 5 || op == 6 || dst.model == LPP_MODEL_HEISENBERG)
-		return lpp_apply_spin_op_source(src, dst, op, site, spin, r, b1, b2, src_row, sign);
+		return lpp_apply_spin_op_source(src, dst, op, site, spin, orb, r, b1, b2, src_row, sign);
 	const word_t bra = spin == 0 ? b1 : b2;
 	const int pos = site * dst.orbitals + orb;
 	const word_t ms = lpp_bit(pos);

@@ -1326,7 +1326,7 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	const bool spinop = op == LPP_OP_SZ || op == LPP_OP_SPLUS || op == LPP_OP_SMINUS;
 	if (model == LPP_MODEL_HUBBARD) { if (!fermion && !spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "unsupported operator"); }
 	else if (model == LPP_MODEL_HEISENBERG) { if (!spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "Heisenberg: sz, splus, sminus, n"); }
-	else if (!fermion) return fail(LPP_ERR_ARG, "FeAsBasedSc / Tj1Orbital: c and cdagger");
+	else if (!fermion && op != LPP_OP_SPLUS && op != LPP_OP_SMINUS) return fail(LPP_ERR_ARG, "FeAsBasedSc / Tj1Orbital: c, cdagger, splus, sminus");
 	if (!src->gs) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
 	if (src->desc.nranks != dst->desc.nranks || src->desc.rank != dst->desc.rank || src->device != dst->device)
 		return fail(LPP_ERR_ARG, "source and destination must share device and sharding");
@@ -1335,8 +1335,8 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	// hasNewParts: HubbardOneOrbital.h:212-257, BasisFeAsBasedSc.h:305-326, TjMultiOrb.h:538-557, Heisenberg.h:218-240
 	int eu = src->md.nup, ed = src->md.ndn;
 	if (fermion) { const int dup = (op == LPP_OP_C) ? -1 : 1; if (spin == 0) eu += dup; else ed += dup; }
-	else if (op == LPP_OP_SPLUS) { eu += 1; if (model == LPP_MODEL_HUBBARD) ed -= 1; }
-	else if (op == LPP_OP_SMINUS) { eu -= 1; if (model == LPP_MODEL_HUBBARD) ed += 1; }
+	else if (op == LPP_OP_SPLUS) { eu += 1; if (model != LPP_MODEL_HEISENBERG) ed -= 1; }
+	else if (op == LPP_OP_SMINUS) { eu -= 1; if (model != LPP_MODEL_HEISENBERG) ed += 1; }
 	if (dst->md.nup != eu || (model != LPP_MODEL_HEISENBERG && dst->md.ndn != ed) || dst->md.nsite != src->md.nsite)
 		return fail(LPP_ERR_ARG, "destination sector does not match operator (hasNewParts)");
 	if (model == LPP_MODEL_FEAS && dst->md.orbitals != src->md.orbitals) return fail(LPP_ERR_ARG, "orbital count differs");

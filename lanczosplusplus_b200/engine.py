@@ -369,7 +369,7 @@ class Engine:
             elif lop in (OP_SPLUS, OP_SMINUS):      # HubbardOneOrbital.h:232-257 ; Heisenberg.h:218-240 (parts = (2S, Sz + const))
                 c = 1 if lop == OP_SPLUS else -1
                 nup += c
-                if self.mat.model == HUBBARD:
+                if self.mat.model != HEISENBERG:
                     ndown -= c
             if nup < 0 or ndown < 0 or nup > nmax or ndown > nmax:
                 continue

@@ -1487,11 +1487,12 @@ static int tj_dosign_gf(word_t a, word_t b, int ind, int sector)
 /* accModifiedState_ for the spin operators: getBraIndex of BasisHubbardLanczos.h:162-257 (sz -> getBraIndexSz, splus/sminus ->
  * getBraIndexSplusSminus, sign doSignSpSm :151-160) and of BasisHeisenberg.h:123-139,230-280 (sz value 1 - 2 n_up, n value
  * n_up or 1 - n_up, splus/sminus flip the site; doSignSpSm is the BasisBase default 1) */
-static void apply_spin_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, double factor,
+static void apply_spin_op(const orc_model* src, const orc_model* dst, int op, int site, int spin, int orb, double factor,
                           const double* srcv, double* z)
 {
 	size_t n = orc_rows(src);
-	word_t ms = ((word_t)1) << site;
+	int pos = site * src->orbitals + orb;
+	word_t ms = ((word_t)1) << pos;
 	for (size_t r = 0; r < n; r++) {
 		word_t k1, k2;
 		row_kets(src, r, &k1, &k2);
@@ -1506,9 +1507,10 @@ static void apply_spin_op(const orc_model* src, const orc_model* dst, int op, in
 				else { if (op == ORC_OP_SMINUS) continue; }
 				idx = (long)perfect_index(dst, k1 ^ ms, 0);
 			}
-		} else { /* Hubbard */
+		} else { /* Hubbard; FeAs per orbital (BasisFeAsBasedSc.h:291-303,356-379, doSignSpSm :202-211); t-J (BasisTjMultiOrbLanczos.h:213-242) */
 			int b1 = (k1 & ms) ? 1 : 0, b2 = (k2 & ms) ? 1 : 0;
 			if (op == ORC_OP_SZ) {
+				if (src->model != ORC_HUBBARD) continue;
 				if (!b1 && !b2) continue;
 				if (b1 && b2) continue;
 				value = b1 ? 1 : -1;
@@ -1529,7 +1531,7 @@ static void apply_spin_op(const orc_model* src, const orc_model* dst, int op, in
 					brar2 = k1 ^ ms;
 					idx = (long)perfect_index(dst, brar2, brar1);
 				}
-				mysign = do_sign(k1, site) * do_sign(k2, site);   /* doSignSpSm */
+				if (src->model != ORC_TJ) mysign = do_sign(k1, pos) * do_sign(k2, pos);   /* doSignSpSm (BasisBase default 1 for t-J) */
 			}
 		}
 		if (idx < 0) continue;
@@ -1541,7 +1543,7 @@ void orc_apply_op_orb(const orc_model* src, const orc_model* dst, int op, int si
                       const double* srcv, double* z)
 {
 	if (op == ORC_OP_SZ || op == ORC_OP_SPLUS || op == ORC_OP_SMINUS || src->model == ORC_HEISENBERG) {
-		apply_spin_op(src, dst, op, site, spin, factor, srcv, z);
+		apply_spin_op(src, dst, op, site, spin, orb, factor, srcv, z);
 		return;
 	}
 	size_t n = orc_rows(src);

@@ -122,12 +122,12 @@ def test_apply_op_other_models_match_oracle(oracle, name):
     assert done > 0
 
 
-@pytest.mark.parametrize("name", ["c1_hub8", "hub_rand7", "hub_empty_dn", "heis12", "heis10_field"])
+@pytest.mark.parametrize("name", ["c1_hub8", "hub_rand7", "hub_empty_dn", "heis12", "heis10_field", "feas3", "feas_2x2", "tj8_V", "tj_3x3"])
 def test_spin_operators_match_reference_fixture(name):
     """sz / splus / sminus (/ n): the product's gather form (lpp_apply_spin_op_source, compiled for the host) against the
     fixtures produced by the reference's getBraIndex / doSignSpSm."""
     from tests import golden_util as gu
-    case = cases.SMALL_CASES[name]
+    case = (cases.TJ_CASES if name.startswith("tj") else cases.SMALL_CASES)[name]
     g = gu.load(name, case)
     hs = HostModel(case)
     src = geo.splitmix64_vector(hs.rows(), gu.SRC_SEED)

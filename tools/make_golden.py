@@ -66,6 +66,11 @@ def op_list(case):
     if case["model"] == cases.HEISENBERG:
         for spin in (0, 1):
             out.append((ref.OP_N, sites[-1], spin, 0))
+    if case["model"] in (cases.FEAS, cases.TJ):
+        for op in (ref.OP_SPLUS, ref.OP_SMINUS):
+            for site in sites[:2]:
+                for orb in range(case["orbitals"]):
+                    out.append((op, site, 0, orb))
     return out
 
 
