@@ -150,7 +150,7 @@ int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const double* in
 
 /* Engine::accModifiedState_ (Engine.h:416-458): dst.modified (+)= factor * O_{site,spin,orb} |src.groundstate>, 64-bit indices.
  * HubbardOneBand: c, cdagger, n, sz, splus, sminus (BasisHubbardLanczos.h:106-257); FeAsBasedSc (per orbital) and Tj1Orbital: c,
- * cdagger; Heisenberg S=1/2: sz, n, splus, sminus (BasisHeisenberg.h:123-139,230-280).  dst is a handle on the sector hasNewParts
+ * cdagger, splus, sminus; Heisenberg S=1/2: sz, n, splus, sminus (BasisHeisenberg.h:123-139,230-280).  dst is a handle on the sector hasNewParts
  * gives (src itself for sz / n).
  * accumulate == 0 zeroes dst.modified first. */
 int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb, double factor,
