@@ -73,3 +73,22 @@ def test_solver_options_dispatch(lpp):
     assert lpp.kernel_from_solver_options("none,InternalProductCuda") == lpp.KERNEL_AUTO
     assert lpp.kernel_from_solver_options("InternalProductStored") == lpp.KERNEL_STORED
     assert lpp.kernel_from_solver_options("InternalProductCudaGeneric") == lpp.KERNEL_GENERIC
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under lanczosplusplus_b200/, host/ or include/ may import, include, link or
+    load it (a product path that routes through the oracle would void every parity claim)."""
+    bad = []
+    for sub, exts in (("lanczosplusplus_b200", (".py", ".cu", ".cuh", ".h")), ("host", (".cpp", ".h")), ("include", (".h",))):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if not f.endswith(exts):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                for pat in (r"^\s*(from|import)\s+oracle\b", r"#include\s+[\"<].*oracle", r"liblpp_oracle", r"liblpp_ref",
+                            r"lanczos_oracle"):
+                    if re.search(pat, text, flags=re.M):
+                        bad.append((os.path.join(sub, f), pat))
+    assert not bad, bad
+    # and the build line of the product library names only its own sources
+    assert all(s.startswith("lpp_") for s in __import__("lanczosplusplus_b200")._lib.SOURCES)
