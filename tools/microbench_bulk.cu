@@ -73,6 +73,72 @@ __global__ void __launch_bounds__(THREADS, 1) k_fill(const double* __restrict__ 
 	if (acc == 1.2345) sink[0] = acc;
 }
 
+// Row SEGMENTS instead of column pairs: what the streamed version of the staged down sweep would do.  Every CTA pulls `nseg`
+// segments of SEGB bytes (one per source row, row stride = pitch) per batch into a shared-memory ring, 400 batches.
+//   MODE 0: one elected lane per segment issues cp.async.bulk (SEGB bytes each)      MODE 1: cp.async 16 bytes per thread
+template <int MODE, int SEGB>
+__global__ void __launch_bounds__(256, 1) k_segments(const double* __restrict__ y, uint64_t pitch, int nseg, int batches, double* sink)
+{
+	extern __shared__ __align__(128) double ring[];                 // [nseg][SEGB / 8]
+	__shared__ __align__(8) unsigned long long bar;
+	const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar);
+	if (threadIdx.x == 0) { mbar_init(bar_s, 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+	__syncthreads();
+	double acc = 0;
+	uint32_t phase = 0;
+	const uint64_t col0 = ((uint64_t)blockIdx.x * 64) % (pitch - SEGB / 8);
+	for (int b = 0; b < batches; b++) {
+		const uint64_t row0 = ((uint64_t)b * 131 + blockIdx.x * 17) % (ROWS - nseg * 7);
+		if (MODE == 0) {
+			if (threadIdx.x == 0) mbar_expect(bar_s, (uint32_t)nseg * SEGB);
+			__syncthreads();
+			for (int q = threadIdx.x; q < nseg; q += 256)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring_s + q * SEGB),
+				             "l"(y + (row0 + (uint64_t)q * 7) * pitch + (col0 & ~1ull)), "r"(SEGB), "r"(bar_s)
+				             : "memory");
+			mbar_wait(bar_s, phase);
+			phase ^= 1;
+		} else {
+			constexpr int LPS = SEGB / 16;                           // lanes per segment
+			for (int q = threadIdx.x; q < nseg * LPS; q += 256) {
+				const int sgm = q / LPS, piece = q % LPS;
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_s + sgm * SEGB + piece * 16),
+				             "l"(y + (row0 + (uint64_t)sgm * 7) * pitch + (col0 & ~1ull) + piece * 2));
+			}
+			asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+			__syncthreads();
+		}
+		acc += ring[(threadIdx.x * 13 + b) % (nseg * SEGB / 8)];
+		__syncthreads();
+	}
+	if (acc == 1.2345) sink[0] = acc;
+}
+
+template <int MODE, int SEGB>
+static int run_segments(const double* y, uint64_t pitch, double* sink, int khz)
+{
+	const int nseg = 96, batches = 400;
+	const size_t smem = (size_t)nseg * SEGB;
+	CK(cudaFuncSetAttribute(k_segments<MODE, SEGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	float ms = 0;
+	for (int rep = 0; rep < 3; rep++) {
+		CK(cudaEventRecord(e0));
+		k_segments<MODE, SEGB><<<148, 256, smem>>>(y, pitch, nseg, batches, sink);
+		CK(cudaEventRecord(e1));
+		CK(cudaEventSynchronize(e1));
+		CK(cudaGetLastError());
+		cudaEventElapsedTime(&ms, e0, e1);
+	}
+	const double bytes = 148.0 * batches * nseg * SEGB;
+	printf("%-22s %4d-byte segments, %d per batch (no overlap between batches): %.3f ms, %.1f clk/segment/SM, %.0f GB/s chip-wide\n",
+	       MODE == 0 ? "cp.async.bulk" : "cp.async 16B/thread", SEGB, nseg, ms, 1e-3 * ms / batches / nseg * khz * 1e3, bytes / (ms * 1e6));
+	return 0;
+}
+
 int main()
 {
 	const uint64_t pitch = 12870, n = (uint64_t)ROWS * pitch;
@@ -111,5 +177,8 @@ int main()
 				       1e3 * ms / tiles, 1e-3 * ms / tiles / ROWS * khz * 1e3, khz / 1000, 148.0 * tiles * ROWS * 16 / (ms * 1e6));
 		}
 	}
+	if (run_segments<0, 512>(y, pitch, sink, khz) || run_segments<1, 512>(y, pitch, sink, khz) || run_segments<0, 1024>(y, pitch, sink, khz) ||
+	    run_segments<1, 1024>(y, pitch, sink, khz) || run_segments<0, 2048>(y, pitch, sink, khz))
+		return 1;
 	return 0;
 }
