@@ -24,6 +24,8 @@ METRIC = "Lanczos s/iteration (16-site Hubbard 4x4, 8 up 8 down, on-the-fly SpMV
 UNIT = "s/iteration"
 BYTES_PER_ROW_SPMV = 24.0    # read y, read x, write x
 BYTES_PER_ROW_ITER = 48.0    # fused Lanczos iteration
+KERNELS = {"c3": "k_sweep_down_lean + k_sweep_up_packed (one launch each)", "c3small": "k_sweep_down_lean + k_sweep_up_packed",
+           "c4": "k_sweep_down_lean + k_sweep_up_packed + k_sweep_twospin_tab", "c2": "k_spmv_heis (one launch)"}
 
 
 def metric_name(workload_name, desc):
@@ -116,6 +118,8 @@ def cpu_sample(case, budget_rows, faithful, steps, warmup):
     plus the three PsimagLite sweeps on n elements, scaled to the full dimension."""
     from oracle import oracle as orc
     from lanczosplusplus_b200 import geometry as geo
+    orc.build()
+    orc.set_num_threads(host_cores())
     m = orc.OracleModel(case["model"], case["nsite"], case["nup"], case["ndown"], case["orbitals"], hop=case.get("hop"),
                         jzz=case.get("jzz"), U=case.get("U"), V=case.get("V"), D=case.get("D"),
                         fast_rank=0 if faithful else 1)
@@ -179,19 +183,63 @@ def compiled_reference_check(case):
         return {"unavailable": str(exc)[:200]}
 
 
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def checks_vs_fixtures(workload_name, a, b):
+    """alpha/beta of the seeded decomposition against (1) the oracle pin at the named size (tools/make_fullsize_pins.py) and
+    (2) the committed 1-GPU coefficients (tests/golden/bench_ab_1gpu.json, written by `bench.py --write-ab-fixture`)."""
+    out = {"alpha0": float(a[0]), "beta0": float(b[0]), "n": int(min(20, len(a))),
+           "ab_checksum": float(np.sum(a[:20]) + np.sum(b[:20]))}
+    pins = os.path.join(ROOT, "tests", "golden", "fullsize_pins.json")
+    if os.path.exists(pins):
+        p = json.load(open(pins)).get(workload_name)
+        if p and "alpha0" in p:
+            out["oracle_pin"] = {"alpha0_rel_err": abs(a[0] - p["alpha0"]) / abs(p["alpha0"]),
+                                 "beta0_rel_err": abs(b[0] - p["beta0"]) / abs(p["beta0"])}
+        elif p and "alpha" in p:
+            n = min(len(p["alpha"]), len(a))
+            out["oracle_pin"] = {"alpha_rel_err": float(np.max(np.abs(np.array(p["alpha"][:n]) - a[:n]) / np.abs(p["alpha"][:n]))),
+                                 "beta_rel_err": float(np.max(np.abs(np.array(p["beta"][:n]) - b[:n]) / np.abs(p["beta"][:n])))}
+    fx = os.path.join(ROOT, "tests", "golden", "bench_ab_1gpu.json")
+    if os.path.exists(fx):
+        f = json.load(open(fx)).get(workload_name)
+        if f:
+            n = min(len(f["alpha"]), len(a), 20)
+            fa, fb = np.array(f["alpha"][:n]), np.array(f["beta"][:n])
+            out["vs_1gpu"] = {"n": n, "max_rel_diff": float(max(np.max(np.abs(a[:n] - fa) / np.abs(fa)), np.max(np.abs(b[:n] - fb) / np.abs(fb))))}
+    return out
+
+
 def run_reference(args, case, desc):
+    """The reference's CPU implementation of the path (oracle port; oracle/_ref has no row-range entry point) on ALL host cores,
+    whatever OMP_NUM_THREADS says (torchrun exports 1).  Every step is a bounded row sample, scaled to the full dimension."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_sample(case, args.cpu_rows, True, max(1, min(args.steps, 3)), min(args.warmup, 1))
+    from oracle import oracle as orc
+    orc.build()
+    orc.set_num_threads(host_cores())
+    r = cpu_sample(case, args.cpu_rows, True, max(1, args.steps), max(0, args.warmup))
+    tuned = cpu_sample(case, args.cpu_rows, False, 3, 1)
+    frac = r["sample_rows"] / r["rows"]
     line = {"impl": "reference", "metric": metric_name(args.workload, desc), "value": r["s_per_iter"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["s_per_iter"] * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "rows": r["rows"]},
+            "extrapolated": frac < 1.0, "sample_fraction": frac,
             "cpu_baseline": {"value": r["s_per_iter"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-                             "sample": "rows [%d..+%d) of x+=Hy (faithful HubbardHelper.h:105-134 port, OpenMP) + 3 sweeps, "
-                                       "scaled by %d/%d" % ((r["rows"] - r["sample_rows"]) // 2, r["sample_rows"],
-                                                            r["rows"], r["sample_rows"])},
+                             "sample": "rows [%d..+%d) of x+=Hy (faithful HubbardHelper.h:105-134 port: serial diagonal pass, "
+                                       "SparseRow per row, OpenMP over rows) + 3 PsimagLite sweeps, median of %d steps after %d "
+                                       "warm-up, scaled by %d/%d" % ((r["rows"] - r["sample_rows"]) // 2, r["sample_rows"],
+                                                                     max(1, args.steps), max(0, args.warmup), r["rows"], r["sample_rows"])},
+            "cpu_baseline_tuned": {"value": tuned["s_per_iter"], "unit": UNIT, "cores": tuned["cores"], "kind": "port",
+                                   "sample": "same rows, tuned port: diagonal computed inline, no per-row allocation, table rank "
+                                             "(3 steps after 1 warm-up)"},
             "spmv_gbs": BYTES_PER_ROW_SPMV * r["rows"] / r["spmv_s"] / 1e9,
             "e2e": {"value": r["s_per_iter"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "compiled_reference_check": compiled_reference_check(case)}
@@ -209,6 +257,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=5_000_000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-energy", action="store_true")
+    ap.add_argument("--write-ab-fixture", action="store_true", help="1 GPU: store alpha/beta of the seeded run in tests/golden")
     args = ap.parse_args()
     case, desc = workload(args.workload)
     if args.impl == "reference":
@@ -278,11 +327,18 @@ def main():
     torch.cuda.synchronize()
     e2e_s = maxranks((time.perf_counter() - t0) / len(a))
     energy = None
-    if not args.no_energy and world == 1:
+    if not args.no_energy:
         gs = lpp.LanczosSolver(eng, lpp.ParametersForSolver(steps=300, eps=1e-12))
         energy, _, aa, _ = gs.computeOneState(None, want_vector=False)
     if rank != 0:
         return
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if args.write_ab_fixture and world == 1:
+        fx = os.path.join(ROOT, "tests", "golden", "bench_ab_1gpu.json")
+        cur = json.load(open(fx)) if os.path.exists(fx) else {}
+        cur[args.workload] = {"alpha": [float(t) for t in a[:20]], "beta": [float(t) for t in b[:20]], "seed": 1234,
+                              "how": "bench.py --write-ab-fixture on 1 B200 (lpp_lanczos_decomposition, eps 0)"}
+        json.dump(cur, open(fx, "w"), indent=1)
     peak, peak_src = measured_peak()
     spmv_bytes = BYTES_PER_ROW_SPMV * rows / world           # per GPU, per launch of the SpMV
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
@@ -290,21 +346,22 @@ def main():
     line = {"metric": metric_name(args.workload, desc), "value": iter_ms * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": iter_ms, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "rows": rows, "kernel": args.kernel, "l2": "vectors (1.3 GB) exceed L2; no flush",
-                       "sharding": ("two-layout: up sweep on row shards, down sweep on column shards, re-layout by peer-memory kernels "
-                                    "over NVLink (CUDA IPC); NCCL for the scalar all-reduces") if world > 1 else "none"},
+            "config": {"workload": desc, "rows": rows},
+            "run": {"kernel": args.kernel, "l2": "vectors (%.2f GB) %s L2; no flush" % (rows * 8e-9, "exceed" if rows * 8 > 2.5e8 else "FIT in"),
+                    "sharding": ("two-layout: up sweep on row shards, down sweep on column shards, re-layout by peer-memory kernels "
+                                 "over NVLink (CUDA IPC); NCCL for the scalar all-reduces") if world > 1 else "none"},
             "spmv_ms": spmv_ms, "spmv_gbs": BYTES_PER_ROW_SPMV * rows / (spmv_ms * 1e-3) / 1e9,
             "iter_gbs": BYTES_PER_ROW_ITER * rows / (iter_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "x += H y = k_sweep_down_lean + k_sweep_up_packed (one launch each), 24 B/row algorithmic, "
-                                   "per GPU; duration = CUDA events around both launches on the engine's stream",
+                         "kernel": "x += H y = %s, 24 B/row algorithmic, per GPU; duration = CUDA events around the launches "
+                                   "on the engine's stream" % KERNELS.get(args.workload, "engine AUTO kernels"),
                          "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram read+write of both sweeps)"
                                            if traffic else None,
                          "ncu_kernels": traffic_kernels},
             "gpu_launches": int(launches), "clocks": clocks,
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": nloc * 8.0 / len(a), "d2h_bytes_per_step": 16},
-            "energy": energy}
+            "energy": energy, "parity": checks_vs_fixtures(args.workload, a, b)}
     if world == 1 and not args.no_cpu:
         r = cpu_sample(case, args.cpu_rows, True, 2, 1)
         line["cpu_baseline"] = {"value": r["s_per_iter"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -23,12 +23,73 @@
 
 #include <vector>
 #include <cassert>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <string>
+#include <unistd.h>
 #include "Vector.h"
 #include "Matrix.h"
 #include "lpp_b200.h"
 
 namespace LanczosPlusPlus {
+
+// Which GPU this process drives and, for a row-sharded run (one process per GPU, all started with the same input file), its
+// rank.  Filled by the driver from the input label `Gpus=` (integration/engine_cuda.patch, LanczosDriver1.h) or, when the
+// label is absent, from the launcher's environment: LPP_DEVICE | LOCAL_RANK, LPP_RANK | RANK, LPP_NRANKS | WORLD_SIZE,
+// LPP_NCCL_ID_FILE (a path every rank can read: rank 0 writes the 128-byte NCCL id there).
+struct CudaTopology {
+	int device, rank, nranks;
+	std::string idFile;
+	CudaTopology() : device(0), rank(0), nranks(1) {}
+	static CudaTopology& global()
+	{
+		static CudaTopology t = fromEnvironment();
+		return t;
+	}
+	// `Gpus=` value: a comma-separated list of device ordinals, one per rank; this process takes entry `rank`
+	static void setFromGpusLabel(const std::string& gpus)
+	{
+		CudaTopology& t = global();
+		std::vector<int> devs;
+		size_t pos = 0;
+		while (pos < gpus.size()) {
+			size_t q = gpus.find(',', pos);
+			if (q == std::string::npos) q = gpus.size();
+			if (q > pos) devs.push_back(std::atoi(gpus.substr(pos, q - pos).c_str()));
+			pos = q + 1;
+		}
+		if (devs.empty()) return;
+		t.nranks = devs.size();
+		if (t.rank >= t.nranks) err("InternalProductCuda: rank >= number of entries of Gpus=\n");
+		t.device = devs[t.rank];
+	}
+private:
+	static int envInt(const char* a, const char* b, int dflt)
+	{
+		const char* v = std::getenv(a);
+		if (!v) v = std::getenv(b);
+		return v ? std::atoi(v) : dflt;
+	}
+	static CudaTopology fromEnvironment()
+	{
+		CudaTopology t;
+		t.device = envInt("LPP_DEVICE", "LOCAL_RANK", 0);
+		t.rank = envInt("LPP_RANK", "RANK", 0);
+		t.nranks = envInt("LPP_NRANKS", "WORLD_SIZE", 1);
+		const char* f = std::getenv("LPP_NCCL_ID_FILE");
+		if (f) t.idFile = f;
+		return t;
+	}
+};
+
+// Tag for Engine's two solver call sites (integration/engine_cuda.patch): products that keep the Krylov loop on the GPU
+struct KrylovOnHostTag {};
+struct KrylovOnDeviceTag {};
+template<typename InternalProductType>
+struct KrylovPlacement {
+	typedef KrylovOnHostTag Tag;
+};
 
 template<typename ModelType_, typename SpecialSymmetryType_>
 class InternalProductCuda {
@@ -127,6 +188,33 @@ public:
 		check(lpp_ground_state(handle_, &p, &(init[0]), 1, &energy, &(z[0]), 0, 0, &n));
 	}
 
+	// Device-resident replacement of lanczosSolver.computeAllStatesBelow(eigs, zs, initial, excitedPlusOne) (Engine.h:626):
+	// the form integration/engine_cuda.patch calls.  zs[k] is the k-th Ritz vector (length rows()).
+	template<typename VectorVectorType>
+	void statesBelow(VectorRealType& eigs,
+	                 VectorVectorType& zs,
+	                 const VectorType& init,
+	                 SizeType excitedPlusOne,
+	                 SizeType steps,
+	                 RealType eps,
+	                 SizeType minSteps) const
+	{
+		lpp_solver_params p;
+		p.steps = steps; p.minsteps = minSteps; p.eps = eps; p.kernel = LPP_KERNEL_AUTO; p.reortho = 0; p.seed = 0;
+		const SizeType n = rows();
+		eigs.resize(excitedPlusOne);
+		zs.resize(excitedPlusOne);
+		int32_t ns = 0;
+		if (excitedPlusOne == 1) {
+			zs[0].resize(n);
+			check(lpp_ground_state(handle_, &p, &(init[0]), 1, &(eigs[0]), &(zs[0][0]), 0, 0, &ns));
+			return;
+		}
+		std::vector<double> all(excitedPlusOne*n);
+		check(lpp_states_below(handle_, &p, &(init[0]), excitedPlusOne, &(eigs[0]), &(all[0]), &ns));
+		for (SizeType k = 0; k < excitedPlusOne; ++k) zs[k].assign(all.begin() + k*n, all.begin() + (k + 1)*n);
+	}
+
 private:
 
 	static void check(int status)
@@ -142,7 +230,12 @@ private:
 
 		const GeometryType& geometry = model_.geometry();
 		const SizeType nsite = geometry.numberOfSites();
-		const int modelId = model_.cudaModelId();
+		const int modelId = model_.cudaModelId();         // the model refuses variants the engine does not implement
+		// geometry terms the engine reads: 1 (HubbardOneBand, FeAsBasedSc), 2 (Heisenberg: J+-, Jzz), 4 (Tj1Orbital).  More terms
+		// mean an Extended / Super / KaneMele variant (HubbardHelper.h:39-65, FeBasedSc.h ctor) whose couplings would be dropped.
+		const SizeType wantTerms = (modelId == LPP_MODEL_HEISENBERG) ? 2 : (modelId == LPP_MODEL_TJ) ? 4 : 1;
+		if (geometry.terms() != wantTerms)
+			err("InternalProductCuda: this model variant has geometry terms the CUDA engine does not implement\n");
 		const SizeType orbitals = (modelId == LPP_MODEL_FEAS) ? model_.orbitals(0) : 1;
 		const SizeType nb = nsite*orbitals;
 
@@ -186,16 +279,77 @@ private:
 		d.jpm = jpm.size() ? &(jpm[0]) : 0;
 		d.w = w.size() ? &(w[0]) : 0;
 		model_.exportForCuda(d);            // fills U/nU, V/nV, D/nD from hubbardU, potentialV, anisotropy
-		d.device = 0;
-		d.rank = 0;
-		d.nranks = 1;
+		const CudaTopology& topo = CudaTopology::global();
+		d.device = topo.device;
+		d.rank = topo.rank;
+		d.nranks = topo.nranks;
 		check(lpp_create(&d, &handle_));
+		if (topo.nranks > 1) joinRanks(topo);
+	}
+
+	// nranks > 1: rank 0 creates the NCCL id and publishes it in a file, every rank joins the communicator; the CUDA IPC
+	// handles of the column shards (peer-memory exchange) travel the same way.  Handles are created in the same order on every
+	// rank (ground state first, then one per new sector of Engine::spectralFunction), so a per-process counter names the files.
+	void joinRanks(const CudaTopology& topo)
+	{
+		if (topo.idFile.empty()) err("InternalProductCuda: nranks > 1 needs LPP_NCCL_ID_FILE\n");
+		static int serial = 0;
+		char tag[32];
+		std::snprintf(tag, sizeof(tag), ".%d", serial++);
+		const std::string base = topo.idFile + tag;
+		uint8_t id[128];
+		if (topo.rank == 0) {
+			check(lpp_comm_unique_id(id));
+			publish(base + ".id", id, 128);
+		} else {
+			await(base + ".id", id, 128);
+		}
+		check(lpp_comm_init(handle_, id));
+		uint8_t mine[128];
+		if (lpp_p2p_export(handle_, LPP_KERNEL_AUTO, mine) != 0) return;     // sharding without peer memory: NCCL paths
+		char r[16];
+		std::snprintf(r, sizeof(r), ".p2p.%d", topo.rank);
+		publish(base + r, mine, 128);
+		std::vector<uint8_t> all(128*topo.nranks);
+		for (int q = 0; q < topo.nranks; ++q) {
+			std::snprintf(r, sizeof(r), ".p2p.%d", q);
+			await(base + r, &(all[128*q]), 128);
+		}
+		check(lpp_p2p_import(handle_, &(all[0])));
+	}
+
+	static void publish(const std::string& name, const uint8_t* data, size_t n)
+	{
+		const std::string tmp = name + ".tmp";
+		FILE* f = std::fopen(tmp.c_str(), "wb");
+		if (!f || std::fwrite(data, 1, n, f) != n) err("InternalProductCuda: cannot write " + tmp + "\n");
+		std::fclose(f);
+		if (std::rename(tmp.c_str(), name.c_str()) != 0) err("InternalProductCuda: cannot rename " + tmp + "\n");
+	}
+
+	static void await(const std::string& name, uint8_t* data, size_t n)
+	{
+		for (int tries = 0; tries < 6000; ++tries) {                             // 60 s
+			FILE* f = std::fopen(name.c_str(), "rb");
+			if (f) {
+				const size_t got = std::fread(data, 1, n, f);
+				std::fclose(f);
+				if (got == n) return;
+			}
+			usleep(10000);
+		}
+		err("InternalProductCuda: timed out waiting for " + name + "\n");
 	}
 
 	const ModelType& model_;
 	const BasisType& basis_;
 	lpp_handle* handle_;
 }; // class InternalProductCuda
+
+template<typename ModelType, typename SpecialSymmetryType>
+struct KrylovPlacement<InternalProductCuda<ModelType, SpecialSymmetryType> > {
+	typedef KrylovOnDeviceTag Tag;
+};
 } // namespace LanczosPlusPlus
 
 #endif // INTERNALPRODUCT_CUDA_H

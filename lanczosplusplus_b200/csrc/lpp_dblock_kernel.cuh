@@ -322,7 +322,7 @@ static void db_free_plan(DbDevPlan* dp)
 #define DB_NW (DB_THREADS / 32)
 #define DB_SPR (DB_THREADS / 8)         // states staged per round of the CTA (8 lanes per state)
 #ifndef DB_FILL_MODE
-#define DB_FILL_MODE 1                  // 0: 16-byte cp.async per thread, 1: LDG.128 batches + STS.128
+#define DB_FILL_MODE 0                  // 0: 16-byte cp.async per thread (4.2 k cycles per tile), 1: LDG.128 batches + STS.128 (9 k)
 #endif
 
 struct DbKernelArgs {

@@ -889,6 +889,9 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 	if (tl == 2 && h->comm_borrowed && !h->p2p_requested) return 0;
 	const int G = h->desc.nranks, me = h->desc.rank;
 	const uint64_t n1 = h->md.n1, n2 = h->md.n2;
+	// every rank needs a non-empty column shard (pairs of columns) and row shard: otherwise the gather scheme (all ranks
+	// compute the same split, so the decision is consistent)
+	if (n1 / 2 < (uint64_t)G || n2 < (uint64_t)G) return 0;
 	h->cols.nranks = G;
 	h->cols.me = me;
 	h->dstart.assign(G + 1, 0);

@@ -733,13 +733,13 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add(double* __restrict__ x, 
 // Peer-memory variants (NVLink, CUDA IPC mappings): the pack kernel stores each element straight into the owning rank's
 // column shard, the unpack kernel loads the column results from the owning rank -- transfer and re-layout are one kernel,
 // no staging buffers and no library collective on the data path.
-// one block row per matrix row (no integer division), each thread walks columns with stride blockDim
+// one block row per matrix row (blockIdx.x; no integer division), each thread walks columns with stride blockDim * gridDim.y
 __global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restrict__ src, PeerPtrs ycols, uint64_t nrows,
                                                           uint64_t n1, ColSplit c, uint64_t d0loc)
 {
-	const uint64_t r = blockIdx.y;
+	const uint64_t r = blockIdx.x;
 	const double* __restrict__ srow = src + r * n1;
-	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+	for (uint64_t u = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.y * LPP_TPB) {
 		const int q = lpp_col_owner(c, u);
 		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
 		ycols.p[q][(d0loc + r) * nc + cu] = srow[u];
@@ -749,9 +749,9 @@ __global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restr
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__ x, PeerPtrs xcols, uint64_t nrows, uint64_t n1,
                                                            ColSplit c, uint64_t d0loc)
 {
-	const uint64_t r = blockIdx.y;
+	const uint64_t r = blockIdx.x;
 	double* __restrict__ xrow = x + r * n1;
-	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+	for (uint64_t u = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.y * LPP_TPB) {
 		const int q = lpp_col_owner(c, u);
 		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
 		xrow[u] += xcols.p[q][(d0loc + r) * nc + cu];
@@ -767,11 +767,11 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
                                                                  PeerPtrs xcols, PeerPtrs ycols, uint64_t nrows, uint64_t n1,
                                                                  ColSplit c, uint64_t d0loc, double* __restrict__ partials)
 {
-	const uint64_t r = blockIdx.y;
+	const uint64_t r = blockIdx.x;
 	double* __restrict__ xrow = x + r * n1;
 	const double* __restrict__ yrow = y + r * n1;
 	double s = 0.0;
-	for (uint64_t u = (uint64_t)blockIdx.x * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.x * LPP_TPB) {
+	for (uint64_t u = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; u < n1; u += (uint64_t)gridDim.y * LPP_TPB) {
 		const int q = lpp_col_owner(c, u);
 		const uint64_t nc = c.cs[q + 1] - c.cs[q], cu = u - c.cs[q];
 		const double v = xrow[u] + xcols.p[q][(d0loc + r) * nc + cu] - coef * yrow[u];
@@ -780,13 +780,14 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
 		s += v * v;
 	}
 	s = lpp_block_sum(s);
-	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
 }
 
 static dim3 lpp_rowwise_grid(uint64_t nrows, uint64_t n1)
 {
-	unsigned gx = (unsigned)((n1 + (uint64_t)LPP_TPB * 4 - 1) / ((uint64_t)LPP_TPB * 4));
-	return dim3(gx ? gx : 1, (unsigned)nrows, 1);
+	// rows in grid.x (up to 2^31-1), column chunks in grid.y: a rank's row shard can exceed the 65 535 limit of grid.y
+	unsigned gy = (unsigned)((n1 + (uint64_t)LPP_TPB * 4 - 1) / ((uint64_t)LPP_TPB * 4));
+	return dim3((unsigned)nrows, gy ? gy : 1, 1);
 }
 
 void lpp_launch_pack_cols_p2p(const double* src, const PeerPtrs& ycols, uint64_t nrows, uint64_t n1, const ColSplit& c,

@@ -1608,3 +1608,13 @@ int orc_num_threads(void)
 	return 1;
 #endif
 }
+
+/* bench.py --impl reference: torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm uses all host cores anyway */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}

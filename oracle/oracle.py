@@ -88,6 +88,7 @@ def lib():
                                        C.c_void_p]
         L.orc_two_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -283,3 +284,8 @@ def lanczos_sweeps(x, y):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP thread count of the oracle (overrides OMP_NUM_THREADS, which torchrun sets to 1)."""
+    lib().orc_set_num_threads(int(n))

@@ -7,6 +7,8 @@
 // The reference's ModelBase has no accessor for the (private) model parameters; INTEGRATION.md adds two virtual functions
 // to it.  Here the same arrangement is a wrapper around the reference's model object (ModelWithCuda below), so that no
 // reference source is modified or copied.  Built by `make -C oracle _ref` into oracle/_ref/adapter_check.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -138,6 +140,112 @@ double maxdiff(const std::vector<double>& a, const std::vector<double>& b)
 	return d;
 }
 
+// ---- what PsimagLite::LanczosSolver does at Engine.h:474-478 / :626, restated on the host for any product
+struct Tridiagonal {
+	std::vector<double> a_, b_;
+	void resize(SizeType n) { a_.assign(n, 0.0); b_.assign(n, 0.0); }
+	SizeType size() const { return a_.size(); }
+	double& a(SizeType i) { return a_[i]; }
+	double& b(SizeType i) { return b_[i]; }
+};
+
+template <class ProductType>
+void hostDecomposition(const ProductType& m, const std::vector<double>& init, Tridiagonal& ab, SizeType steps)
+{
+	const SizeType n = m.rows();
+	steps = std::min(steps, n);
+	std::vector<double> x(n, 0.0), y(init);
+	double nrm = 0;
+	for (SizeType i = 0; i < n; i++) nrm += y[i]*y[i];
+	nrm = std::sqrt(nrm);
+	for (SizeType i = 0; i < n; i++) y[i] /= nrm;
+	ab.resize(steps);
+	for (SizeType j = 0; j < steps; j++) {
+		m.matrixVectorProduct(x, y);
+		double a = 0, b = 0;
+		for (SizeType i = 0; i < n; i++) a += y[i]*x[i];
+		for (SizeType i = 0; i < n; i++) { x[i] -= a*y[i]; b += x[i]*x[i]; }
+		b = std::sqrt(b);
+		ab.a(j) = a;
+		ab.b(j) = b;
+		for (SizeType i = 0; i < n; i++) { const double t = y[i]; y[i] = (b < 1e-10) ? x[i] : x[i]/b; x[i] = -b*t; }
+	}
+}
+
+// lowest eigenvalue of the tridiagonal matrix by bisection on the Sturm count
+double lowestEigenvalue(const Tridiagonal& ab)
+{
+	const SizeType n = ab.size();
+	double lo = 1e300, hi = -1e300;
+	for (SizeType i = 0; i < n; i++) {
+		const double r = (i ? std::abs(ab.b_[i - 1]) : 0.0) + (i + 1 < n ? std::abs(ab.b_[i]) : 0.0);
+		lo = std::min(lo, ab.a_[i] - r);
+		hi = std::max(hi, ab.a_[i] + r);
+	}
+	for (int it = 0; it < 200; it++) {
+		const double mid = 0.5*(lo + hi);
+		int below = 0;
+		double q = 1.0;
+		for (SizeType i = 0; i < n; i++) {
+			const double b2 = i ? ab.b_[i - 1]*ab.b_[i - 1] : 0.0;
+			q = ab.a_[i] - mid - (i ? b2/q : 0.0);
+			if (q == 0.0) q = 1e-300;
+			if (q < 0) below++;
+		}
+		if (below >= 1) hi = mid; else lo = mid;
+	}
+	return 0.5*(lo + hi);
+}
+
+// The two call sites of integration/engine_cuda.patch, in the form the patch gives them: tag dispatch on KrylovPlacement
+template <class ProductType>
+void engineDecomposition(const ProductType& m, const std::vector<double>& init, Tridiagonal& ab, SizeType steps, LanczosPlusPlus::KrylovOnHostTag)
+{
+	hostDecomposition(m, init, ab, steps);
+}
+template <class ProductType>
+void engineDecomposition(const ProductType& m, const std::vector<double>& init, Tridiagonal& ab, SizeType steps, LanczosPlusPlus::KrylovOnDeviceTag)
+{
+	m.decomposition(init, ab, steps, 0.0, 4);
+}
+
+// decomposition() and groundState() of the adapter against the host recurrence through the reference's own product
+template <class HostProductType>
+int checkKrylov(const char* name, const HostProductType& host, const CudaType& cuda, const std::vector<double>& init)
+{
+	const SizeType n = host.rows();
+	Tridiagonal abh, abc;
+	const SizeType steps = std::min<SizeType>(n, 24);
+	engineDecomposition(host, init, abh, steps, typename LanczosPlusPlus::KrylovPlacement<HostProductType>::Tag());
+	engineDecomposition(cuda, init, abc, steps, typename LanczosPlusPlus::KrylovPlacement<CudaType>::Tag());
+	double dab = 0;
+	const SizeType ncmp = std::min<SizeType>(std::min(abh.size(), abc.size()), 12);
+	for (SizeType i = 0; i < ncmp; i++) {
+		dab = std::max(dab, std::abs(abh.a_[i] - abc.a_[i])/std::max(1.0, std::abs(abh.a_[i])));
+		if (i + 1 < ncmp) dab = std::max(dab, std::abs(abh.b_[i] - abc.b_[i])/std::max(1.0, std::abs(abh.b_[i])));
+	}
+	Tridiagonal full;
+	hostDecomposition(host, init, full, std::min<SizeType>(n, 200));
+	const double eh = lowestEigenvalue(full);
+	double ec = 0;
+	std::vector<double> z;
+	cuda.groundState(ec, z, init, 200, 1e-12, 4);
+	std::vector<double> hz(n, 0.0);
+	host.matrixVectorProduct(hz, z);
+	double res = 0, zz = 0;
+	for (SizeType i = 0; i < n; i++) { res += (hz[i] - ec*z[i])*(hz[i] - ec*z[i]); zz += z[i]*z[i]; }
+	res = std::sqrt(res);
+	// the form Engine::computeAllStatesBelow calls after integration/engine_cuda.patch
+	std::vector<double> eigs;
+	std::vector<std::vector<double> > zs;
+	cuda.statesBelow(eigs, zs, init, 1, 200, 1e-12, 4);
+	const bool sb = eigs.size() == 1 && zs.size() == 1 && zs[0].size() == n && std::abs(eigs[0] - ec) <= 1e-12*std::max(1.0, std::abs(ec)) && maxdiff(zs[0], z) <= 1e-12;
+	const bool ok = sb && abc.size() == abh.size() && dab <= 1e-10 && std::abs(eh - ec) <= 1e-9*std::max(1.0, std::abs(eh)) && res <= 1e-6 && std::abs(zz - 1.0) <= 1e-9;
+	std::printf("%s krylov steps=%zu ab_rel_diff=%.3e energy_host=%.12f energy_cuda=%.12f residual=%.3e %s\n", name, (size_t)abc.size(), dab, eh, ec, res,
+	            ok ? "ok" : "MISMATCH");
+	return ok ? 0 : 1;
+}
+
 int check(const char* name, const ModelBaseType& model, int id, const MapInput& io, bool hasOnTheFly, bool run_cuda)
 {
 	ModelWithCuda m(model, id, io);
@@ -165,6 +273,9 @@ int check(const char* name, const ModelBaseType& model, int id, const MapInput& 
 		xc = x0;
 		cuda.matrixVectorProduct(xc, y);
 		d_cuda = maxdiff(xc, xs);
+		std::vector<double> init(n);
+		for (SizeType i = 0; i < n; i++) init[i] = splitmix(1234, i);
+		if (checkKrylov(name, stored, cuda, init)) return 1;
 	}
 	std::printf("%s rows=%zu otf_vs_stored=%.3e cuda_vs_stored=%.3e\n", name, (size_t)n, d_otf, d_cuda);
 	return (run_cuda && !(d_cuda <= 1e-12)) ? 1 : 0;

@@ -37,3 +37,8 @@ def test_adapter_matches_reference_internal_products(lpp):
     for name in ("HubbardOneBand", "FeAsBasedSc", "Heisenberg", "Tj1Orbital"):
         d = float(re.search(name + r" rows=\d+ otf_vs_stored=\S+ cuda_vs_stored=(\S+)", r.stdout).group(1))
         assert 0 <= d <= 1e-12, (name, d)
+        # decomposition() / groundState() / statesBelow() of the adapter (the device-resident Krylov loop, reached through the
+        # tag dispatch of integration/engine_cuda.patch) against a host Lanczos through the reference's InternalProductStored
+        m = re.search(name + r" krylov steps=\d+ ab_rel_diff=(\S+) energy_host=(\S+) energy_cuda=(\S+) residual=(\S+) (\w+)", r.stdout)
+        assert m and m.group(5) == "ok", r.stdout
+        assert float(m.group(1)) <= 1e-10 and abs(float(m.group(2)) - float(m.group(3))) <= 1e-9 * max(1.0, abs(float(m.group(2))))

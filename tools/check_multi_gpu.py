@@ -43,6 +43,27 @@ for name, kw in (("hubbard 18-chain 9 up 2 down (blocked up sweep)", dict(model=
             print("%-14s kernel %d ranks %d: max|d(a,b)| %.2e  E %.12f vs %.12f  %.3f ms/iteration  %s" % (name, kernel, world, err, e, e1, ms_iter, "OK" if good else "FAIL"), flush=True)
         sharded.close()
         single.close()
+# config 3 at its named size (dim 165 636 900): first coefficients against the oracle pin and the committed 1-GPU values
+import json  # noqa: E402
+import bench  # noqa: E402
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if os.environ.get("LPP_CHECK_FULL", "1") != "0":
+    case, _ = bench.workload("c3")
+    big = lpp.InternalProductCuda(case["model"], case["nsite"], case["nup"], case["ndown"], case["orbitals"], hop=case["hop"], U=case["U"],
+                                  V=case["V"], device=local, rank=rank, nranks=world)
+    D.attach(big, dist)
+    a, b, _ = lpp.LanczosSolver(big, lpp.ParametersForSolver(steps=20, eps=0.0, seed=1234)).decomposition(None)
+    chk = bench.checks_vs_fixtures("c3", np.asarray(a), np.asarray(b))
+    pin = chk.get("oracle_pin", {})
+    good = pin.get("alpha0_rel_err", 1.0) <= 1e-10 and pin.get("beta0_rel_err", 1.0) <= 1e-10
+    if "vs_1gpu" in chk:
+        good = good and chk["vs_1gpu"]["max_rel_diff"] <= 1e-10
+    ok = ok and good
+    if rank == 0:
+        print("config 3 full size, ranks %d: %s  %s" % (world, json.dumps(chk), "OK" if good else "FAIL"), flush=True)
+    big.close()
 dist.barrier()
 dist.destroy_process_group()
+if rank == 0 and ok:
+    print("ALL OK", flush=True)
 sys.exit(0 if ok else 1)
