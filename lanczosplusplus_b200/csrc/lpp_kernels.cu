@@ -2,6 +2,7 @@
 // generic / table-driven on-the-fly x = beta x + alpha H y (K3, K4), stored CRS build + SpMV (K5), the fused Lanczos
 // vector sweeps (K6, K7, K8) and operator application (K9).  The shared-memory tiled fast path is in lpp_tiled.cu.
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include "lpp_kernels.cuh"
 
 #define LPP_TPB 256
@@ -485,8 +486,9 @@ __global__ void __launch_bounds__(LPP_TPB) k_dot(const double* __restrict__ a, c
 
 // PsimagLite oneStepDecomposition sweep 2: x -= a y ; b2 += |x|^2
 __global__ void __launch_bounds__(LPP_TPB) k_axpy_norm(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                      uint64_t n, double* __restrict__ partials)
+                                                      const double* __restrict__ coef_dev, uint64_t n, double* __restrict__ partials)
 {
+	if (coef_dev) coef = *coef_dev;
 	double s = 0.0;
 	const uint64_t n2 = n / 2;
 	double2* x2 = reinterpret_cast<double2*>(x);
@@ -648,10 +650,47 @@ void lpp_launch_dot(const double* a, const double* b, uint64_t n, double* partia
 {
 	k_dot<<<lpp_vec_blocks(n), LPP_TPB, 0, s>>>(a, b, n, partials);
 }
-void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s)
+void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s, const double* coef_dev)
 {
-	k_axpy_norm<<<lpp_vec_blocks(n), LPP_TPB, 0, s>>>(x, y, coef, n, partials);
+	k_axpy_norm<<<lpp_vec_blocks(n), LPP_TPB, 0, s>>>(x, y, coef, coef_dev, n, partials);
 }
+
+// device-resident Lanczos scalars (one thread): the same operations, in the same order, as the host loop performs
+__global__ void k_lz_init(double nj, double* coefs)
+{
+	coefs[LPP_LZ_NORM] = nj;
+	coefs[LPP_LZ_ALPHA] = 1.0 / nj;
+	coefs[LPP_LZ_BETA] = 0.0;
+	coefs[LPP_LZ_AXPY] = 0.0;
+	coefs[LPP_LZ_STEP] = 0.0;
+}
+__global__ void k_lz_after_dot(const double* __restrict__ dot_parts, int nparts, double* coefs, double* __restrict__ a_out)
+{
+	double dot = dot_parts[0];
+	for (int i = 1; i < nparts; i++) dot += dot_parts[i];
+	const double nj = coefs[LPP_LZ_NORM];
+	const double aj = dot / nj;
+	a_out[(int)coefs[LPP_LZ_STEP]] = aj;
+	coefs[LPP_LZ_AXPY] = aj / nj;
+}
+__global__ void k_lz_after_norm(const double* __restrict__ b2, double* coefs, double* __restrict__ b_out)
+{
+	const double bj = sqrt(*b2);
+	const int j = (int)coefs[LPP_LZ_STEP];
+	b_out[j] = bj;
+	const double nprev = coefs[LPP_LZ_NORM];
+	const double nj = (bj < 1e-10) ? 1.0 : bj;
+	coefs[LPP_LZ_NORM] = nj;
+	coefs[LPP_LZ_ALPHA] = 1.0 / nj;
+	coefs[LPP_LZ_BETA] = -(bj / nprev);
+	coefs[LPP_LZ_STEP] = (double)(j + 1);
+}
+void lpp_launch_lz_init(double nj, double* coefs, cudaStream_t s) { k_lz_init<<<1, 1, 0, s>>>(nj, coefs); }
+void lpp_launch_lz_after_dot(const double* dot_parts, int nparts, double* coefs, double* a_out, cudaStream_t s)
+{
+	k_lz_after_dot<<<1, 1, 0, s>>>(dot_parts, nparts, coefs, a_out);
+}
+void lpp_launch_lz_after_norm(const double* b2, double* coefs, double* b_out, cudaStream_t s) { k_lz_after_norm<<<1, 1, 0, s>>>(b2, coefs, b_out); }
 void lpp_launch_axpy(double* z, const double* v, double coef, uint64_t n, cudaStream_t s)
 {
 	k_axpy<<<lpp_vec_blocks(n * 2), LPP_TPB, 0, s>>>(z, v, coef, n);
@@ -764,9 +803,11 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__
 // (A variant with one owner per block and 16-byte accesses measured 0.84-0.93 ms against 0.70 ms for this one on 2 x B200.)
 template <bool PACK>
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                                 PeerPtrs xcols, PeerPtrs ycols, uint64_t nrows, uint64_t n1,
-                                                                 ColSplit c, uint64_t d0loc, double* __restrict__ partials)
+                                                                 const double* __restrict__ coef_dev, PeerPtrs xcols, PeerPtrs ycols,
+                                                                 uint64_t nrows, uint64_t n1, ColSplit c, uint64_t d0loc,
+                                                                 double* __restrict__ partials)
 {
+	if (coef_dev) coef = *coef_dev;
 	const uint64_t r = blockIdx.x;
 	double* __restrict__ xrow = x + r * n1;
 	const double* __restrict__ yrow = y + r * n1;
@@ -778,6 +819,44 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
 		xrow[u] = v;
 		if (PACK) ycols.p[q][(d0loc + r) * nc + cu] = v;
 		s += v * v;
+	}
+	s = lpp_block_sum(s);
+	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
+}
+
+// The same sweep with 16-byte accesses (n1 even: every shard boundary and every row start is a multiple of two columns).
+// Peer loads are request bound over NVLink: 8-byte loads measured 354 GB/s per GPU on 8 x B200 (0.41 ms for 145 MB), the
+// 16-byte form moves twice the bytes per request; two independent pairs per thread keep more requests in flight.
+// coef is read from `coef_dev` when non-null (device-resident recurrence: no host round trip before this sweep).
+__global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __restrict__ x, const double* __restrict__ y, double coef,
+                                                                    const double* __restrict__ coef_dev, PeerPtrs xcols, uint64_t nrows,
+                                                                    uint64_t n1, ColSplit c, uint64_t d0loc, double* __restrict__ partials)
+{
+	const uint64_t r = blockIdx.x;
+	if (coef_dev) coef = *coef_dev;
+	double2* __restrict__ xrow = reinterpret_cast<double2*>(x + r * n1);
+	const double2* __restrict__ yrow = reinterpret_cast<const double2*>(y + r * n1);
+	const uint64_t npair = n1 >> 1;
+	const uint64_t stride = (uint64_t)gridDim.y * LPP_TPB;
+	double s = 0.0;
+	for (uint64_t p0 = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; p0 < npair; p0 += 2 * stride) {
+		const uint64_t p1 = p0 + stride;
+		const bool two = p1 < npair;
+		const uint64_t u0 = 2 * p0, u1 = 2 * (two ? p1 : p0);
+		const int q0 = lpp_col_owner(c, u0), q1 = lpp_col_owner(c, u1);
+		const uint64_t nc0 = c.cs[q0 + 1] - c.cs[q0], nc1 = c.cs[q1 + 1] - c.cs[q1];
+		const double2 r0 = *reinterpret_cast<const double2*>(xcols.p[q0] + (d0loc + r) * nc0 + (u0 - c.cs[q0]));
+		const double2 r1 = *reinterpret_cast<const double2*>(xcols.p[q1] + (d0loc + r) * nc1 + (u1 - c.cs[q1]));
+		const double2 xa = xrow[p0], ya = yrow[p0];
+		double2 va = make_double2(xa.x + r0.x - coef * ya.x, xa.y + r0.y - coef * ya.y);
+		xrow[p0] = va;
+		s += va.x * va.x + va.y * va.y;
+		if (two) {
+			const double2 xb = xrow[p1], yb = yrow[p1];
+			double2 vb = make_double2(xb.x + r1.x - coef * yb.x, xb.y + r1.y - coef * yb.y);
+			xrow[p1] = vb;
+			s += vb.x * vb.x + vb.y * vb.y;
+		}
 	}
 	s = lpp_block_sum(s);
 	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
@@ -808,13 +887,18 @@ int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1, int nranks)
 	return (int)(g.x * g.y);
 }
 void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, const PeerPtrs* ycols_or_null,
-                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s)
+                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s,
+                                     const double* coef_dev)
 {
 	PeerPtrs yc;
 	for (int i = 0; i < LPP_MAX_RANKS; i++) yc.p[i] = ycols_or_null ? ycols_or_null->p[i] : nullptr;
 	const dim3 g = lpp_rowwise_grid(nrows, n1);
-	if (ycols_or_null) k_unpack_axpy_norm_p2p<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, xcols, yc, nrows, n1, c, d0loc, partials);
-	else k_unpack_axpy_norm_p2p<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, xcols, yc, nrows, n1, c, d0loc, partials);
+	static const bool v2 = !(getenv("LPP_UNPACK_V2") && getenv("LPP_UNPACK_V2")[0] == '0');
+	bool even = (n1 % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
+	for (int q = 0; q <= c.nranks; q++) even = even && (c.cs[q] % 2 == 0);
+	if (ycols_or_null) k_unpack_axpy_norm_p2p<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
+	else if (v2 && even) k_unpack_axpy_norm_p2p_v2<<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, nrows, n1, c, d0loc, partials);
+	else k_unpack_axpy_norm_p2p<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
 }
 
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,

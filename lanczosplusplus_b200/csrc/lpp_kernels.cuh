@@ -21,8 +21,24 @@ struct DiagTables {
 	double U0;
 };
 
+// A coefficient that is either a host value or lives in device memory (the Lanczos loop keeps 1/n_j, -b_{j-1}/n_{j-1} and a_j/n_j
+// on the device so that an iteration needs no host round trip).  Kernels read it like a double.
+struct LppCoef {
+	double v;
+	const double* p;
+	__host__ __device__ LppCoef& operator=(double x) { v = x; p = nullptr; return *this; }
+	__host__ __device__ operator double() const
+	{
+#ifdef __CUDA_ARCH__
+		return p ? *p : v;
+#else
+		return v;                // the host never dereferences the device copy
+#endif
+	}
+};
+
 struct SpmvArgs {
-	double alpha, beta;      // x = beta*x + alpha*(H y)
+	LppCoef alpha, beta;     // x = beta*x + alpha*(H y)
 	double* x;               // local rows
 	const double* y;         // full vector (global indexing)
 	double* dot_partials;    // optional: per-block partial sums of y_local . x_new
@@ -78,7 +94,8 @@ int lpp_vec_blocks(uint64_t n);
 void lpp_launch_fill_random(double* v, uint64_t row0, uint64_t n, uint64_t seed, cudaStream_t s);
 void lpp_launch_dot(const double* a, const double* b, uint64_t n, double* partials, cudaStream_t s);
 // x -= coef*y ; partials <- block sums of x_new^2
-void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s);
+void lpp_launch_axpy_norm(double* x, const double* y, double coef, uint64_t n, double* partials, cudaStream_t s,
+                          const double* coef_dev = nullptr);
 void lpp_launch_axpy(double* z, const double* v, double coef, uint64_t n, cudaStream_t s);
 void lpp_launch_scale(double* v, double coef, uint64_t n, cudaStream_t s);
 // out[0] = sum of partials[0..n) in a fixed order
@@ -103,7 +120,17 @@ void lpp_launch_unpack_add_p2p(double* x, const PeerPtrs& xcols, uint64_t nrows,
                                cudaStream_t s);
 int lpp_unpack_axpy_norm_blocks(uint64_t nrows, uint64_t n1, int nranks);
 void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, const PeerPtrs& xcols, const PeerPtrs* ycols_or_null,
-                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s);
+                                     uint64_t nrows, uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, cudaStream_t s,
+                                     const double* coef_dev = nullptr);
+// device-resident Lanczos scalars: coefs = {alpha = 1/n_j, beta = -b_{j-1}/n_{j-1}, a_j/n_j, n_j, j}
+#define LPP_LZ_ALPHA 0
+#define LPP_LZ_BETA 1
+#define LPP_LZ_AXPY 2
+#define LPP_LZ_NORM 3
+#define LPP_LZ_STEP 4
+void lpp_launch_lz_init(double nj, double* coefs, cudaStream_t s);
+void lpp_launch_lz_after_dot(const double* dot_parts, int nparts, double* coefs, double* a_out, cudaStream_t s);
+void lpp_launch_lz_after_norm(const double* b2, double* coefs, double* b_out, cudaStream_t s);
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,
                           uint64_t d0loc, cudaStream_t s);
 void lpp_launch_unpack_add(double* x, const double* recvbuf, const double* xcol, uint64_t nrows, uint64_t n1, const ColSplit& c,
