@@ -129,6 +129,8 @@ struct lpp_handle {
 	// LPP_PHASES=1: CUDA-event breakdown of the sharded iteration (printed by lpp_destroy)
 	cudaStream_t copy_stream2 = nullptr;
 	cudaEvent_t ev_copy2 = nullptr;
+	cudaStream_t copy_streams[4] = {};    // extra copy streams of the pack: the remote blocks go out on several copy engines
+	cudaEvent_t ev_copies[4] = {};
 	const double* packed_vec = nullptr;   // vector whose column-shard copy (ycol on every rank) is already in place
 	int phases = -1;
 	cudaEvent_t pev[8] = {};
@@ -1011,9 +1013,18 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 				CK(cudaEventCreateWithFlags(&h->ev_copy2, cudaEventDisableTiming));
 			}
 			CK(cudaStreamWaitEvent(h->copy_stream2, h->ev_pack, 0));
+			static const int nextra = []() { const char* e = getenv("LPP_PACK_STREAMS"); int v = e ? atoi(e) : 3; return v < 0 ? 0 : v > 4 ? 4 : v; }();
+			for (int k = 0; k < nextra; k++) {
+				if (!h->copy_streams[k]) {
+					CK(cudaStreamCreateWithFlags(&h->copy_streams[k], cudaStreamNonBlocking));
+					CK(cudaEventCreateWithFlags(&h->ev_copies[k], cudaEventDisableTiming));
+				}
+				CK(cudaStreamWaitEvent(h->copy_streams[k], h->ev_pack, 0));
+			}
 			for (int q = 0; q < G; q++) {
 				const int qq = (me + q) % G;                     // the local block goes to its own stream (another copy engine)
-				cudaStream_t cs = (q % 2 == 0) ? h->copy_stream2 : h->comm_stream;
+				// remote blocks round-robin over comm_stream and the extra copy streams
+				cudaStream_t cs = (q == 0) ? h->copy_stream2 : ((q - 1) % (nextra + 1) == 0) ? h->comm_stream : h->copy_streams[(q - 1) % (nextra + 1) - 1];
 				if (pulled) {
 					// rows of rank qq (its whole row shard), my columns  ->  rows dstart[qq].. of my column shard
 					const uint64_t nrq = h->dstart[qq + 1] - h->dstart[qq];
@@ -1027,6 +1038,10 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 			}
 			CK(cudaEventRecord(h->ev_copy2, h->copy_stream2));
 			CK(cudaStreamWaitEvent(h->comm_stream, h->ev_copy2, 0));
+			for (int k = 0; k < nextra; k++) {
+				CK(cudaEventRecord(h->ev_copies[k], h->copy_streams[k]));
+				CK(cudaStreamWaitEvent(h->comm_stream, h->ev_copies[k], 0));
+			}
 		} else {
 			lpp_launch_pack_cols_p2p(y, h->peer_ycol, nrows, n1, h->cols, d0loc, h->comm_stream);
 		}

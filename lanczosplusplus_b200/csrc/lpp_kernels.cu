@@ -838,11 +838,18 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __r
 	const double2* __restrict__ yrow = reinterpret_cast<const double2*>(y + r * n1);
 	const uint64_t npair = n1 >> 1;
 	const uint64_t stride = (uint64_t)gridDim.y * LPP_TPB;
+	// Every rank walks the columns starting behind its OWN shard (rank r reads peer r+1 first, then r+2, ...): with all ranks
+	// starting at column 0 the eight GPUs read the same peer at the same time and share one NVLink egress (measured on
+	// 8 x B200: 0.45-0.59 ms per sweep against 0.28 ms for the one rank whose first shard is local).
+	const uint64_t rot = c.cs[(c.me + 1) % c.nranks] >> 1;
 	double s = 0.0;
-	for (uint64_t p0 = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; p0 < npair; p0 += 2 * stride) {
-		const uint64_t p1 = p0 + stride;
-		const bool two = p1 < npair;
-		const uint64_t u0 = 2 * p0, u1 = 2 * (two ? p1 : p0);
+	for (uint64_t l0 = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; l0 < npair; l0 += 2 * stride) {
+		const uint64_t l1 = l0 + stride;
+		const bool two = l1 < npair;
+		uint64_t p0 = l0 + rot, p1 = (two ? l1 : l0) + rot;
+		if (p0 >= npair) p0 -= npair;
+		if (p1 >= npair) p1 -= npair;
+		const uint64_t u0 = 2 * p0, u1 = 2 * p1;
 		const int q0 = lpp_col_owner(c, u0), q1 = lpp_col_owner(c, u1);
 		const uint64_t nc0 = c.cs[q0 + 1] - c.cs[q0], nc1 = c.cs[q1 + 1] - c.cs[q1];
 		const double2 r0 = *reinterpret_cast<const double2*>(xcols.p[q0] + (d0loc + r) * nc0 + (u0 - c.cs[q0]));

@@ -726,6 +726,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 {
 	using VT = typename std::conditional<E16, uint2, uint4>::type;
 	extern __shared__ double ys[];                       // [position][R] + G zero slots
+	const double c_alpha = a.alpha, c_beta = a.beta;     // read once (they may live in device memory: LppCoef)
 	constexpr int G = 16 / R;
 	const uint64_t dl0 = (uint64_t)blockIdx.x * R;
 	const uint64_t n1 = m.n1;
@@ -767,7 +768,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 
 	VT en[NG];
 	double xn_old[R];
-	const bool need_x = a.beta != 0.0;
+	const bool need_x = c_beta != 0.0;
 	const uint32_t lane = threadIdx.x & 31;
 	auto prefetch = [&](uint32_t ii) {
 		const uint32_t c = ii >> 5;
@@ -814,7 +815,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 		for (int r = 0; r < R; r++) {
 			if (!live[r]) continue;
 			const double hv = UNI ? t0 * acc[r] : acc[r];
-			double xn = a.beta * xold[r] + a.alpha * hv;
+			double xn = c_beta * xold[r] + c_alpha * hv;
 			xrow[r][i] = xn;
 			contrib += yown[r] * xn;
 		}
@@ -841,6 +842,7 @@ __global__ void __launch_bounds__(PAL_COLS, (VEC == 2) ? 3 : 4) k_sweep_down_lea
                                                                uint64_t dcount, uint32_t nrowchunks, ColView cv)
 {
 	extern __shared__ double ys[];
+	const double c_alpha = a.alpha, c_beta = a.beta;     // read once (they may live in device memory: LppCoef)
 	DownEntry* ent = reinterpret_cast<DownEntry*>(ys);                                  // [PAL_ROWS][width]
 	const uint32_t panel = blockIdx.x / nrowchunks, chunk = blockIdx.x % nrowchunks;
 	const uint64_t pitch = cv.pitch;
@@ -868,7 +870,7 @@ __global__ void __launch_bounds__(PAL_COLS, (VEC == 2) ? 3 : 4) k_sweep_down_lea
 			dv1[v] = dt.dv1[cv.u0 + c + v];
 		}
 		const char* __restrict__ ycol = reinterpret_cast<const char*>(a.y + c);
-		const bool need_x = a.beta != 0.0;
+		const bool need_x = c_beta != 0.0;
 		constexpr int NB = (VEC == 2) ? 4 : 8;            // independent row reads in flight per thread
 #pragma unroll 1
 		for (int r = 0; r < nrows; r++) {
@@ -940,8 +942,8 @@ __global__ void __launch_bounds__(PAL_COLS, (VEC == 2) ? 3 : 4) k_sweep_down_lea
 			double xn[VEC];
 #pragma unroll
 			for (int v = 0; v < VEC; v++) {
-				xn[v] = a.alpha * (acc[v] + acc2[v]);
-				if (need_x) xn[v] += a.beta * xold[v];
+				xn[v] = c_alpha * (acc[v] + acc2[v]);
+				if (need_x) xn[v] += c_beta * xold[v];
 				contrib += yr[v] * xn[v];
 			}
 			if (VEC == 2) *reinterpret_cast<double2*>(a.x + t) = make_double2(xn[0], xn[VEC - 1]);
