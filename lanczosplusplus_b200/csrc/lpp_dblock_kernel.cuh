@@ -280,6 +280,8 @@ struct DbArgs {
 	const double* y;
 	uint64_t pitch, ncols;
 	double alpha, beta, U0, tmag;
+	const double* alpha_dev;           // optional: alpha / beta in device memory (device-resident Lanczos scalars)
+	const double* beta_dev;
 	const uint32_t* w1;                // up word of every column (32-bit copy)
 	const double* dv1;                 // up potential of every column
 	double* dot_partials;              // optional: per pass-2 tile partial sums of y . x_new  [npanels * nblocks2]
@@ -417,7 +419,9 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 	__shared__ double s_red[DB_NW];
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int q = lane >> 3, c = lane & 7;
-	const DbArgs& a = ka.a;
+	DbArgs a = ka.a;
+	if (a.alpha_dev) a.alpha = *a.alpha_dev;
+	if (a.beta_dev) a.beta = *a.beta_dev;
 	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&s_bar);
 	if (tid < 32) reinterpret_cast<float*>(db_smem)[tid] = 0.0f;                 // slot 0 of the tile is the zero line
 	if (tid == 0) {

@@ -19,6 +19,7 @@
 #include "lpp_tiled.cuh"
 #include "lpp_sweep_common.cuh"
 #include "lpp_dtile.cuh"
+#include "lpp_dblock.cuh"
 
 static thread_local std::string g_terr;
 const char* lpp_tiled_error() { return g_terr.c_str(); }
@@ -90,6 +91,7 @@ struct TiledPlan {
 	double stInternal = 0;
 	DownRowsPlan* drows = nullptr;   // row-walking sweep A (k_sweep_down_rows, lpp_dtile.cu); nullptr: streaming kernel
 	DownTilePlan* dtile = nullptr;   // shared-memory tile kernel for sweep A (lpp_dtile.cu, opt-in); nullptr: streaming kernel
+	DownBlockPlan* dblock = nullptr; // two-pass block sweep A (lpp_dblock.cu): default for HubbardOneBand when every down state is local
 	size_t smemAL = 0, smemBL = 0;
 	size_t smemA3 = 0;
 	// v1 fallback
@@ -1785,6 +1787,15 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		if (rd < 0) { g_terr = std::string("down rows plan: ") + lpp_dtile_error(); delete p; return -1; }
 		if (rd > 0 && getenv("LPP_VERBOSE")) fprintf(stderr, "[lpp tiled] row-walking down kernel not used: %s\n", lpp_dtile_error());
 	}
+	if (mags_ok && p->leanA && !p->dtile && !p->drows && !p->stagedA) {
+		int rb = lpp_dblock_create(m, dn, dt, s, &p->dblock);
+		if (rb < 0) { g_terr = std::string("down block plan: ") + lpp_dblock_error(); delete p; return -1; }
+		if (getenv("LPP_VERBOSE")) {
+			char buf[256] = "";
+			if (p->dblock) lpp_dblock_describe(p->dblock, buf, sizeof(buf));
+			fprintf(stderr, "[lpp tiled] block down sweep: %s\n", p->dblock ? buf : lpp_dblock_error());
+		}
+	}
 	if (getenv("LPP_VERBOSE"))
 		fprintf(stderr, "[lpp tiled] leanA=%d leanB=%d widthL=%d dtile=%d packedB=%d e16=%d mean slots/warp=%.2f\n", p->leanA, p->leanB, p->widthL,
 		        p->dtile ? 1 : 0, p->packedB, p->packedE16, p->packed_mean_slots);
@@ -1840,6 +1851,7 @@ void lpp_tiled_destroy(TiledPlan* p)
 	for (void* q : p->allocs) cudaFree(q);
 	lpp_dtile_destroy(p->dtile);
 	lpp_drows_destroy(p->drows);
+	lpp_dblock_destroy(p->dblock);
 	delete p;
 }
 
@@ -1882,7 +1894,11 @@ int lpp_tiled_spmv(TiledPlan* p, const ModelDev& m, const HopTable& up, const Ho
 	int launches = 0;
 	const int dot_in_b = p->has_twospin ? 0 : 1;
 	const ColView cvfull{m.n1, m.n1, 0};
-	if (p->drows && !p->dtile && p->blocksA == 0 && lpp_drows_accepts(p->drows, cvfull)) {
+	if (p->dblock && p->blocksA == 0 && lpp_dblock_accepts(p->dblock, m, dt, p->d0, p->dcount, cvfull)) {
+		SpmvArgs aa = a;
+		aa.dot_partials = nullptr;
+		if (lpp_dblock_sweep(p->dblock, m, dt, aa, cvfull, s) < 0) { g_terr = lpp_dblock_error(); return -1; }
+	} else if (p->drows && !p->dtile && p->blocksA == 0 && lpp_drows_accepts(p->drows, cvfull)) {
 		SpmvArgs aa = a;
 		aa.dot_partials = nullptr;
 		if (lpp_drows_sweep(p->drows, m, dt, aa, p->d0, p->dcount, cvfull, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
@@ -2034,6 +2050,11 @@ int lpp_tiled_sweep_up_rows(TiledPlan* p, const ModelDev& m, const SpmvArgs& a, 
 int lpp_tiled_down_cols_blocks(const TiledPlan* p, const ModelDev& m, uint64_t ncols)
 {
 	const ColView cvt{ncols, ncols, 0};
+	{
+		DiagTables dtu{};
+		dtu.uniformU = 1;
+		if (p->dblock && lpp_dblock_accepts(p->dblock, m, dtu, 0, m.n2, cvt)) return lpp_dblock_partials(p->dblock, cvt);
+	}
 	if (p->drows && !p->dtile && lpp_drows_accepts(p->drows, cvt)) return lpp_drows_grid(p->drows, cvt);
 	if (p->dtile && lpp_dtile_accepts(p->dtile, cvt)) return lpp_dtile_grid(p->dtile, cvt);
 	if (staged_accepts(p, cvt)) return (int)staged_grid(p, 0, m.n2, cvt);
@@ -2048,6 +2069,10 @@ int lpp_tiled_sweep_down_cols(TiledPlan* p, const ModelDev& m, const HopTable& d
 {
 	const uint32_t nchunks = (uint32_t)((m.n2 + PAL_ROWS - 1) / PAL_ROWS);
 	ColView cv{ncols, ncols, u0};
+	if (p->dblock && lpp_dblock_accepts(p->dblock, m, dt, 0, m.n2, cv)) {
+		if (lpp_dblock_sweep(p->dblock, m, dt, a, cv, s) < 0) { g_terr = lpp_dblock_error(); return -1; }
+		return 2;
+	}
 	if (p->drows && !p->dtile && lpp_drows_accepts(p->drows, cv)) {
 		if (lpp_drows_sweep(p->drows, m, dt, a, 0, m.n2, cv, s) < 0) { g_terr = lpp_dtile_error(); return -1; }
 		return 1;

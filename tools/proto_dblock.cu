@@ -178,6 +178,8 @@ int main(int argc, char** argv)
 	DbArgs a;
 	a.x = dx; a.y = dy; a.pitch = pitch; a.ncols = ncols; a.alpha = alpha; a.beta = beta; a.U0 = U0; a.w1 = dw1; a.dv1 = ddv1; a.tmag = 1.0;
 	a.dot_partials = nullptr;
+	a.alpha_dev = nullptr;
+	a.beta_dev = nullptr;
 	if (db_launch(dp, a, nsm, 0)) { printf("launch failed\n"); return 1; }
 	CK(cudaDeviceSynchronize());
 	// compare
