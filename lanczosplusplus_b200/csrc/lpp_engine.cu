@@ -1056,7 +1056,8 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nrows, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
 		phase_mark(h, 1, S);                                    // 0->1 up sweep
 		CK(cudaStreamWaitEvent(S, h->ev_ycol, 0));
-		if (!pulled) CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
+		// prepacked: the stores were issued before the previous all-reduce, which every rank enters after its fused sweep
+		if (!pulled && !prepacked) CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
 		phase_mark(h, 2, S);                                    // 1->2 wait for the pack (+ all-reduce #1 when it was pushed)
 		SpmvArgs aa;
 		aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
@@ -1170,6 +1171,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	const uint64_t n = h->nloc;
 	double* x = h->vx;
 	double* y = h->vy;
+	h->packed_vec = nullptr;                                 // y was just (re)loaded: no column-shard copy of it exists
 	int np = lpp_vec_blocks(n);
 	lpp_launch_dot(y, y, n, h->partials, h->stream);
 	h->launches += 1;
@@ -1243,8 +1245,14 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 					const uint64_t n1 = h->md.n1, nrows = h->nloc / n1;
 					npb = lpp_unpack_axpy_norm_blocks(nrows, n1, h->desc.nranks);
 					CKR(ensure_partials(h, npb));
-					lpp_launch_unpack_axpy_norm_p2p(x, y, 0.0, h->peer_xcol, nullptr, nrows, n1, h->cols, h->row0 / n1, h->partials, h->stream,
-					                                coefs + LPP_LZ_AXPY);
+					// LPP_FUSE_PACK=1: the fused sweep also stores the new vector into the owners' column shards (the next pack), so the
+					// next up sweep runs without the copy engines beside it and all-reduce #1 disappears.  Measured on 8 x B200: up sweep
+					// 0.272 -> 0.247 ms, pack wait 0.07 -> 0.007 ms, but the sweep itself 0.255 -> 0.48 ms (1.03 ms per iteration against
+					// 0.92 ms); 4 GPUs 1.84 against 1.49 ms; 2 GPUs 3.23 against 2.97 ms.  Off by default.
+					static const bool fuse_pack = getenv("LPP_FUSE_PACK") && getenv("LPP_FUSE_PACK")[0] == '1';
+					lpp_launch_unpack_axpy_norm_p2p(x, y, 0.0, h->peer_xcol, fuse_pack ? &h->peer_ycol : nullptr, nrows, n1, h->cols, h->row0 / n1,
+					                                h->partials, h->stream, coefs + LPP_LZ_AXPY);
+					if (fuse_pack) h->packed_vec = x;               // x is the next Lanczos vector (becomes y after the swap)
 					phase_mark(h, 5, h->stream);
 				} else {
 					lpp_launch_axpy_norm(x, y, 0.0, n, h->partials, h->stream, coefs + LPP_LZ_AXPY);
@@ -1270,6 +1278,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 			}
 		}
 		*nsteps = j;
+		h->packed_vec = nullptr;
 		return 0;
 	}
 	for (; j < steps; j++) {

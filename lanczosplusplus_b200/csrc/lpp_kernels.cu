@@ -828,9 +828,14 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
 // Peer loads are request bound over NVLink: 8-byte loads measured 354 GB/s per GPU on 8 x B200 (0.41 ms for 145 MB), the
 // 16-byte form moves twice the bytes per request; two independent pairs per thread keep more requests in flight.
 // coef is read from `coef_dev` when non-null (device-resident recurrence: no host round trip before this sweep).
+// PACK: the new vector is also stored into the owners' column shards (the pack of the NEXT mat-vec): NVLink carries the loads
+// of this sweep in one direction and the stores in the other at the same time, and the next up sweep runs without the copy
+// engines next to it.
+template <bool PACK>
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                                    const double* __restrict__ coef_dev, PeerPtrs xcols, uint64_t nrows,
-                                                                    uint64_t n1, ColSplit c, uint64_t d0loc, double* __restrict__ partials)
+                                                                    const double* __restrict__ coef_dev, PeerPtrs xcols, PeerPtrs ycols,
+                                                                    uint64_t nrows, uint64_t n1, ColSplit c, uint64_t d0loc,
+                                                                    double* __restrict__ partials)
 {
 	const uint64_t r = blockIdx.x;
 	if (coef_dev) coef = *coef_dev;
@@ -857,11 +862,13 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __r
 		const double2 xa = xrow[p0], ya = yrow[p0];
 		double2 va = make_double2(xa.x + r0.x - coef * ya.x, xa.y + r0.y - coef * ya.y);
 		xrow[p0] = va;
+		if (PACK) *reinterpret_cast<double2*>(ycols.p[q0] + (d0loc + r) * nc0 + (u0 - c.cs[q0])) = va;
 		s += va.x * va.x + va.y * va.y;
 		if (two) {
 			const double2 xb = xrow[p1], yb = yrow[p1];
 			double2 vb = make_double2(xb.x + r1.x - coef * yb.x, xb.y + r1.y - coef * yb.y);
 			xrow[p1] = vb;
+			if (PACK) *reinterpret_cast<double2*>(ycols.p[q1] + (d0loc + r) * nc1 + (u1 - c.cs[q1])) = vb;
 			s += vb.x * vb.x + vb.y * vb.y;
 		}
 	}
@@ -903,8 +910,9 @@ void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, co
 	static const bool v2 = !(getenv("LPP_UNPACK_V2") && getenv("LPP_UNPACK_V2")[0] == '0');
 	bool even = (n1 % 2 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(y) % 16 == 0);
 	for (int q = 0; q <= c.nranks; q++) even = even && (c.cs[q] % 2 == 0);
-	if (ycols_or_null) k_unpack_axpy_norm_p2p<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
-	else if (v2 && even) k_unpack_axpy_norm_p2p_v2<<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, nrows, n1, c, d0loc, partials);
+	if (ycols_or_null && v2 && even) k_unpack_axpy_norm_p2p_v2<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
+	else if (ycols_or_null) k_unpack_axpy_norm_p2p<true><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
+	else if (v2 && even) k_unpack_axpy_norm_p2p_v2<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
 	else k_unpack_axpy_norm_p2p<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
 }
 
