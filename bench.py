@@ -24,7 +24,7 @@ METRIC = "Lanczos s/iteration (16-site Hubbard 4x4, 8 up 8 down, on-the-fly SpMV
 UNIT = "s/iteration"
 BYTES_PER_ROW_SPMV = 24.0    # read y, read x, write x
 BYTES_PER_ROW_ITER = 48.0    # fused Lanczos iteration
-KERNELS = {"c3": "k_sweep_down_lean + k_sweep_up_packed (one launch each)", "c3small": "k_sweep_down_lean + k_sweep_up_packed",
+KERNELS = {"c3": "k_dblock (two-pass block down sweep) + k_sweep_up_packed (one launch each)", "c3small": "k_dblock + k_sweep_up_packed",
            "c4": "k_sweep_down_lean + k_sweep_up_packed + k_sweep_twospin_tab", "c2": "k_spmv_heis (one launch)"}
 
 
@@ -105,8 +105,8 @@ def measured_peak():
 
 def measured_traffic(workload, world):
     """DRAM bytes (read + write) per SpMV from the committed `ncu --set full` capture of the two sweep kernels
-    (profiles/traffic_r01.json, written from profiles/prof_sweeps_r01_final_raw.csv); None when no capture applies."""
-    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    (profiles/traffic_r02.json, written from profiles/prof_sweeps_r02_raw.csv); None when no capture applies."""
+    p = os.path.join(ROOT, "profiles", "traffic_r02.json")
     if workload != "c3" or world != 1 or not os.path.exists(p):
         return None, None
     t = json.load(open(p))
@@ -356,7 +356,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "x += H y = %s, 24 B/row algorithmic, per GPU; duration = CUDA events around the launches "
                                    "on the engine's stream" % KERNELS.get(args.workload, "engine AUTO kernels"),
-                         "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram read+write of both sweeps)"
+                         "traffic_source": "profiles/traffic_r02.json (ncu --set full, dram read+write of both sweeps)"
                                            if traffic else None,
                          "ncu_kernels": traffic_kernels},
             "gpu_launches": int(launches), "clocks": clocks,
