@@ -681,7 +681,7 @@ k_sweep_up_lean(ModelDev m, const uint32_t* __restrict__ tabL, const uint8_t* __
 // load per lane.  NG = groups a state can have: 8 (32 slots) or, with 2-byte entries, 12 (48 slots: FeAs with orbital hoppings).
 template <int R, bool UNI, bool E16, int NG, int N4>
 __device__ __forceinline__ void up_packed_gather(const typename std::conditional<E16, uint2, uint4>::type (&ec)[NG], const MagTable& mt,
-                                                 uint32_t ys_s, double (&acc)[R])
+                                                 uint32_t ys_s, uint32_t hole_off, double (&acc)[R])
 {
 #pragma unroll
 	for (int g = 0; g < N4; g++) {
@@ -708,7 +708,16 @@ __device__ __forceinline__ void up_packed_gather(const typename std::conditional
 			}
 			const uint32_t addr = ys_s + off[i];
 			if (R == 2) {
-				double vx, vy;
+				// Predicating the padding / hole entries off (a quarter-warp without an operand in a slot then costs no shared-memory
+				// wavefront: 24.0 executed slots against 20.9 needed per quarter-warp) was measured and is NOT faster: x += H y
+				// 3.593 ms against 3.568 ms, the extra compare and zero moves cost what the 13 % fewer wavefronts save.
+				// LPP_UP_SKIP_HOLES (compile time) keeps the variant.
+				double vx = 0.0, vy = 0.0;
+#ifdef LPP_UP_SKIP_HOLES
+				if (off[i] < hole_off)
+#else
+				(void)hole_off;
+#endif
 				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(addr));
 				acc[0] = fma(amp, vx, acc[0]);
 				acc[1] = fma(amp, vy, acc[1]);
@@ -788,6 +797,7 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 	__syncthreads();
 
 	const double t0 = mt.mag[0];
+	const uint32_t hole_off = bsize * (uint32_t)(8 * R);     // byte offset of the zero slots = first offset that is no operand
 	double contrib = 0.0;
 	for (; i < bsize; i += UPP_THREADS) {
 		VT ec[NG];
@@ -806,12 +816,12 @@ k_sweep_up_packed(ModelDev m, const void* __restrict__ tabP, const uint32_t* __r
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = 0.0;
 		switch (cnt >> 2) {                                // warp-uniform: branch-free runs of 4*N independent gathers
-#define LPP_UPP_CASE(N_) case N_: up_packed_gather<R, UNI, E16, NG, (N_ <= NG ? N_ : NG)>(ec, mt, ys_s, acc); break;
+#define LPP_UPP_CASE(N_) case N_: up_packed_gather<R, UNI, E16, NG, (N_ <= NG ? N_ : NG)>(ec, mt, ys_s, hole_off, acc); break;
 		case 0: break;
 			LPP_UPP_CASE(1) LPP_UPP_CASE(2) LPP_UPP_CASE(3) LPP_UPP_CASE(4) LPP_UPP_CASE(5) LPP_UPP_CASE(6) LPP_UPP_CASE(7)
 			LPP_UPP_CASE(8) LPP_UPP_CASE(9) LPP_UPP_CASE(10) LPP_UPP_CASE(11)
 #undef LPP_UPP_CASE
-		default: up_packed_gather<R, UNI, E16, NG, NG>(ec, mt, ys_s, acc); break;
+		default: up_packed_gather<R, UNI, E16, NG, NG>(ec, mt, ys_s, hole_off, acc); break;
 		}
 #pragma unroll
 		for (int r = 0; r < R; r++) {
