@@ -708,3 +708,30 @@ def test_multi_gpu_matches_single(lpp):
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL OK" in r.stdout
+
+
+def test_block_down_sweep_cases(lpp, oracle, monkeypatch):
+    """The two-pass block down sweep (k_dblock, default for HubbardOneBand with one U) against the oracle on cases that exercise
+    its corners: site potentials (the per-state dv2 path), a column count that is not a multiple of 16 (last panel partly
+    empty), odd block sizes, an open chain (different F1 / F2 choice), and the streaming sweep (LPP_DBLOCK=0) as a second
+    opinion on the same inputs."""
+    V12 = np.linspace(-0.4, 0.6, 12)
+    todo = (cases.hubbard_square(4, 3, 6, 6), cases.hubbard_chain(12, 6, 5, periodic=True, V=V12),
+            cases.hubbard_chain(12, 5, 6, V=V12), cases.hubbard_chain(14, 3, 7), cases.hubbard_square(4, 3, 5, 7))
+    for case in todo:
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        n = o.rows()
+        y = geo.splitmix64_vector(n, 42)
+        x0 = geo.splitmix64_vector(n, 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        for off in ("1", "0"):
+            monkeypatch.setenv("LPP_DBLOCK", off)
+            e = cases.make_engine(lpp, case)
+            x = x0.copy()
+            e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+            assert relerr(x, xref) <= 1e-13, (case["nsite"], case["nup"], case["ndown"], off)
+            a, b, _ = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=12, eps=0.0)).decomposition(y)
+            a0, b0 = o.decomposition(y, steps=12, eps=0.0)
+            assert relerr(a, a0) <= 1e-10 and relerr(b[:-1], b0[:-1]) <= 1e-10
+            e.close()
