@@ -138,6 +138,46 @@ public:
 		return result;
 	}
 
+	// Engine.h:341-389 with bra = ket = ground state: <gs| O_n ... O_1 |gs>, O_k = what[k] at (sites[k], spins[k], orbs[k]), what[0]
+	// applied first; 0 when the string leaves the allowed particle numbers or does not come back to the ground state's sector
+	double manyPoint(const std::vector<int>& sites, const std::vector<int>& what, const std::vector<int>& spins, const std::vector<int>& orbs) const
+	{
+		const int n = (int)sites.size();
+		std::vector<lpp_handle*> chain(1, h_), own;
+		std::vector<std::pair<int, int> > parts(1, std::make_pair((int)desc_.nup, (int)desc_.ndown));
+		int nup = desc_.nup, ndn = desc_.ndown;
+		const bool heis = desc_.model == LPP_MODEL_HEISENBERG;
+		const int nmax = desc_.nsite * (desc_.model == LPP_MODEL_FEAS ? desc_.orbitals : 1);
+		double r = 0;
+		int rc = 0;
+		bool zero = false;
+		for (int k = 0; k < n && !zero && rc == 0; k++) {
+			const int op = what[k], spin = spins[k];
+			if (op == LPP_OP_C || op == LPP_OP_CDAGGER) { const int d = (op == LPP_OP_C) ? -1 : 1; if (spin == 0) nup += d; else ndn += d; }
+			else if (op == LPP_OP_SPLUS) { nup += 1; if (!heis) ndn -= 1; }
+			else if (op == LPP_OP_SMINUS) { nup -= 1; if (!heis) ndn += 1; }
+			if (nup < 0 || ndn < 0 || nup > nmax || ndn > nmax) { zero = true; break; }
+			if (nup == parts.back().first && ndn == parts.back().second) chain.push_back(chain.back());
+			else if (k == n - 1 && nup == (int)desc_.nup && ndn == (int)desc_.ndown) chain.push_back(h_);
+			else {
+				lpp_desc d = desc_;
+				d.nup = nup;
+				d.ndown = ndn;
+				lpp_handle* s = nullptr;
+				rc = lpp_create(&d, &s);
+				if (rc == 0) { own.push_back(s); chain.push_back(s); }
+			}
+			parts.push_back(std::make_pair(nup, ndn));
+		}
+		if (!zero && rc == 0 && nup == (int)desc_.nup && ndn == (int)desc_.ndown) {
+			std::vector<int32_t> o(what.begin(), what.end()), s(sites.begin(), sites.end()), sp(spins.begin(), spins.end()), ob(orbs.begin(), orbs.end());
+			rc = lpp_many_point(chain.data(), n, o.data(), s.data(), sp.data(), ob.data(), &r);
+		}
+		for (lpp_handle* q : own) lpp_destroy(q);
+		check(rc);
+		return r;
+	}
+
 	// Engine.h:208-249 with bra = ket = ground state: <gs| op_0[site_0]; ...; op_{n-1}[site_{n-1}] |gs>, ModelBase::rahulMethod
 	// semantics; labels 0 identity, 1 n, 2 sz, 3 c (cdagger when transpose), dof 0 up / 1 down, site = bit position
 	struct MeasureOp { int label, dof, site, transpose; };

@@ -164,6 +164,12 @@ int lpp_two_point(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t spin, in
  * 1 down; sites are bit positions in the one-spin word (site*orbitals + orb).  The operators must conserve the sector. */
 int lpp_measure(lpp_handle* h, int32_t nops, const int32_t* labels, const int32_t* dofs, const int32_t* transposes,
                 const int32_t* sites, double* result);
+/* Engine::manyPoint (Engine.h:341-389), bra = ket = ground state of chain[0]: tmp_0 = |gs>, tmp_k = O_k tmp_{k-1} with
+ * O_k = ops[k-1] at (sites[k-1], spins[k-1], orbs[k-1]) applied like lpp_apply_op (accModifiedState_, isign = 1); chain[k] is a handle on
+ * the sector the k-th operator leads to (the basis Engine::getNeededBasis creates, Engine.h:391-413; chain[k] may equal chain[k-1] for
+ * sz / n); chain[nops] must be on the ground state's sector (it may be chain[0]).  result = <gs | tmp_nops>. */
+int lpp_many_point(lpp_handle* const* chain, int32_t nops, const int32_t* ops, const int32_t* sites, const int32_t* spins,
+                   const int32_t* orbs, double* result);
 /* copy the handle's ground-state / modified vector to the host (parity tests) */
 int lpp_get_vector(lpp_handle* h, int32_t which /*0 = ground state, 1 = modified*/, double* out_host);
 int lpp_set_groundstate(lpp_handle* h, const double* z_host);

@@ -1179,6 +1179,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	CKR(reduce_scalar(h, np, &nrm2));
 	if (init_norm2) *init_norm2 = nrm2;
 	if (!(nrm2 > 0)) return fail(LPP_ERR_ARG, "initial Lanczos vector has zero norm");
+	if (steps < 1) return fail(LPP_ERR_ARG, "the number of Lanczos steps must be at least 1");
 	double nj = sqrt(nrm2), nprev = 1.0, bprev = 0.0, eold = 100.0;
 	if ((uint64_t)steps > h->rows) steps = (int)h->rows;
 	// <prefix>Options=reortho: every Lanczos vector is kept on the device (un-normalised U_k with its squared norm) and the new
@@ -1186,7 +1187,8 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	struct SavedVectors {
 		std::vector<double*> v;
 		std::vector<double> n2;
-		~SavedVectors() { for (double* q : v) cudaFree(q); }
+		std::vector<double*> slabs;       // the vectors are carved out of slabs of 8: one cudaMalloc (an implicit device sync) per 8 steps
+		~SavedVectors() { for (double* q : slabs) cudaFree(q); }
 	} saved;
 	const bool reortho = p->reortho != 0;
 	const int npro = lpp_vec_blocks(n * 2);
@@ -1284,11 +1286,16 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	for (; j < steps; j++) {
 		if (tm && j == tm->from) { CK(cudaEventRecord(h->ev0, h->stream)); tm->launches_at_from = h->launches; }
 		if (reortho) {
-			double* keep = nullptr;
-			if (cudaMalloc((void**)&keep, sizeof(double) * std::max<uint64_t>(n, 1)) != cudaSuccess) {
-				cudaGetLastError();
-				return fail(LPP_ERR_CUDA, "reortho: out of device memory for the saved Lanczos vectors (steps x rows x 8 bytes)");
+			const uint64_t stride = (std::max<uint64_t>(n, 1) + 31) & ~(uint64_t)31;
+			if (saved.v.size() % 8 == 0) {
+				double* slab = nullptr;
+				if (cudaMalloc((void**)&slab, sizeof(double) * stride * 8) != cudaSuccess) {
+					cudaGetLastError();
+					return fail(LPP_ERR_CUDA, "reortho: out of device memory for the saved Lanczos vectors (steps x rows x 8 bytes)");
+				}
+				saved.slabs.push_back(slab);
 			}
+			double* keep = saved.slabs.back() + (saved.v.size() % 8) * stride;
 			saved.v.push_back(keep);
 			saved.n2.push_back(nj * nj);
 			CK(cudaMemcpyAsync(keep, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
@@ -1464,8 +1471,9 @@ extern "C" int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const
 }
 
 // ------------------------------------------------------------------ operator application / vectors
-extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb,
-                            double factor, int32_t accumulate)
+// dst.modified (+)= factor * O |srcvec>, srcvec = a vector on src's sector (local rows)
+static int apply_op_vec(lpp_handle* src, const double* srcvec_local, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb,
+                        double factor, int32_t accumulate)
 {
 	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
 	const int model = src->md.model;
@@ -1477,7 +1485,7 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	if (model == LPP_MODEL_HUBBARD) { if (!fermion && !spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "unsupported operator"); }
 	else if (model == LPP_MODEL_HEISENBERG) { if (!spinop && op != LPP_OP_N) return fail(LPP_ERR_ARG, "Heisenberg: sz, splus, sminus, n"); }
 	else if (!fermion && op != LPP_OP_SPLUS && op != LPP_OP_SMINUS) return fail(LPP_ERR_ARG, "FeAsBasedSc / Tj1Orbital: c, cdagger, splus, sminus");
-	if (!src->gs) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
+	if (!srcvec_local) return fail(LPP_ERR_STATE, "source handle holds no ground-state vector");
 	if (src->desc.nranks != dst->desc.nranks || src->desc.rank != dst->desc.rank || src->device != dst->device)
 		return fail(LPP_ERR_ARG, "source and destination must share device and sharding");
 	if (src->desc.nranks > 1 && (spin != 0 || op == LPP_OP_SPLUS || op == LPP_OP_SMINUS || model == LPP_MODEL_HEISENBERG))
@@ -1498,11 +1506,60 @@ extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_
 	if (!accumulate) CK(cudaMemsetAsync(dst->modified, 0, sizeof(double) * dst->nloc, dst->stream));
 	CK(cudaStreamSynchronize(src->stream));
 	// source vector is indexed globally inside the kernel: shift the local pointer by the shard's first row
-	const double* srcv = src->gs - src->row0;
+	const double* srcv = srcvec_local - src->row0;
 	lpp_launch_apply_op(src->md, dst->md, op, site, spin, orb, factor, srcv, dst->modified, dst->row0, dst->nloc, dst->stream);
 	dst->launches += 1;
 	CK(cudaStreamSynchronize(dst->stream));
 	CK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int lpp_apply_op(lpp_handle* src, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb,
+                            double factor, int32_t accumulate)
+{
+	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
+	return apply_op_vec(src, src->gs, dst, op, site, spin, orb, factor, accumulate);
+}
+
+// Engine::manyPoint (Engine.h:341-389) with bra = ket = ground state: the operators are applied one after the other,
+// tmp_0 = |gs>, tmp_k = O_k tmp_{k-1} on the sector hasNewParts gives (chain[k], created by the caller like Engine's getNeededBasis),
+// result = <gs | tmp_n> when the last sector is the first one again.  Nothing leaves the device.
+extern "C" int lpp_many_point(lpp_handle* const* chain, int32_t nops, const int32_t* ops, const int32_t* sites, const int32_t* spins,
+                              const int32_t* orbs, double* result)
+{
+	if (!chain || nops < 1 || !ops || !sites || !spins || !orbs || !result) return fail(LPP_ERR_ARG, "bad argument");
+	for (int k = 0; k <= nops; k++)
+		if (!chain[k]) return fail(LPP_ERR_ARG, "null handle in the sector chain");
+	lpp_handle* h0 = chain[0];
+	lpp_handle* hn = chain[nops];
+	if (!h0->gs) return fail(LPP_ERR_STATE, "the first handle holds no ground-state vector");
+	if (hn->md.nup != h0->md.nup || hn->md.ndn != h0->md.ndn || hn->rows != h0->rows)
+		return fail(LPP_ERR_ARG, "the operator string does not return to the sector of the ground state");
+	const double* cur = h0->gs;
+	double* tmp = nullptr;                                           // copy of the source when an operator maps a handle onto itself
+	for (int k = 1; k <= nops; k++) {
+		lpp_handle* src = chain[k - 1];
+		lpp_handle* dst = chain[k];
+		CK(cudaSetDevice(dst->device));
+		if (dst->modified && cur == dst->modified) {
+			if (!tmp) { if (cudaMalloc((void**)&tmp, sizeof(double) * std::max<uint64_t>(dst->nloc, 1)) != cudaSuccess) return fail(LPP_ERR_CUDA, "out of device memory"); }
+			CK(cudaMemcpyAsync(tmp, cur, sizeof(double) * dst->nloc, cudaMemcpyDeviceToDevice, dst->stream));
+			CK(cudaStreamSynchronize(dst->stream));
+			cur = tmp;
+		}
+		const int rc = apply_op_vec(src, cur, dst, ops[k - 1], sites[k - 1], spins[k - 1], orbs[k - 1], 1.0, 0);
+		if (rc != 0) { cudaFree(tmp); return rc; }
+		cur = dst->modified;
+	}
+	CK(cudaSetDevice(h0->device));
+	CKR(ensure_partials(h0, lpp_vec_blocks(h0->nloc)));
+	lpp_launch_dot(h0->gs, cur, h0->nloc, h0->partials, h0->stream);
+	h0->launches += 1;
+	double v = 0;
+	const int rc = reduce_scalar(h0, lpp_vec_blocks(h0->nloc), &v);
+	cudaFree(tmp);
+	if (rc != 0) return rc;
+	*result = v;
 	return 0;
 }
 

@@ -773,8 +773,8 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add(double* __restrict__ x, 
 // column shard, the unpack kernel loads the column results from the owning rank -- transfer and re-layout are one kernel,
 // no staging buffers and no library collective on the data path.
 // one block row per matrix row (blockIdx.x; no integer division), each thread walks columns with stride blockDim * gridDim.y
-__global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restrict__ src, PeerPtrs ycols, uint64_t nrows,
-                                                          uint64_t n1, ColSplit c, uint64_t d0loc)
+__global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restrict__ src, const __grid_constant__ PeerPtrs ycols, uint64_t nrows,
+                                                          uint64_t n1, const __grid_constant__ ColSplit c, uint64_t d0loc)
 {
 	const uint64_t r = blockIdx.x;
 	const double* __restrict__ srow = src + r * n1;
@@ -785,8 +785,8 @@ __global__ void __launch_bounds__(LPP_TPB) k_pack_cols_p2p(const double* __restr
 	}
 }
 
-__global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__ x, PeerPtrs xcols, uint64_t nrows, uint64_t n1,
-                                                           ColSplit c, uint64_t d0loc)
+__global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__ x, const __grid_constant__ PeerPtrs xcols, uint64_t nrows, uint64_t n1,
+                                                           const __grid_constant__ ColSplit c, uint64_t d0loc)
 {
 	const uint64_t r = blockIdx.x;
 	double* __restrict__ xrow = x + r * n1;
@@ -803,8 +803,9 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_add_p2p(double* __restrict__
 // (A variant with one owner per block and 16-byte accesses measured 0.84-0.93 ms against 0.70 ms for this one on 2 x B200.)
 template <bool PACK>
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                                 const double* __restrict__ coef_dev, PeerPtrs xcols, PeerPtrs ycols,
-                                                                 uint64_t nrows, uint64_t n1, ColSplit c, uint64_t d0loc,
+                                                                 const double* __restrict__ coef_dev, const __grid_constant__ PeerPtrs xcols,
+                                                                 const __grid_constant__ PeerPtrs ycols, uint64_t nrows, uint64_t n1,
+                                                                 const __grid_constant__ ColSplit c, uint64_t d0loc,
                                                                  double* __restrict__ partials)
 {
 	if (coef_dev) coef = *coef_dev;
@@ -833,8 +834,9 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p(double* __rest
 // engines next to it.
 template <bool PACK>
 __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __restrict__ x, const double* __restrict__ y, double coef,
-                                                                    const double* __restrict__ coef_dev, PeerPtrs xcols, PeerPtrs ycols,
-                                                                    uint64_t nrows, uint64_t n1, ColSplit c, uint64_t d0loc,
+                                                                    const double* __restrict__ coef_dev, const __grid_constant__ PeerPtrs xcols,
+                                                                    const __grid_constant__ PeerPtrs ycols, uint64_t nrows, uint64_t n1,
+                                                                    const __grid_constant__ ColSplit c, uint64_t d0loc,
                                                                     double* __restrict__ partials)
 {
 	const uint64_t r = blockIdx.x;

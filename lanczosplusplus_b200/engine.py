@@ -348,6 +348,50 @@ class Engine:
             dst.close()
         return out
 
+    def manyPoint(self, sites, what, spins, orbs=None):
+        """Engine.h:341-389 with bra = ket = ground state: <gs| O_n ... O_2 O_1 |gs>, O_k = what[k] at (sites[k], spins[k], orbs[k]),
+        applied in the order given (what[0] first).  Every operator leads to the sector hasNewParts names (getNeededBasis,
+        Engine.h:391-413); a string that leaves the allowed particle numbers or does not return to the ground state's sector gives 0
+        like the reference.  The chain of modified vectors stays on the device (lpp_many_point)."""
+        n = len(sites)
+        orbs = [0] * n if orbs is None else list(orbs)
+        chain, own = [self.mat], []
+        nup, ndn = self.mat.nup, self.mat.ndown
+        heis = self.mat.model == HEISENBERG
+        nmax = self.mat.nsite * self.mat.orbitals
+        try:
+            for k in range(n):
+                op, spin = what[k], spins[k]
+                if op in (OP_C, OP_CDAGGER):
+                    d = -1 if op == OP_C else 1
+                    nup, ndn = (nup + d, ndn) if spin == 0 else (nup, ndn + d)
+                elif op == OP_SPLUS:
+                    nup, ndn = nup + 1, (ndn if heis else ndn - 1)
+                elif op == OP_SMINUS:
+                    nup, ndn = nup - 1, (ndn if heis else ndn + 1)
+                if min(nup, ndn) < 0 or max(nup, ndn) > nmax:
+                    return 0.0
+                last = k == n - 1
+                if (nup, ndn) == (chain[-1].nup, chain[-1].ndown):
+                    chain.append(chain[-1])                      # sz, n: same sector, same handle
+                elif last and (nup, ndn) == (self.mat.nup, self.mat.ndown):
+                    chain.append(self.mat)
+                else:
+                    s = self.mat.sector(nup, ndn)
+                    own.append(s)
+                    chain.append(s)
+            if (nup, ndn) != (self.mat.nup, self.mat.ndown):
+                return 0.0
+            arr = (C.c_void_p * (n + 1))(*[c.h for c in chain])
+            i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)   # noqa: E731
+            o, si, sp, ob = i32(what), i32(sites), i32(spins), i32(orbs)
+            out = C.c_double()
+            check(_lib.lib().lpp_many_point(arr, n, o.ctypes.data, si.ctypes.data, sp.ctypes.data, ob.ctypes.data, C.byref(out)))
+            return out.value
+        finally:
+            for s in own:
+                s.close()
+
     def spectralFunction(self, op, isite, jsite, spin=0, orbs=(0, 0)):
         """Engine.h:133-206: list of (type, ContinuedFraction).  Fermionic c/cdagger for HubbardOneBand, FeAsBasedSc (orbital
         pair) and Tj1Orbital; sz / splus / sminus for HubbardOneBand and Heisenberg (S(q, omega) building blocks)."""

@@ -735,3 +735,43 @@ def test_block_down_sweep_cases(lpp, oracle, monkeypatch):
             a0, b0 = o.decomposition(y, steps=12, eps=0.0)
             assert relerr(a, a0) <= 1e-10 and relerr(b[:-1], b0[:-1]) <= 1e-10
             e.close()
+
+
+def test_many_point_matches_oracle_chain(lpp, oracle):
+    """Engine::manyPoint (Engine.h:341-389): <gs| O_n ... O_1 |gs> through the chain of sectors, on the device, against the
+    oracle's accModifiedState_ restatement applied step by step (same ground-state vector on both sides); also against
+    twoPoint for the two-operator string and against the reference's answer 0 for strings that do not return."""
+    case = cases.hubbard_chain(6, 3, 3, periodic=True, V=[0.3, -0.2, 0.1, 0.0, 0.5, -0.4])
+    o = cases.make_oracle(oracle, case)
+    init = geo.splitmix64_vector(o.rows(), 1234)
+    e0, z0, _, _ = o.ground_state(init, 300, 1e-13, 4)
+    eng = cases.make_engine(lpp, case)
+    en = lpp.Engine(eng, {"LanczosSteps": 300, "LanczosEps": 1e-13}, init=init)
+    eng.set_groundstate(z0)
+    OPS = {lpp.OP_C: oracle.OP_C, lpp.OP_CDAGGER: oracle.OP_CDAGGER, lpp.OP_N: oracle.OP_N, lpp.OP_SZ: oracle.OP_SZ}
+
+    def chain_oracle(sites, what, spins):
+        cur, vec, nu, nd = o, z0, 3, 3
+        for s, w, sp in zip(sites, what, spins):
+            if w in (lpp.OP_C, lpp.OP_CDAGGER):
+                d = -1 if w == lpp.OP_C else 1
+                nu, nd = (nu + d, nd) if sp == 0 else (nu, nd + d)
+            nxt = cases.make_oracle(oracle, dict(case, nup=nu, ndown=nd))
+            out = np.zeros(nxt.rows())
+            cur.apply_op(nxt, OPS[w], s, sp, 1.0, vec, out)
+            cur, vec = nxt, out
+        return float(z0 @ vec) if (nu, nd) == (3, 3) else 0.0
+
+    strings = [([1, 4], [lpp.OP_C, lpp.OP_CDAGGER], [0, 0]),
+               ([2, 2], [lpp.OP_C, lpp.OP_CDAGGER], [1, 1]),
+               ([0, 3, 5, 2], [lpp.OP_C, lpp.OP_C, lpp.OP_CDAGGER, lpp.OP_CDAGGER], [0, 1, 1, 0]),
+               ([1, 1, 4], [lpp.OP_N, lpp.OP_C, lpp.OP_CDAGGER], [0, 0, 0]),
+               ([3, 2], [lpp.OP_N, lpp.OP_N], [0, 1]),
+               ([1, 4], [lpp.OP_C, lpp.OP_C], [0, 0])]          # does not return to the sector: 0
+    for sites, what, spins in strings:
+        got = en.manyPoint(sites, what, spins)
+        ref = chain_oracle(sites, what, spins)
+        assert abs(got - ref) <= 1e-12 * max(1.0, abs(ref)), (sites, what, spins, got, ref)
+    tp = en.twoPoint(lpp.OP_C, spin=0)                         # result(i, j) = <c_j gs | c_i gs> = <gs| cdagger_j c_i |gs>
+    assert abs(en.manyPoint([1, 4], [lpp.OP_C, lpp.OP_CDAGGER], [0, 0]) - tp[1, 4]) <= 1e-12
+    eng.close()
