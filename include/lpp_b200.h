@@ -199,6 +199,9 @@ int lpp_comm_share(lpp_handle* h, const lpp_handle* parent);
 int lpp_p2p_export(lpp_handle* h, int32_t kernel, uint8_t handles[128]);
 int lpp_p2p_import(lpp_handle* h, const uint8_t* all_handles);
 
+/* test hook: all-reduce (sum) of n <= 4 doubles over the handle's ranks through the scalar path of the sharded Krylov loop */
+int lpp_allreduce_selftest(lpp_handle* h, double* inout, int32_t n);
+
 /* contiguous near-equal split of n items over nranks (the row-sharding rule used for the slow index) */
 int lpp_shard_range(uint64_t n, int32_t rank, int32_t nranks, uint64_t* first, uint64_t* count);
 

@@ -129,6 +129,7 @@ SYMBOLS = {
     "lpp_measure": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
     "lpp_two_point": (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _VP]),
     "lpp_many_point": (C.c_int, [_VP, C.c_int32, _VP, _VP, _VP, _VP, _VP]),
+    "lpp_allreduce_selftest": (C.c_int, [_VP, _VP, C.c_int32]),
     "lpp_row_words": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
     "lpp_rank_pairs": (C.c_int, [_VP, _VP, _VP, C.c_uint64, _VP]),
     "lpp_matvec_host": (C.c_int, [_VP, C.c_int32, _VP, _VP]),

@@ -156,6 +156,11 @@ struct lpp_handle {
 	PeerPtrs peer_vx{}, peer_vy{};  // peers' Lanczos work vectors (same slab): the pack PULLS the columns it owns from them
 	double* slab = nullptr;       // one allocation [ycol | xcol | vx | vy]: one CUDA IPC handle covers all four
 	uint64_t slab_off_xcol = 0, slab_off_vx = 0, slab_off_vy = 0;   // offsets in doubles; vx/vy = 0: not in the slab
+	uint64_t slab_off_psx = 0;    // scalar exchange area (lpp_launch_psx_allreduce)
+	PeerPtrs peer_psx{};
+	bool psx = false;             // scalar all-reduces of the peer-memory path go over NVLink stores + flags instead of NCCL
+	unsigned long long psx_seq = 0;
+	int* psx_err = nullptr;
 	std::vector<void*> ipc_opened;
 	cudaStream_t comm_stream = nullptr;
 	cudaEvent_t ev_pack = nullptr, ev_ycol = nullptr, ev_xcol = nullptr, ev_recv = nullptr, ev_scal = nullptr;
@@ -251,6 +256,7 @@ extern "C" int lpp_destroy(lpp_handle* h)
 	for (void* p : h->allocs) cudaFree(p);
 	if (h->scal_host) cudaFreeHost(h->scal_host);
 	if (h->lz_ab_host) cudaFreeHost(h->lz_ab_host);
+	if (h->psx_err) cudaFreeHost(h->psx_err);
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);
 	for (cudaEvent_t e : {h->ev_pack, h->ev_ycol, h->ev_xcol, h->ev_recv, h->ev_scal}) if (e) cudaEventDestroy(e);
@@ -831,6 +837,9 @@ extern "C" int lpp_cf_eval(int32_t n, const double* a, const double* b, double e
 static int ensure_tiled(lpp_handle* h);
 static int ensure_two_layout(lpp_handle* h, int kernel);
 
+// sum of `n` doubles at `vals` (device) over the ranks, result in place: peer-memory exchange when the handle has it, else NCCL
+static int allreduce_small(lpp_handle* h, double* vals, int n, cudaStream_t s);
+
 static int ensure_vectors(lpp_handle* h, int kernel)
 {
 	if (!h->vx) CKR(dev_alloc(h, &h->vx, h->nloc));
@@ -925,7 +934,9 @@ static int ensure_two_layout(lpp_handle* h, int kernel)
 		const uint64_t ncol = up32(n2 * h->ncols);
 		const bool own_vecs = !h->vx && !h->vy;
 		const uint64_t nv = own_vecs ? up32(h->nloc) : 0;
-		CKR(dev_alloc(h, &h->slab, 2 * ncol + 2 * nv));
+		CKR(dev_alloc(h, &h->slab, 2 * ncol + 2 * nv + LPP_PSX_DOUBLES));
+		h->slab_off_psx = 2 * ncol + 2 * nv;
+		CK(cudaMemset(h->slab + h->slab_off_psx, 0, sizeof(double) * LPP_PSX_DOUBLES));
 		h->ycol = h->slab;
 		h->xcol = h->slab + ncol;
 		h->slab_off_xcol = ncol;
@@ -1057,7 +1068,7 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		phase_mark(h, 1, S);                                    // 0->1 up sweep
 		CK(cudaStreamWaitEvent(S, h->ev_ycol, 0));
 		// prepacked: the stores were issued before the previous all-reduce, which every rank enters after its fused sweep
-		if (!pulled && !prepacked) CKN(g_nccl.AllReduce(h->scal_dev + 4, h->scal_dev + 4, 1, kNcclFloat64, kNcclSum, h->comm, S));
+		if (!pulled && !prepacked) CKR(allreduce_small(h, h->scal_dev + 4, 0, S));
 		phase_mark(h, 2, S);                                    // 1->2 wait for the pack (+ all-reduce #1 when it was pushed)
 		SpmvArgs aa;
 		aa.alpha = alpha; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
@@ -1070,7 +1081,7 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 			lpp_launch_finalize_sum(h->partials, nbB, h->scal_dev, S);
 			lpp_launch_finalize_sum(h->partials2, h->partials2_cap, h->scal_dev + 1, S);
 		}
-		CKN(g_nccl.AllReduce(h->scal_dev, h->scal_dev, 2, kNcclFloat64, kNcclSum, h->comm, S));
+		CKR(allreduce_small(h, h->scal_dev, 2, S));
 		phase_mark(h, 4, S);                                    // 3->4 finalize + all-reduce #2
 		if (want_dot && !coefs_dev) CK(cudaMemcpyAsync(h->scal_host, h->scal_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, S));
 		// defer_unpack: the caller folds the re-layout of the column-shard result into its next pass over x
@@ -1140,6 +1151,17 @@ static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, 
 		*dot_out = h->scal_host[0] + h->scal_host[1];
 	}
 	CK(cudaGetLastError());
+	return 0;
+}
+
+static int allreduce_small(lpp_handle* h, double* vals, int n, cudaStream_t s)
+{
+	if (h->psx && h->p2p && n <= 4) {
+		lpp_launch_psx_allreduce(vals, n, h->peer_psx, h->desc.rank, h->desc.nranks, ++h->psx_seq, h->psx_err, s);
+		h->launches += 1;
+		return 0;
+	}
+	CKN(g_nccl.AllReduce(vals, vals, std::max(n, 1), kNcclFloat64, kNcclSum, h->comm, s));
 	return 0;
 }
 
@@ -1223,7 +1245,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 		auto reduce_dev = [&](int npartials, double* out_dev) -> int {
 			lpp_launch_finalize_sum(h->partials, npartials, out_dev, h->stream);
 			h->launches += 1;
-			if (h->desc.nranks > 1) CKN(g_nccl.AllReduce(out_dev, out_dev, 1, kNcclFloat64, kNcclSum, h->comm, h->stream));
+			if (h->desc.nranks > 1) CKR(allreduce_small(h, out_dev, 1, h->stream));
 			return 0;
 		};
 		bool stop = false;
@@ -1269,6 +1291,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 			CK(cudaMemcpyAsync(h->lz_ab_host + j0, a_dev + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, h->stream));
 			CK(cudaMemcpyAsync(h->lz_ab_host + h->lz_ab_cap + j0, b_dev + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, h->stream));
 			CK(cudaStreamSynchronize(h->stream));
+			if (h->psx_err && *h->psx_err) return fail(LPP_ERR_STATE, "peer-memory scalar exchange timed out (a rank did not arrive)");
 			for (j = j0; j < j1; j++) {
 				a[j] = h->lz_ab_host[j];
 				b[j] = h->lz_ab_host[h->lz_ab_cap + j];
@@ -1709,7 +1732,7 @@ extern "C" int lpp_p2p_export(lpp_handle* h, int32_t kernel, uint8_t handles[128
 	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
 	memset(handles, 0, 128);
 	memcpy(handles, &a, 64);
-	const uint64_t hdr[4] = {0x3142414c5350504cull /* "LPPSLAB1" */, h->slab_off_xcol, h->slab_off_vx, h->slab_off_vy};
+	const uint64_t hdr[5] = {0x3142414c5350504cull /* "LPPSLAB1" */, h->slab_off_xcol, h->slab_off_vx, h->slab_off_vy, h->slab_off_psx};
 	memcpy(handles + 64, hdr, sizeof(hdr));
 	return 0;
 }
@@ -1726,10 +1749,11 @@ extern "C" int lpp_p2p_import(lpp_handle* h, const uint8_t* all_handles)
 			h->peer_xcol.p[q] = h->xcol;
 			h->peer_vx.p[q] = h->vx;
 			h->peer_vy.p[q] = h->vy;
+			h->peer_psx.p[q] = h->slab + h->slab_off_psx;
 			continue;
 		}
 		cudaIpcMemHandle_t a;
-		uint64_t hdr[4];
+		uint64_t hdr[5];
 		memcpy(&a, all_handles + (size_t)q * 128, 64);
 		memcpy(hdr, all_handles + (size_t)q * 128 + 64, sizeof(hdr));
 		if (hdr[0] != 0x3142414c5350504cull) return fail(LPP_ERR_ARG, "peer handle block has the wrong format");
@@ -1741,12 +1765,52 @@ extern "C" int lpp_p2p_import(lpp_handle* h, const uint8_t* all_handles)
 		h->peer_xcol.p[q] = base + hdr[1];
 		h->peer_vx.p[q] = hdr[2] ? base + hdr[2] : nullptr;
 		h->peer_vy.p[q] = hdr[3] ? base + hdr[3] : nullptr;
+		h->peer_psx.p[q] = base + hdr[4];
 		pull = pull && hdr[2] && hdr[3];
 	}
 	h->p2p = 1;
+	// scalar all-reduces over peer memory (default; LPP_PSX=0 keeps NCCL for them)
+	h->psx = !(getenv("LPP_PSX") && getenv("LPP_PSX")[0] == '0');
+	h->psx_seq = 0;
+	if (h->psx && !h->psx_err) {
+		// pinned, device-visible: the exchange kernel raises it when a peer did not show up within ~2 s
+		CK(cudaHostAlloc((void**)&h->psx_err, sizeof(int), cudaHostAllocMapped));
+		*h->psx_err = 0;
+	}
 	// opt-in: on 8 x B200 the copy engines PULL 145 MB per rank in 0.42 ms against 0.29 ms for the push form, and without the
 	// all-reduce the ranks drift apart (1.44 ms per iteration against 1.15 ms); on 2 GPUs the two forms are equal
 	h->pull_pack = pull && (getenv("LPP_PULL_PACK") && getenv("LPP_PULL_PACK")[0] == '1');
+	return 0;
+}
+
+// diagnostic / test hook: all-reduce (sum) of n <= 4 host doubles over the ranks of a handle through the path the sharded Krylov loop
+// uses for its scalars (peer-memory exchange when the handle has it, NCCL otherwise)
+extern "C" int lpp_allreduce_selftest(lpp_handle* h, double* inout, int32_t n)
+{
+	if (!h || !inout || n < 0 || n > 4) return fail(LPP_ERR_ARG, "bad argument");
+	if (h->desc.nranks > 1 && !h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
+	CK(cudaSetDevice(h->device));
+	// eight all-reduces of the same input back to back (no host synchronisation in between, like the Krylov loop), interleaved
+	// with empty ones (the barrier form); every result must be the same
+	double in[4] = {0, 0, 0, 0}, out[8][4];
+	for (int i = 0; i < n; i++) in[i] = inout[i];
+	double* dev = nullptr;
+	CKR(dev_alloc(h, &dev, 8 * 4));
+	for (int r = 0; r < 8; r++) {
+		CK(cudaMemcpyAsync(dev + 4 * r, in, sizeof(double) * 4, cudaMemcpyHostToDevice, h->stream));
+		if (h->desc.nranks > 1) {
+			CKR(allreduce_small(h, dev + 4 * r, n, h->stream));
+			if (r % 3 == 1) CKR(allreduce_small(h, h->scal_dev + 4, 0, h->stream));
+		}
+	}
+	CK(cudaMemcpyAsync(&out[0][0], dev, sizeof(double) * 32, cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	dev_free(h, dev);
+	for (int r = 1; r < 8; r++)
+		for (int i = 0; i < n; i++)
+			if (out[r][i] != out[0][i]) return fail(LPP_ERR_STATE, "back-to-back all-reduces disagree");
+	for (int i = 0; i < n; i++) inout[i] = out[0][i];
+	if (h->psx_err && *h->psx_err) return fail(LPP_ERR_STATE, "peer-memory scalar exchange timed out (a rank did not arrive)");
 	return 0;
 }
 

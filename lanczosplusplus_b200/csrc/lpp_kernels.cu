@@ -2,6 +2,7 @@
 // generic / table-driven on-the-fly x = beta x + alpha H y (K3, K4), stored CRS build + SpMV (K5), the fused Lanczos
 // vector sweeps (K6, K7, K8) and operator application (K9).  The shared-memory tiled fast path is in lpp_tiled.cu.
 #include <cub/cub.cuh>
+#include <cstdio>
 #include <cstdlib>
 #include "lpp_kernels.cuh"
 
@@ -876,6 +877,44 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __r
 	}
 	s = lpp_block_sum(s);
 	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
+}
+
+__global__ void __launch_bounds__(32) k_psx_allreduce(double* __restrict__ vals, int nvals, const __grid_constant__ PeerPtrs areas, int me,
+                                                      int nranks, unsigned long long seq, int* __restrict__ err)
+{
+	__shared__ double sv[LPP_MAX_RANKS][4];
+	const int q = threadIdx.x;
+	const unsigned par = (unsigned)(seq & 1ull);
+	if (q < nranks) {
+		volatile double* dst = areas.p[q] + ((size_t)par * LPP_MAX_RANKS + me) * LPP_PSX_SLOT_DOUBLES;
+		for (int i = 0; i < nvals; i++) dst[i] = vals[i];
+		__threadfence_system();
+		*reinterpret_cast<volatile unsigned long long*>(dst + 4) = seq;
+		volatile double* src = areas.p[me] + ((size_t)par * LPP_MAX_RANKS + q) * LPP_PSX_SLOT_DOUBLES;
+		const long long t0 = clock64();
+		bool ok = true;
+		while (*reinterpret_cast<volatile unsigned long long*>(src + 4) != seq) {
+			if (clock64() - t0 > (1ll << 32)) { ok = false; break; }
+		}
+		__threadfence_system();
+		if (!ok) {
+			*err = 1;
+			printf("[lpp psx] rank %d timed out waiting for rank %d: want seq %llu, slot holds %llu (nvals %d)\n", me, q, seq,
+			       *reinterpret_cast<volatile unsigned long long*>(src + 4), nvals);
+		}
+		for (int i = 0; i < nvals; i++) sv[q][i] = src[i];
+	}
+	__syncthreads();
+	if (threadIdx.x < nvals) {
+		double s = 0.0;
+		for (int r = 0; r < nranks; r++) s += sv[r][threadIdx.x];
+		vals[threadIdx.x] = s;
+	}
+}
+void lpp_launch_psx_allreduce(double* vals, int nvals, const PeerPtrs& areas, int me, int nranks, unsigned long long seq, int* err,
+                              cudaStream_t s)
+{
+	k_psx_allreduce<<<1, 32, 0, s>>>(vals, nvals, areas, me, nranks, seq, err);
 }
 
 static dim3 lpp_rowwise_grid(uint64_t nrows, uint64_t n1)

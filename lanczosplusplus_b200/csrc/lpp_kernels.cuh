@@ -136,5 +136,13 @@ void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint
 void lpp_launch_unpack_add(double* x, const double* recvbuf, const double* xcol, uint64_t nrows, uint64_t n1, const ColSplit& c,
                            uint64_t d0loc, cudaStream_t s);
 
+// All-reduce (sum) of up to 4 doubles over peer memory (NVLink): every rank stores its values into a slot of every peer's exchange
+// area and a sequence number behind a system-scope fence, waits for the G slots of its own area, and adds them in rank order
+// (identical result on every rank).  Slots alternate with the parity of `seq`.  A rank that waits longer than ~2 s sets *err.
+#define LPP_PSX_SLOT_DOUBLES 8          // 4 values, sequence number, padding: 64 bytes
+#define LPP_PSX_DOUBLES (2 * LPP_MAX_RANKS * LPP_PSX_SLOT_DOUBLES)
+void lpp_launch_psx_allreduce(double* vals, int nvals, const PeerPtrs& areas, int me, int nranks, unsigned long long seq, int* err,
+                              cudaStream_t s);
+
 // tiled two-sweep kernels (lpp_tiled.cu)
 struct TiledPlan;
