@@ -1202,6 +1202,10 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	if (init_norm2) *init_norm2 = nrm2;
 	if (!(nrm2 > 0)) return fail(LPP_ERR_ARG, "initial Lanczos vector has zero norm");
 	if (steps < 1) return fail(LPP_ERR_ARG, "the number of Lanczos steps must be at least 1");
+	// the sharding of a handle is decided once (by the kernel of the first call / of lpp_p2p_export); a two-layout handle only runs
+	// the tiled sweeps, so asking it for another kernel later is an error rather than a silent switch
+	if (h->two_layout == 1 && resolve_kernel(h, p->kernel) != LPP_KERNEL_TILED)
+		return fail(LPP_ERR_ARG, "this sharded handle is laid out for the tiled kernel (two-layout exchange); create another handle for a different kernel");
 	double nj = sqrt(nrm2), nprev = 1.0, bprev = 0.0, eold = 100.0;
 	if ((uint64_t)steps > h->rows) steps = (int)h->rows;
 	// <prefix>Options=reortho: every Lanczos vector is kept on the device (un-normalised U_k with its squared norm) and the new
