@@ -703,7 +703,8 @@ def test_multi_gpu_matches_single(lpp):
     if ng < 2:
         pytest.skip("needs at least 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(ng, 8)), "--master-addr", "127.0.0.1",
+    # two ranks here (every exchange path is exercised); `torchrun --nproc-per-node 8 tools/check_multi_gpu.py` is the 8-rank form
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29731", os.path.join(root, "tools", "check_multi_gpu.py")]
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
