@@ -2,6 +2,7 @@
 // dispatch, the device-resident Krylov loops (PsimagLite::LanczosSolver role) and the C-ABI of include/lpp_b200.h.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -13,6 +14,15 @@
 #include "lpp_kernels.cuh"
 #include "lpp_tiled.cuh"
 #include "lpp_setup.h"
+
+// NVTX ranges around the host phases ("lpp:spmv", "lpp:lanczos", ...): no cost without a tool attached; under ncu they select
+// kernels by phase (ncu --nvtx --nvtx-include "lpp:spmv/")
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -194,6 +204,18 @@ static void dev_free(lpp_handle* h, void* p)
 	if (it != h->allocs.end()) h->allocs.erase(it);
 	cudaFree(p);
 }
+
+// call-scoped device buffer: freed on every way out of the entry point, the CK() error returns included
+template <class T>
+struct ScopedDev {
+	T* p = nullptr;
+	ScopedDev() = default;
+	ScopedDev(const ScopedDev&) = delete;
+	ScopedDev& operator=(const ScopedDev&) = delete;
+	~ScopedDev() { if (p) cudaFree(p); }
+	cudaError_t alloc(size_t count) { return cudaMalloc((void**)&p, sizeof(T) * std::max<size_t>(count, 1)); }
+	operator T*() const { return p; }
+};
 
 extern "C" int lpp_device_check(int32_t device)
 {
@@ -457,14 +479,13 @@ extern "C" int lpp_rank(const lpp_handle* hc, int32_t spin, const uint64_t* word
 	lpp_handle* h = const_cast<lpp_handle*>(hc);
 	if (!h || !words || !index) return fail(LPP_ERR_ARG, "null argument");
 	CK(cudaSetDevice(h->device));
-	word_t* dw; uint64_t* di;
-	CK(cudaMalloc((void**)&dw, sizeof(word_t) * std::max<uint64_t>(n, 1)));
-	CK(cudaMalloc((void**)&di, sizeof(uint64_t) * std::max<uint64_t>(n, 1)));
+	ScopedDev<word_t> dw; ScopedDev<uint64_t> di;
+	CK(dw.alloc(n));
+	CK(di.alloc(n));
 	CK(cudaMemcpy(dw, words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
 	lpp_launch_rank(h->md, spin, dw, n, di, h->stream);
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaMemcpy(index, di, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
-	cudaFree(dw); cudaFree(di);
 	return 0;
 }
 
@@ -474,14 +495,13 @@ extern "C" int lpp_row_words(const lpp_handle* hc, uint64_t first, uint64_t coun
 	if (!h) return fail(LPP_ERR_ARG, "null argument");
 	if (first > h->rows || count > h->rows - first) return fail(LPP_ERR_ARG, "row range outside the basis");
 	CK(cudaSetDevice(h->device));
-	word_t* du = nullptr; word_t* dd = nullptr;
-	if (up_words) CK(cudaMalloc((void**)&du, sizeof(word_t) * std::max<uint64_t>(count, 1)));
-	if (down_words) CK(cudaMalloc((void**)&dd, sizeof(word_t) * std::max<uint64_t>(count, 1)));
+	ScopedDev<word_t> du, dd;
+	if (up_words) CK(du.alloc(count));
+	if (down_words) CK(dd.alloc(count));
 	lpp_launch_row_words(h->md, first, count, du, dd, h->stream);
 	CK(cudaStreamSynchronize(h->stream));
 	if (du) CK(cudaMemcpy(up_words, du, sizeof(word_t) * count, cudaMemcpyDeviceToHost));
 	if (dd) CK(cudaMemcpy(down_words, dd, sizeof(word_t) * count, cudaMemcpyDeviceToHost));
-	cudaFree(du); cudaFree(dd);
 	return 0;
 }
 
@@ -490,16 +510,15 @@ extern "C" int lpp_rank_pairs(const lpp_handle* hc, const uint64_t* up_words, co
 	lpp_handle* h = const_cast<lpp_handle*>(hc);
 	if (!h || !up_words || !down_words || !index) return fail(LPP_ERR_ARG, "null argument");
 	CK(cudaSetDevice(h->device));
-	word_t* du; word_t* dd; uint64_t* di;
-	CK(cudaMalloc((void**)&du, sizeof(word_t) * std::max<uint64_t>(n, 1)));
-	CK(cudaMalloc((void**)&dd, sizeof(word_t) * std::max<uint64_t>(n, 1)));
-	CK(cudaMalloc((void**)&di, sizeof(uint64_t) * std::max<uint64_t>(n, 1)));
+	ScopedDev<word_t> du, dd; ScopedDev<uint64_t> di;
+	CK(du.alloc(n));
+	CK(dd.alloc(n));
+	CK(di.alloc(n));
 	CK(cudaMemcpy(du, up_words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(dd, down_words, sizeof(word_t) * n, cudaMemcpyHostToDevice));
 	lpp_launch_rank_pairs(h->md, du, dd, n, di, h->stream);
 	CK(cudaStreamSynchronize(h->stream));
 	CK(cudaMemcpy(index, di, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
-	cudaFree(du); cudaFree(dd); cudaFree(di);
 	return 0;
 }
 
@@ -609,6 +628,7 @@ static int ensure_tiled(lpp_handle* h)
 static int do_spmv(lpp_handle* h, int kernel, double alpha, double beta, double* x, const double* y, bool want_dot,
                    int* npartials, const double* coefs_dev = nullptr)
 {
+	NvtxRange nvtx("lpp:spmv");
 	kernel = resolve_kernel(h, kernel);
 	SpmvArgs a;
 	a.alpha = alpha; a.beta = beta; a.x = x; a.y = y; a.row0 = h->row0; a.nloc = h->nloc;
@@ -679,9 +699,9 @@ extern "C" int lpp_matvec_host(lpp_handle* h, int32_t kernel, double* x, const d
 	if (!h || !x || !y) return fail(LPP_ERR_ARG, "null argument");
 	if (h->desc.nranks != 1) return fail(LPP_ERR_STATE, "lpp_matvec_host needs the whole Hilbert space on one GPU");
 	CK(cudaSetDevice(h->device));
-	double* dx; double* dy;
-	CK(cudaMalloc((void**)&dx, sizeof(double) * h->rows));
-	CK(cudaMalloc((void**)&dy, sizeof(double) * h->rows));
+	ScopedDev<double> dx, dy;
+	CK(dx.alloc(h->rows));
+	CK(dy.alloc(h->rows));
 	CK(cudaMemcpyAsync(dx, x, sizeof(double) * h->rows, cudaMemcpyHostToDevice, h->stream));
 	CK(cudaMemcpyAsync(dy, y, sizeof(double) * h->rows, cudaMemcpyHostToDevice, h->stream));
 	int rc = do_spmv(h, kernel, 1.0, 1.0, dx, dy, false, nullptr);
@@ -689,8 +709,9 @@ extern "C" int lpp_matvec_host(lpp_handle* h, int32_t kernel, double* x, const d
 		cudaError_t e = cudaMemcpyAsync(x, dx, sizeof(double) * h->rows, cudaMemcpyDeviceToHost, h->stream);
 		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
 		if (e != cudaSuccess) rc = fail(LPP_ERR_CUDA, std::string("matvec_host: ") + cudaGetErrorString(e));
+	} else {
+		cudaStreamSynchronize(h->stream);      // nothing of this call is left in flight when the buffers go
 	}
-	cudaFree(dx); cudaFree(dy);
 	return rc;
 }
 
@@ -990,6 +1011,7 @@ static void phase_collect(lpp_handle* h, int last)
 static int spmv_two_layout(lpp_handle* h, double alpha, double beta, double* x, const double* y, bool want_dot, double* dot_out,
                            bool defer_unpack = false, const double* coefs_dev = nullptr)
 {
+	NvtxRange nvtx("lpp:spmv two-layout");
 	if (!h->comm) return fail(LPP_ERR_STATE, "nranks>1 but lpp_comm_init has not been called");
 	cudaStream_t S = h->stream, C = h->comm_stream;
 	const int G = h->desc.nranks, me = h->desc.rank;
@@ -1190,6 +1212,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
                         const double* zcoef, double* z, double* a, double* b, int* nsteps, double* init_norm2,
                         LoopTiming* tm)
 {
+	NvtxRange nvtx("lpp:lanczos");
 	const uint64_t n = h->nloc;
 	double* x = h->vx;
 	double* y = h->vy;
@@ -1502,6 +1525,7 @@ extern "C" int lpp_states_below(lpp_handle* h, const lpp_solver_params* p, const
 static int apply_op_vec(lpp_handle* src, const double* srcvec_local, lpp_handle* dst, int32_t op, int32_t site, int32_t spin, int32_t orb,
                         double factor, int32_t accumulate)
 {
+	NvtxRange nvtx("lpp:apply_op");
 	if (!src || !dst) return fail(LPP_ERR_ARG, "null argument");
 	const int model = src->md.model;
 	if (model != dst->md.model) return fail(LPP_ERR_ARG, "source and destination models differ");
@@ -1563,19 +1587,19 @@ extern "C" int lpp_many_point(lpp_handle* const* chain, int32_t nops, const int3
 	if (hn->md.nup != h0->md.nup || hn->md.ndn != h0->md.ndn || hn->rows != h0->rows)
 		return fail(LPP_ERR_ARG, "the operator string does not return to the sector of the ground state");
 	const double* cur = h0->gs;
-	double* tmp = nullptr;                                           // copy of the source when an operator maps a handle onto itself
+	ScopedDev<double> tmp;                                           // copy of the source when an operator maps a handle onto itself
 	for (int k = 1; k <= nops; k++) {
 		lpp_handle* src = chain[k - 1];
 		lpp_handle* dst = chain[k];
 		CK(cudaSetDevice(dst->device));
 		if (dst->modified && cur == dst->modified) {
-			if (!tmp) { if (cudaMalloc((void**)&tmp, sizeof(double) * std::max<uint64_t>(dst->nloc, 1)) != cudaSuccess) return fail(LPP_ERR_CUDA, "out of device memory"); }
+			if (!tmp && tmp.alloc(dst->nloc) != cudaSuccess) { cudaGetLastError(); return fail(LPP_ERR_CUDA, "many_point: out of device memory"); }
 			CK(cudaMemcpyAsync(tmp, cur, sizeof(double) * dst->nloc, cudaMemcpyDeviceToDevice, dst->stream));
 			CK(cudaStreamSynchronize(dst->stream));
 			cur = tmp;
 		}
 		const int rc = apply_op_vec(src, cur, dst, ops[k - 1], sites[k - 1], spins[k - 1], orbs[k - 1], 1.0, 0);
-		if (rc != 0) { cudaFree(tmp); return rc; }
+		if (rc != 0) return rc;
 		cur = dst->modified;
 	}
 	CK(cudaSetDevice(h0->device));
@@ -1584,7 +1608,6 @@ extern "C" int lpp_many_point(lpp_handle* const* chain, int32_t nops, const int3
 	h0->launches += 1;
 	double v = 0;
 	const int rc = reduce_scalar(h0, lpp_vec_blocks(h0->nloc), &v);
-	cudaFree(tmp);
 	if (rc != 0) return rc;
 	*result = v;
 	return 0;
