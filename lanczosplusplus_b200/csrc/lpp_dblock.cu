@@ -1,4 +1,4 @@
-// lpp_dblock.cu -- engine side of the two-pass block down sweep (kernel, plan builder and launcher: lpp_dblock_kernel.cuh).
+// lpp_dblock.cu -- engine side of the multi-pass block down sweep (kernel, plan builder and launcher: lpp_dblock_kernel.cuh).
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -40,19 +40,22 @@ int lpp_dblock_create(const ModelDev& m, const HopTable& dn, const DiagTables& d
 		g_dberr = "table download failed";
 		return -1;
 	}
-	int dev = 0, maxsm = 0, nsm = 0;
+	int dev = 0, maxblk = 0, maxsm = 0, nsm = 0;
 	cudaGetDevice(&dev);
-	cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	cudaDeviceGetAttribute(&maxblk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+	cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	DownBlockPlan* p = new DownBlockPlan();
 	std::string err;
-	if (!db_build_host_plan(w2.data(), n2, m.nbits, hidx.data(), hval.data(), hcnt.data(), W, dv2.data(), (size_t)maxsm - 1024, &p->host, &err)) {
+	const char* lay = getenv("LPP_DBLOCK_LAYOUT");                  // 1: one CTA of 1024 threads per SM only (A/B timing)
+	if (!db_build_host_plan(w2.data(), n2, m.nbits, hidx.data(), hval.data(), hcnt.data(), W, dv2.data(), (size_t)maxblk, (size_t)maxsm,
+	                        lay ? atoi(lay) : 0, &p->host, &err)) {
 		g_dberr = err;
 		delete p;
 		return 1;
 	}
-	// small bases gain nothing: a tile must be worth a CTA of 1024 threads
-	if (std::max(p->host.pass[0].max_pos, p->host.pass[1].max_pos) < 64) { g_dberr = "blocks too small"; delete p; return 1; }
+	// small bases gain nothing: a tile must be worth a CTA
+	if (p->host.max_pos < 64) { g_dberr = "blocks too small"; delete p; return 1; }
 	if (!db_upload_plan(p->host, &p->dev, &err)) { g_dberr = err; db_free_plan(&p->dev); delete p; return -1; }
 	std::vector<uint32_t> w32(m.n1);
 	for (uint64_t i = 0; i < m.n1; i++) w32[i] = (uint32_t)w1[i];
@@ -90,7 +93,7 @@ int lpp_dblock_accepts(const DownBlockPlan* p, const ModelDev& m, const DiagTabl
 
 int lpp_dblock_partials(const DownBlockPlan* p, const ColView& cv)
 {
-	return (int)(((cv.ncols + DB_COLS - 1) / DB_COLS) * p->dev.pass[1].nblocks);
+	return (int)(((cv.ncols + DB_COLS - 1) / DB_COLS) * p->dev.pass[p->dev.npass - 1].nblocks);
 }
 
 int lpp_dblock_sweep(DownBlockPlan* p, const ModelDev& m, const DiagTables& dt, const SpmvArgs& a, const ColView& cv, cudaStream_t s)
@@ -117,7 +120,9 @@ int lpp_dblock_sweep(DownBlockPlan* p, const ModelDev& m, const DiagTables& dt, 
 
 void lpp_dblock_describe(const DownBlockPlan* p, char* buf, size_t n)
 {
-	snprintf(buf, n, "F1 %#x F2 %#x, %u + %u blocks, max %u states, %.2f + %.2f hops per state, %zu bytes of shared memory, lag %d",
-	         p->host.f1, p->host.f2, p->dev.pass[0].nblocks, p->dev.pass[1].nblocks, std::max(p->host.pass[0].max_pos, p->host.pass[1].max_pos),
-	         p->host.pass[0].mean_hops, p->host.pass[1].mean_hops, p->host.smem_bytes, p->dev.lag);
+	const DbHostPlan& h = p->host;
+	int o = snprintf(buf, n, "%d passes, %d CTA(s) of %d threads per SM, max %u states, %zu bytes of shared memory, lag %d:", h.npass, h.ctas_per_sm,
+	                 h.threads, h.max_pos, h.smem_bytes + (size_t)h.max_pos * 8, p->dev.lag);
+	for (int k = 0; k < h.npass && o > 0 && (size_t)o < n; k++)
+		o += snprintf(buf + o, n - (size_t)o, " F%d %#x (%u blocks, %.2f hops per state)", k + 1, h.fmask[k], p->dev.pass[k].nblocks, h.pass[k].mean_hops);
 }

@@ -1,16 +1,19 @@
-// lpp_dblock_kernel.cuh -- two-pass BLOCK sweep over one spin species of a product basis (HubbardHelper.h:119-133,191-243:
+// lpp_dblock_kernel.cuh -- multi-pass BLOCK sweep over one spin species of a product basis (HubbardHelper.h:119-133,191-243:
 // the spin-down hopping terms and the diagonal of x += H y):   x = beta x + alpha (D + 1 (x) T_dn) y.
 //
-// Pick two disjoint sets of sites F1, F2 with no hopping amplitude between them.  Pass 1 groups the down states by their
-// occupation of F1: every hop that does not touch F1 stays inside its group ("block").  Pass 2 groups them by F2 and applies
-// the hops that touch F1; none of those touches F2, so they stay inside the F2 blocks.  A tile = (block, 16 columns of the
-// Ndn x Nup matrix) of y is staged in shared memory; each hop operand is a conflict-free 16-byte shared-memory load (the 8
-// lanes of a state read one 128-byte line).  No operand lies outside the tile: the global traffic is y once and x read + write
-// per pass.  A persistent grid takes tiles from a ticket counter in panel-major order, pass 2 of a panel LAG panels behind
-// pass 1, so a panel's x and y stay L2 resident between its two passes (DRAM sees 24 bytes per element).
+// Pick K sets of sites F_1 .. F_K such that every bond misses at least one of them.  Pass k groups the down states by their
+// occupation of F_k ("blocks") and applies the hops that touch F_1 .. F_{k-1} but not F_k: such a hop cannot leave its block.
+// Two sets do when no bond joins them; three pairwise disjoint sets always do (a bond has two ends).  A tile = (block, 16
+// columns of the Ndn x Nup matrix) of y is staged in shared memory; each hop operand is a conflict-free 16-byte shared-memory
+// load (the 8 lanes of a state read one 128-byte line).  No operand lies outside the tile: the global traffic is y once and x
+// read + write per pass.  A persistent grid takes tiles from a ticket counter in panel-major order, pass k of a panel LAG
+// panels behind pass k-1, so a panel's x and y stay L2 resident between its passes (DRAM sees 24 bytes per element).
 //
-// This header holds the host-side plan builder, the kernel and the launcher; it is included by lpp_dblock.cu (engine) and by
-// tools/proto_dblock.cu (stand-alone timing harness).
+// The plan prefers blocks small enough for TWO resident CTAs (512 threads each) per SM, so that one CTA's tile fill and
+// barriers hide behind the other's gathers; when only the one-CTA layout fits, the CTA has 1024 threads.
+//
+// This header holds the host-side plan builder, the kernel and the launcher; it is included by lpp_dblock.cu (engine), by
+// tools/proto_dblock.cu (stand-alone timing harness) and by tests/dblock_plan_check.cu (CPU walk of the tables).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -20,7 +23,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 
-#define DB_THREADS 1024
+#define DB_MAX_PASS 3
 #define DB_COLS 16
 #define DB_LINE 128u                   // bytes of one state's 16 columns
 #define DB_ROW_NONE 0xffffffffu
@@ -43,10 +46,13 @@ struct DbHostPass {
 };
 
 struct DbHostPlan {
-	uint32_t f1 = 0, f2 = 0;
-	DbHostPass pass[2];
-	size_t smem_bytes = 0;
+	int npass = 0;
+	uint32_t fmask[DB_MAX_PASS] = {0, 0, 0};
+	DbHostPass pass[DB_MAX_PASS];
+	size_t smem_bytes = 0;             // tile + largest table blob (the two row lists come on top: max_pos * 8)
 	uint32_t tile_bytes = 0;           // (max_pos + 1) * 128: slot 0 is the zero line
+	uint32_t max_pos = 0;
+	int ctas_per_sm = 1, threads = 1024;
 	double tmag = 1.0;                 // the one hop magnitude (entries carry signs only)
 };
 
@@ -55,8 +61,9 @@ struct DbHostPlan {
 // ---------------------------------------------------------------------------------------------------------------
 template <class W>
 static bool db_build_pass(const W* words, uint64_t n, const uint32_t* idx, const double* val, const uint32_t* cnt, const double* dv2,
-                          uint64_t fmask_group, uint64_t f1mask, int which, DbHostPass* out, std::string* err)
+                          const uint64_t* masks, int npass, int which, DbHostPass* out, std::string* err)
 {
+	const uint64_t fmask_group = masks[which];
 	// group states by their occupation of the fixed sites
 	std::vector<std::pair<uint64_t, uint32_t>> key(n);
 	for (uint64_t s = 0; s < n; s++) key[s] = {(uint64_t)words[s] & fmask_group, (uint32_t)s};
@@ -77,8 +84,10 @@ static bool db_build_pass(const W* words, uint64_t n, const uint32_t* idx, const
 				const double v = val[(uint64_t)k * n + s];
 				if (v == 0.0) continue;
 				const uint64_t diff = (uint64_t)words[s] ^ (uint64_t)words[t];
-				const bool touches_f1 = (diff & f1mask) != 0;
-				if ((which == 0) == touches_f1) continue;
+				int owner = 0;                                       // the first pass whose fixed sites the hop does not touch
+				while (owner < npass && (diff & masks[owner]) != 0) owner++;
+				if (owner == npass) { *err = "a hop touches every set of fixed sites"; return false; }
+				if (owner != which) continue;
 				if (((uint64_t)words[t] & fmask_group) != key[b0].first) { *err = "a hop leaves its block"; return false; }
 				hl[i].push_back({t, v});
 			}
@@ -167,11 +176,63 @@ static bool db_build_pass(const W* words, uint64_t n, const uint32_t* idx, const
 	return true;
 }
 
+// largest group of states with equal occupation of the sites in F
+template <class W>
+static uint32_t db_max_block(const W* words, uint64_t n, uint64_t F)
+{
+	std::vector<uint64_t> keys(n);
+	for (uint64_t s = 0; s < n; s++) keys[s] = (uint64_t)words[s] & F;
+	std::sort(keys.begin(), keys.end());
+	uint32_t run = 0, mx = 0;
+	for (uint64_t s = 0; s < n; s++) {
+		run = (s && keys[s] == keys[s - 1]) ? run + 1 : 1;
+		mx = std::max(mx, run);
+	}
+	return mx;
+}
+
+// site sets for `npass` passes with f fixed sites each.  F_1 takes the highest sites (its blocks are then runs of rows).
+// Two passes: F_2 = the highest f sites that no bond joins to F_1 (tried over all F_1 in descending order).
+// Three passes: the next f sites and the f after them (fewer if the lattice runs out): pairwise disjoint is all it takes.
+static bool db_pick_sets(int nbits, const std::vector<uint64_t>& adj, int npass, int f, uint64_t* masks)
+{
+	const uint64_t all = (nbits == 64) ? ~0ull : ((1ull << nbits) - 1);
+	if (npass == 3) {
+		if (2 * f >= nbits) return false;
+		const int f3 = std::min(f, nbits - 2 * f);
+		masks[0] = (((1ull << f) - 1) << (nbits - f)) & all;
+		masks[1] = (((1ull << f) - 1) << (nbits - 2 * f)) & all;
+		masks[2] = (((1ull << f3) - 1) << (nbits - 2 * f - f3)) & all;
+		return true;
+	}
+	std::vector<int> c(f);
+	for (int i = 0; i < f; i++) c[i] = nbits - 1 - i;          // f-subsets in descending order of their mask
+	for (;;) {
+		uint64_t F1 = 0, nb = 0;
+		for (int i = 0; i < f; i++) { F1 |= 1ull << c[i]; nb |= adj[c[i]]; }
+		uint64_t a = all & ~(F1 | nb);
+		if (__builtin_popcountll(a) >= f) {
+			uint64_t F2 = 0;
+			for (int i = 0; i < f; i++) { const int b = 63 - __builtin_clzll(a); F2 |= 1ull << b; a &= ~(1ull << b); }
+			masks[0] = F1;
+			masks[1] = F2;
+			return true;
+		}
+		int i = f - 1;
+		while (i >= 0 && c[i] == f - 1 - i) i--;
+		if (i < 0) return false;
+		c[i]--;
+		for (int j = i + 1; j < f; j++) c[j] = c[j - 1] - 1;
+	}
+}
+
 // words: one-spin basis (any order), nbits sites; ELL hop table (column-major idx/val, cnt) on the host.
-// Returns false (with *err) when the two-pass block scheme does not apply (then the caller keeps the streaming sweep).
+// smem_block = the opt-in shared-memory limit of one CTA, smem_sm = shared memory of one SM.  layout: 0 = best (two CTAs per
+// SM when some plan fits, else one), 1 = one CTA per SM only (the round-2 first version; kept for A/B timing).
+// Returns false (with *err) when the block scheme does not apply (then the caller keeps the streaming sweep).
 template <class W>
 static bool db_build_host_plan(const W* words, uint64_t n, int nbits, const uint32_t* idx, const double* val, const uint32_t* cnt, int width,
-                               const double* dv2, size_t max_smem, DbHostPlan* hp, std::string* err)
+                               const double* dv2, size_t smem_block, size_t smem_sm, int layout, DbHostPlan* hp, std::string* err)
 {
 	(void)width;
 	if (n == 0 || n >= (1ull << 24)) { *err = "basis size out of range"; return false; }
@@ -193,63 +254,44 @@ static bool db_build_host_plan(const W* words, uint64_t n, int nbits, const uint
 		}
 	if (mag == 0) { *err = "no hops"; return false; }
 	hp->tmag = mag;
-	const uint64_t all = (nbits == 64) ? ~0ull : ((1ull << nbits) - 1);
-	// smallest number of fixed sites whose largest block fits; F1 = highest sites possible (its blocks are then runs of rows)
-	for (int f = 1; f <= nbits / 2; f++) {
-		// enumerate f-subsets in descending order of their mask
-		std::vector<int> c(f);
-		for (int i = 0; i < f; i++) c[i] = nbits - 1 - i;      // descending positions
-		bool more = true;
-		while (more) {
-			uint64_t F1 = 0, nb = 0;
-			for (int i = 0; i < f; i++) { F1 |= 1ull << c[i]; nb |= adj[c[i]]; }
-			const uint64_t allowed = all & ~(F1 | nb);
-			if (__builtin_popcountll(allowed) >= f) {
-				uint64_t F2 = 0, a = allowed;
-				for (int i = 0; i < f; i++) { const int b = 63 - __builtin_clzll(a); F2 |= 1ull << b; a &= ~(1ull << b); }
-				// block sizes
+	const size_t fixed = 2048;                                       // static shared memory of the kernel + the 1 KB the system keeps per CTA
+	for (int cps = (layout == 1 ? 1 : 2); cps >= 1; cps--) {
+		const size_t per_cta = std::min(smem_block, smem_sm / (size_t)cps);
+		if (per_cta <= fixed + 4096) continue;
+		const size_t budget = per_cta - fixed;
+		for (int npass = 2; npass <= DB_MAX_PASS; npass++)
+			// the smallest number of fixed sites whose largest block fits
+			for (int f = 1; f <= nbits / 2; f++) {
+				uint64_t masks[DB_MAX_PASS] = {0, 0, 0};
+				if (!db_pick_sets(nbits, adj, npass, f, masks)) continue;
 				uint32_t mx = 0;
-				for (int p = 0; p < 2 && mx != 0xffffffffu; p++) {
-					const uint64_t F = p ? F2 : F1;
-					std::vector<uint64_t> keys(n);
-					for (uint64_t s = 0; s < n; s++) keys[s] = (uint64_t)words[s] & F;
-					std::sort(keys.begin(), keys.end());
-					uint32_t run = 0;
-					for (uint64_t s = 0; s < n; s++) {
-						run = (s && keys[s] == keys[s - 1]) ? run + 1 : 1;
-						mx = std::max(mx, run);
-					}
-				}
+				for (int k = 0; k < npass; k++) mx = std::max(mx, db_max_block(words, n, masks[k]));
 				const size_t tile = ((size_t)((mx + 3) & ~3u) + 1) * DB_LINE;
-				if (tile + 16 * 1024 <= max_smem) {           // room for the tables is checked exactly below
-					DbHostPlan cand;
-					cand.f1 = (uint32_t)F1;
-					cand.f2 = (uint32_t)F2;
-					cand.tmag = mag;
-					std::string e2;
-					if (db_build_pass(words, n, idx, val, cnt, dv2, F1, F1, 0, &cand.pass[0], &e2) &&
-					    db_build_pass(words, n, idx, val, cnt, dv2, F2, F1, 1, &cand.pass[1], &e2)) {
-						const uint32_t mp = std::max(cand.pass[0].max_pos, cand.pass[1].max_pos);
-						const uint32_t mb = std::max(cand.pass[0].max_blob, cand.pass[1].max_blob);
-						cand.tile_bytes = (mp + 1) * DB_LINE;
-						cand.smem_bytes = (size_t)cand.tile_bytes + (size_t)mb * 16;
-						if (cand.smem_bytes + (size_t)mp * 8 + 512 <= max_smem) { *hp = std::move(cand); return true; }
-					}
+				if (tile + 4096 > budget) continue;                  // room for the tables is checked exactly below
+				DbHostPlan cand;
+				cand.npass = npass;
+				cand.tmag = mag;
+				cand.ctas_per_sm = cps;
+				cand.threads = cps == 2 ? 512 : 1024;
+				std::string e2;
+				bool ok = true;
+				uint32_t mp = 0, mb = 0;
+				for (int k = 0; k < npass && ok; k++) {
+					cand.fmask[k] = (uint32_t)masks[k];
+					ok = db_build_pass(words, n, idx, val, cnt, dv2, masks, npass, k, &cand.pass[k], &e2);
+					mp = std::max(mp, cand.pass[k].max_pos);
+					mb = std::max(mb, cand.pass[k].max_blob);
 				}
-				// all f-subsets give the same block sizes when the basis is every word of a fixed particle number: next f
-				break;
+				if (!ok) continue;
+				cand.max_pos = mp;
+				cand.tile_bytes = (mp + 1) * DB_LINE;
+				cand.smem_bytes = (size_t)cand.tile_bytes + (size_t)mb * 16;
+				if (cand.smem_bytes + (size_t)mp * 8 > budget) continue;
+				*hp = std::move(cand);
+				return true;
 			}
-			// next combination (descending)
-			int i = f - 1;
-			while (i >= 0 && c[i] == f - 1 - i) i--;
-			if (i < 0) more = false;
-			else {
-				c[i]--;
-				for (int j = i + 1; j < f; j++) c[j] = c[j - 1] - 1;
-			}
-		}
 	}
-	*err = "no pair of separated site sets whose blocks fit shared memory";
+	*err = "no sets of fixed sites whose blocks fit shared memory";
 	return false;
 }
 
@@ -263,13 +305,15 @@ struct DbDevPass {
 	uint32_t nblocks = 0;
 };
 struct DbDevPlan {
-	DbDevPass pass[2];
-	unsigned long long* ctrl = nullptr;   // [0] ticket counter, then uint32 done counters per panel group
-	uint32_t ctrl_groups = 0;
+	int npass = 0;
+	DbDevPass pass[DB_MAX_PASS];
+	unsigned long long* ctrl = nullptr;   // [0] ticket counter, then uint32 done counters [npass - 1][npanels]
+	uint32_t ctrl_panels = 0;
 	size_t smem_bytes = 0;
 	uint32_t tile_bytes = 0;
 	uint32_t max_pos = 0;
-	int lag = 8;                          // pass 2 runs this many panels behind pass 1
+	int ctas_per_sm = 1, threads = 1024;
+	int lag = 8;                          // pass k of a panel runs this many panels behind pass k-1
 	double tmag = 1.0;
 	long long* profile = nullptr;         // DB_PROFILE builds: 8 cycle counters per CTA
 	bool attr_set = false;
@@ -284,12 +328,13 @@ struct DbArgs {
 	const double* beta_dev;
 	const uint32_t* w1;                // up word of every column (32-bit copy)
 	const double* dv1;                 // up potential of every column
-	double* dot_partials;              // optional: per pass-2 tile partial sums of y . x_new  [npanels * nblocks2]
+	double* dot_partials;              // optional: per last-pass tile partial sums of y . x_new  [npanels * nblocks of the last pass]
 };
 
 static bool db_upload_plan(const DbHostPlan& hp, DbDevPlan* dp, std::string* err)
 {
-	for (int p = 0; p < 2; p++) {
+	dp->npass = hp.npass;
+	for (int p = 0; p < hp.npass; p++) {
 		const DbHostPass& h = hp.pass[p];
 		DbDevPass& d = dp->pass[p];
 		d.nblocks = (uint32_t)h.blocks.size();
@@ -301,7 +346,9 @@ static bool db_upload_plan(const DbHostPlan& hp, DbDevPlan* dp, std::string* err
 	}
 	dp->smem_bytes = hp.smem_bytes;
 	dp->tile_bytes = hp.tile_bytes;
-	dp->max_pos = std::max(hp.pass[0].max_pos, hp.pass[1].max_pos);
+	dp->max_pos = hp.max_pos;
+	dp->ctas_per_sm = hp.ctas_per_sm;
+	dp->threads = hp.threads;
 	dp->tmag = hp.tmag;
 	if (cudaGetLastError() != cudaSuccess) { *err = "plan upload failed"; return false; }
 	return true;
@@ -309,7 +356,7 @@ static bool db_upload_plan(const DbHostPlan& hp, DbDevPlan* dp, std::string* err
 
 static void db_free_plan(DbDevPlan* dp)
 {
-	for (int p = 0; p < 2; p++) {
+	for (int p = 0; p < DB_MAX_PASS; p++) {
 		cudaFree(dp->pass[p].blocks);
 		cudaFree(dp->pass[p].blob);
 		cudaFree(dp->pass[p].rows);
@@ -321,29 +368,24 @@ static void db_free_plan(DbDevPlan* dp)
 // ---------------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------------
-#define DB_NW (DB_THREADS / 32)
-#define DB_SPR (DB_THREADS / 8)         // states staged per round of the CTA (8 lanes per state)
-#ifndef DB_DYNAMIC_STEPS
-#define DB_DYNAMIC_STEPS 0               // 1: warps take steps from a shared-memory counter (measured 2.00 ms against 1.88 ms)
-#endif
 #ifndef DB_SKIP_PADDING
 #define DB_SKIP_PADDING 0                // 1: predicate padded operands off (measured 1.92 ms against 1.88 ms without)
 #endif
 #ifndef DB_FILL_MODE
-#define DB_FILL_MODE 0                  // 0: 16-byte cp.async per thread (4.2 k cycles per tile), 1: LDG.128 batches + STS.128 (9 k)
+#define DB_FILL_MODE 0                  // 0: 16-byte cp.async per thread; 2: one 128-byte bulk copy (TMA) per state on the tile's mbarrier
 #endif
 
 struct DbKernelArgs {
 	DbArgs a;
-	const DbBlock* blocks[2];
-	const uint4* blob[2];
-	const uint32_t* rows[2];
-	uint32_t nb[2];
-	uint32_t npanels, lag;
+	const DbBlock* blocks[DB_MAX_PASS];
+	const uint4* blob[DB_MAX_PASS];
+	const uint32_t* rows[DB_MAX_PASS];
+	uint32_t nb[DB_MAX_PASS];
+	uint32_t npass, npanels, lag;
 	uint32_t tile_bytes, blob_bytes, max_pos;   // shared-memory layout: tile | tables | 2 row lists of max_pos words
 	long long* profile;
 	unsigned long long* ticket;
-	uint32_t* done1;
+	uint32_t* done;                             // [npass - 1][npanels]: tiles of pass k that have written their x
 };
 
 __device__ __forceinline__ void db_ld2(uint32_t addr, double& vx, double& vy)
@@ -389,24 +431,20 @@ __device__ __forceinline__ void db_pair(uint32_t ta, uint32_t lane_off, double& 
 	b0 += v2; b1 += v3;
 }
 
-// ticket t -> (pass, panel, block): panel-major, pass 2 of a panel `L` panels behind its pass 1
-__device__ __forceinline__ void db_decode(const DbKernelArgs& ka, unsigned long long t, uint32_t L, uint32_t nbt, uint32_t& pass, uint32_t& panel,
+// ticket t -> (pass, panel, block).  Time step ts = t / nbt holds the tiles of pass 0 of panel ts, pass 1 of panel ts - L,
+// pass 2 of panel ts - 2 L, in that order; slots whose panel is out of range are empty (the first and last (npass-1) L steps).
+__device__ __forceinline__ bool db_decode(const DbKernelArgs& ka, unsigned long long t, uint32_t L, uint32_t nbt, uint32_t& pass, uint32_t& panel,
                                           uint32_t& blk)
 {
-	if (t < (unsigned long long)L * ka.nb[0]) {
-		pass = 0; panel = (uint32_t)(t / ka.nb[0]); blk = (uint32_t)(t % ka.nb[0]);
-	} else {
-		const unsigned long long u = t - (unsigned long long)L * ka.nb[0];
-		const unsigned long long mid = (unsigned long long)(ka.npanels - L) * nbt;
-		if (u < mid) {
-			const uint32_t i = (uint32_t)(u / nbt), r = (uint32_t)(u % nbt);
-			if (r < ka.nb[0]) { pass = 0; panel = L + i; blk = r; }
-			else { pass = 1; panel = i; blk = r - ka.nb[0]; }
-		} else {
-			const unsigned long long v = u - mid;
-			pass = 1; panel = (ka.npanels - L) + (uint32_t)(v / ka.nb[1]); blk = (uint32_t)(v % ka.nb[1]);
-		}
-	}
+	const unsigned long long ts = t / nbt;
+	uint32_t r = (uint32_t)(t % nbt), k = 0;
+	while (k + 1 < ka.npass && r >= ka.nb[k]) { r -= ka.nb[k]; k++; }
+	pass = k;
+	blk = r;
+	const unsigned long long back = (unsigned long long)k * L;
+	if (ts < back || ts - back >= ka.npanels) return false;
+	panel = (uint32_t)(ts - back);
+	return true;
 }
 
 __device__ __forceinline__ void db_mbar_wait(uint32_t bar, uint32_t phase)
@@ -419,13 +457,15 @@ struct DbTileRef {
 	bool valid;
 };
 
-// One CTA per SM.  Per tile: the tables arrive by one bulk copy (TMA) on an mbarrier, the 128-byte lines of y by 16-byte
-// cp.async (rows taken from a shared-memory copy made while the previous tile was computed, so the fill issues no dependent
-// global load), then 32 warps walk the steps.  The ticket, block descriptor and row list of the NEXT tile are fetched during
-// the compute phase.
-template <bool DOT>
-__global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
+// NT threads per CTA, 2048 / NT ... 1 or 2 CTAs per SM.  Per tile: the tables arrive by one bulk copy (TMA) on an mbarrier, the
+// 128-byte lines of y by 16-byte cp.async (rows taken from a shared-memory copy made while the previous tile was computed, so
+// the fill issues no dependent global load), then the warps walk the steps.  The ticket, block descriptor and row list of the
+// NEXT tile are fetched during the compute phase.
+template <bool DOT, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_dblock(const DbKernelArgs ka)
 {
+	constexpr uint32_t NW = NT / 32;            // warps
+	constexpr uint32_t SPR = NT / 8;            // states staged per round of the CTA (8 lanes per state)
 	extern __shared__ __align__(128) unsigned char db_smem[];
 	const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(db_smem);
 	uint4* blob_s = reinterpret_cast<uint4*>(db_smem + ka.tile_bytes);
@@ -435,8 +475,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 	__shared__ unsigned long long s_ticket[2];
 	__shared__ DbBlock s_bd[2];
 	__shared__ __align__(8) unsigned long long s_bar;
-	__shared__ double s_red[DB_NW];
-	__shared__ uint32_t s_step;
+	__shared__ double s_red[NW];
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	const int q = lane >> 3, c = lane & 7;
 	DbArgs a = ka.a;
@@ -448,19 +487,27 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	const uint32_t nbt = ka.nb[0] + ka.nb[1];
-	const unsigned long long total = (unsigned long long)ka.npanels * nbt;
-	const uint32_t L = min(ka.lag, ka.npanels);
+	uint32_t nbt = 0;
+	for (uint32_t k = 0; k < ka.npass; k++) nbt += ka.nb[k];
+	const uint32_t L = max(min(ka.lag, ka.npanels), 1u);
+	const unsigned long long total = ((unsigned long long)ka.npanels + (unsigned long long)(ka.npass - 1) * L) * nbt;
+	const uint32_t last = ka.npass - 1;
 	const bool need_x1 = a.beta != 0.0;
 	const uint32_t lane_off = tile_s + (uint32_t)c * 16u;
 	const uint32_t max_pos = ka.max_pos;
 	uint32_t bphase = 0;
 	auto tile_of = [&](unsigned long long t) {
 		DbTileRef T;
-		T.valid = t < total;
 		T.pass = T.panel = T.blk = 0;
-		if (T.valid) db_decode(ka, t, L, nbt, T.pass, T.panel, T.blk);
+		T.valid = t < total && db_decode(ka, t, L, nbt, T.pass, T.panel, T.blk);
 		return T;
+	};
+	// thread 0: the next ticket that holds a tile (>= total when the sweep is over)
+	auto take_ticket = [&]() {
+		unsigned long long t;
+		uint32_t p0, p1, p2;
+		do t = atomicAdd(ka.ticket, 1ull); while (t < total && !db_decode(ka, t, L, nbt, p0, p1, p2));
+		return t;
 	};
 	// stage descriptor + row list of tile T into buffer `buf` (asynchronously)
 	auto stage_next = [&](const DbTileRef& T, uint32_t buf) {
@@ -469,10 +516,10 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 		if (tid == 0) s_bd[buf] = *bdp;
 		const uint32_t ns = __ldg(&bdp->nstates), ro = __ldg(&bdp->rows_off);
 		const uint32_t* __restrict__ rows = ka.rows[T.pass] + ro;
-		for (uint32_t p = tid; p < ns; p += DB_THREADS)
+		for (uint32_t p = tid; p < ns; p += NT)
 			asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rows_sa + (buf * max_pos + p) * 4u), "l"(rows + p) : "memory");
 	};
-	if (tid == 0) s_ticket[0] = atomicAdd(ka.ticket, 1ull);
+	if (tid == 0) s_ticket[0] = take_ticket();
 	__syncthreads();
 	DbTileRef cur = tile_of(s_ticket[0]);
 	stage_next(cur, 0);
@@ -489,46 +536,38 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 		const uint32_t buf = it & 1u;
 		const uint32_t pass = cur.pass, panel = cur.panel, blk = cur.blk;
 		const DbBlock bd = s_bd[buf];
-		const uint64_t mycol = (uint64_t)panel * DB_COLS + 2u * c;
+		const uint64_t col0 = (uint64_t)panel * DB_COLS;
+		const uint64_t mycol = col0 + 2u * c;
 		const bool colok = mycol < a.ncols;
-		// ---- tables: one bulk copy; tile: 16 bytes per thread and copy (8 lanes = one state's 128-byte line)
+		// ---- tables: one bulk copy; tile: one state's 128-byte line per 8 lanes (cp.async) or per thread (bulk copy)
 		if (tid == 0) {
-			const uint32_t bytes = bd.blob_len * 16u;
+			uint32_t bytes = bd.blob_len * 16u;
+#if DB_FILL_MODE == 2
+			bytes += bd.nstates * (uint32_t)(min((uint64_t)DB_COLS, a.ncols - col0) * 8u);
+#endif
 			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(blob_sa),
-			             "l"(ka.blob[pass] + bd.blob_off), "r"(bytes), "r"(bar_s)
+			             "l"(ka.blob[pass] + bd.blob_off), "r"(bd.blob_len * 16u), "r"(bar_s)
 			             : "memory");
-			s_ticket[buf ^ 1u] = atomicAdd(ka.ticket, 1ull);                 // next tile's ticket, read after the fill barrier
-			s_step = DB_NW;                                                  // steps 0 .. DB_NW-1 are the warps' first steps
+			s_ticket[buf ^ 1u] = take_ticket();                             // next tile's ticket, read after the fill barrier
 		}
 		{
 			const uint32_t* rows = rows_sm + buf * max_pos;
-			const double* ycol = a.y + (colok ? mycol : 0);
 #if DB_FILL_MODE == 0
+			const double* ycol = a.y + (colok ? mycol : 0);
 			const uint32_t nbytes = colok ? 16u : 0u;
 			uint32_t dst = tile_s + ((uint32_t)(tid >> 3) + 1u) * DB_LINE + (uint32_t)c * 16u;
-			for (uint32_t p = tid >> 3; p < bd.nstates; p += DB_SPR, dst += DB_SPR * DB_LINE)
+			for (uint32_t p = tid >> 3; p < bd.nstates; p += SPR, dst += SPR * DB_LINE)
 				asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ycol + (uint64_t)rows[p] * a.pitch), "r"(nbytes) : "memory");
 			asm volatile("cp.async.commit_group;" ::: "memory");
 #else
-			// batches of 8 independent 16-byte loads per thread, then 8 shared-memory stores
-			for (uint32_t p0 = tid >> 3; p0 < bd.nstates; p0 += DB_SPR * 8u) {
-				uint4 v[8];
-#pragma unroll
-				for (int k = 0; k < 8; k++) {
-					const uint32_t p = p0 + (uint32_t)k * DB_SPR;
-					v[k] = make_uint4(0u, 0u, 0u, 0u);
-					if (colok && p < bd.nstates) v[k] = __ldcs(reinterpret_cast<const uint4*>(ycol + (uint64_t)rows[p] * a.pitch));
-				}
-#pragma unroll
-				for (int k = 0; k < 8; k++) {
-					const uint32_t p = p0 + (uint32_t)k * DB_SPR;
-					if (p < bd.nstates)
-						asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + (p + 1u) * DB_LINE + (uint32_t)c * 16u), "r"(v[k].x), "r"(v[k].y),
-						             "r"(v[k].z), "r"(v[k].w)
-						             : "memory");
-				}
-			}
+			// the tx-count of an mbarrier may run negative inside a phase, so these copies need not wait for thread 0's expect_tx
+			const uint32_t line = (uint32_t)(min((uint64_t)DB_COLS, a.ncols - col0) * 8u);
+			const double* ycol = a.y + col0;
+			for (uint32_t p = tid; p < bd.nstates; p += NT)
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tile_s + (p + 1u) * DB_LINE),
+				             "l"(ycol + (uint64_t)rows[p] * a.pitch), "r"(line), "r"(bar_s)
+				             : "memory");
 #endif
 		}
 		uint32_t k1[2] = {0u, 0u};
@@ -538,12 +577,13 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 			dv1[0] = __ldg(a.dv1 + mycol); dv1[1] = __ldg(a.dv1 + mycol + 1);
 		}
 		DB_TICK(0);
-		if (pass == 1 && tid == 0) {
-			// wait until every pass-1 tile of this panel has written its x
-			const uint32_t want = ka.nb[0];
+		if (pass != 0 && tid == 0) {
+			// wait until every tile of the previous pass of this panel has written its x
+			const uint32_t want = ka.nb[pass - 1];
+			const uint32_t* flag = ka.done + (uint64_t)(pass - 1) * ka.npanels + panel;
 			uint32_t seen;
 			do {
-				asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ka.done1 + panel) : "memory");
+				asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
 				if (seen < want) __nanosleep(100);
 			} while (seen < want);
 		}
@@ -562,17 +602,10 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 		const uint4* meta_s = blob_s;
 		const uint32_t* info_s = reinterpret_cast<const uint32_t*>(blob_s + bd.nsteps * 4u);
 		const uint32_t tab_sa = blob_sa + (bd.nsteps * 4u + ((bd.nsteps + 3u) >> 2)) * 16u;
-		const bool read_x = pass == 1 || need_x1;
+		const bool read_x = pass != 0 || need_x1;
+		const bool want_dot = DOT && pass == last;
 		double contrib = 0.0;
-#if DB_DYNAMIC_STEPS
-		// steps are handed out from a shared-memory counter (they are sorted longest first): with a fixed stride the last round
-		// has 231 - 7 * 32 = 7 steps for 32 warps and the tile waits for them.  The next index is fetched one step ahead.
-		uint32_t st_next = 0;
-		if (lane == 0) st_next = atomicAdd(&s_step, 1u);
-		for (uint32_t st = wid; st < bd.nsteps;) {
-#else
-		for (uint32_t st = wid; st < bd.nsteps; st += DB_NW) {
-#endif
+		for (uint32_t st = wid; st < bd.nsteps; st += NW) {
 			const uint32_t pos = st * 4u + q;
 			const uint32_t info = info_s[st];
 			const uint4 m = meta_s[pos];
@@ -581,7 +614,7 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 			double2 xo = make_double2(0.0, 0.0);
 			if (valid && read_x) xo = __ldcg(reinterpret_cast<const double2*>(xp));
 			double yo0 = 0.0, yo1 = 0.0;
-			if (pass == 0 || DOT) db_ld2(lane_off + (pos + 1u) * DB_LINE, yo0, yo1);
+			if (pass == 0 || want_dot) db_ld2(lane_off + (pos + 1u) * DB_LINE, yo0, yo1);
 			double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
 			uint32_t ta = tab_sa + (info & 0x000fffffu) * 32u;
 			const uint32_t pp = (info >> 20) & 63u, pm = info >> 26;
@@ -606,21 +639,17 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 			}
 			if (valid) {
 				__stcg(reinterpret_cast<double2*>(xp), make_double2(xn0, xn1));
-				if (DOT && pass == 1) contrib += yo0 * xn0 + yo1 * xn1;
+				if (want_dot) contrib += yo0 * xn0 + yo1 * xn1;
 			}
-#if DB_DYNAMIC_STEPS
-			st = __shfl_sync(0xffffffffu, st_next, 0);
-			if (lane == 0 && st < bd.nsteps) st_next = atomicAdd(&s_step, 1u);
-#endif
 		}
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
-		DB_TICK(3 + pass);
+		DB_TICK(pass == 0 ? 3 : 4);
 		__syncthreads();                                   // all x of this tile are written, the tile may be overwritten
 		DB_TICK(5);
-		if (pass == 0) {
+		if (pass != last) {
 			if (tid == 0) {
 				__threadfence();
-				atomicAdd(ka.done1 + panel, 1u);
+				atomicAdd(ka.done + (uint64_t)pass * ka.npanels + panel, 1u);
 			}
 		} else if (DOT) {
 			// deterministic per-tile partial sum
@@ -629,10 +658,10 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 			if (lane == 0) s_red[wid] = contrib;
 			__syncthreads();
 			if (wid == 0) {
-				double v = lane < DB_NW ? s_red[lane] : 0.0;
+				double v = lane < (int)NW ? s_red[lane] : 0.0;
 #pragma unroll
 				for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-				if (lane == 0) a.dot_partials[(uint64_t)panel * ka.nb[1] + blk] = v;
+				if (lane == 0) a.dot_partials[(uint64_t)panel * ka.nb[last] + blk] = v;
 			}
 		}
 		cur = nxt;
@@ -643,32 +672,45 @@ __global__ void __launch_bounds__(DB_THREADS, 1) k_dblock(const DbKernelArgs ka)
 #endif
 }
 
+template <int NT>
+static int db_launch_nt(DbDevPlan& dp, const DbKernelArgs& ka, unsigned grid, size_t smem, bool dot, cudaStream_t s)
+{
+	if (!dp.attr_set) {
+		if (cudaFuncSetAttribute(k_dblock<false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (cudaFuncSetAttribute(k_dblock<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		dp.attr_set = true;
+	}
+	if (dot) k_dblock<true, NT><<<grid, NT, smem, s>>>(ka);
+	else k_dblock<false, NT><<<grid, NT, smem, s>>>(ka);
+	return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // returns 0 on success
 static int db_launch(DbDevPlan& dp, const DbArgs& a, int nsm, cudaStream_t s)
 {
 	const uint32_t npanels = (uint32_t)((a.ncols + DB_COLS - 1) / DB_COLS);
 	if (npanels == 0) return 0;
-	if (dp.ctrl_groups < npanels) {
+	const size_t ctrl_bytes = 8 + (size_t)npanels * 4 * (size_t)(dp.npass - 1);
+	if (dp.ctrl_panels < npanels) {
 		cudaFree(dp.ctrl);
 		dp.ctrl = nullptr;
-		if (cudaMalloc(&dp.ctrl, 8 + (size_t)npanels * 4) != cudaSuccess) return -1;
-		dp.ctrl_groups = npanels;
+		if (cudaMalloc(&dp.ctrl, ctrl_bytes) != cudaSuccess) return -1;
+		dp.ctrl_panels = npanels;
 	}
 	const size_t smem = dp.smem_bytes + (size_t)dp.max_pos * 8;
-	if (!dp.attr_set) {
-		if (cudaFuncSetAttribute(k_dblock<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-		if (cudaFuncSetAttribute(k_dblock<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-		dp.attr_set = true;
-	}
-	if (cudaMemsetAsync(dp.ctrl, 0, 8 + (size_t)npanels * 4, s) != cudaSuccess) return -1;
+	if (cudaMemsetAsync(dp.ctrl, 0, ctrl_bytes, s) != cudaSuccess) return -1;
 	DbKernelArgs ka;
 	ka.a = a;
-	for (int p = 0; p < 2; p++) {
-		ka.blocks[p] = dp.pass[p].blocks;
-		ka.blob[p] = dp.pass[p].blob;
-		ka.rows[p] = dp.pass[p].rows;
-		ka.nb[p] = dp.pass[p].nblocks;
+	unsigned long long tiles = 0;
+	for (int p = 0; p < DB_MAX_PASS; p++) {
+		const bool on = p < dp.npass;
+		ka.blocks[p] = on ? dp.pass[p].blocks : nullptr;
+		ka.blob[p] = on ? dp.pass[p].blob : nullptr;
+		ka.rows[p] = on ? dp.pass[p].rows : nullptr;
+		ka.nb[p] = on ? dp.pass[p].nblocks : 0u;
+		tiles += (unsigned long long)npanels * ka.nb[p];
 	}
+	ka.npass = (uint32_t)dp.npass;
 	ka.npanels = npanels;
 	ka.lag = (uint32_t)std::max(dp.lag, 1);
 	ka.tile_bytes = dp.tile_bytes;
@@ -676,10 +718,8 @@ static int db_launch(DbDevPlan& dp, const DbArgs& a, int nsm, cudaStream_t s)
 	ka.max_pos = dp.max_pos;
 	ka.profile = dp.profile;
 	ka.ticket = dp.ctrl;
-	ka.done1 = reinterpret_cast<uint32_t*>(dp.ctrl + 1);
-	const unsigned long long total = (unsigned long long)npanels * (ka.nb[0] + ka.nb[1]);
-	const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)nsm, total);
-	if (a.dot_partials) k_dblock<true><<<grid, DB_THREADS, smem, s>>>(ka);
-	else k_dblock<false><<<grid, DB_THREADS, smem, s>>>(ka);
-	return cudaGetLastError() == cudaSuccess ? 0 : -1;
+	ka.done = reinterpret_cast<uint32_t*>(dp.ctrl + 1);
+	const unsigned grid = (unsigned)std::min<unsigned long long>((unsigned long long)nsm * (unsigned)dp.ctas_per_sm, tiles);
+	return dp.threads == 512 ? db_launch_nt<512>(dp, ka, grid, smem, a.dot_partials != nullptr, s)
+	                         : db_launch_nt<1024>(dp, ka, grid, smem, a.dot_partials != nullptr, s);
 }

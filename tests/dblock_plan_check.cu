@@ -3,14 +3,14 @@
 // (tile slot 0 = zero line, "+" quads/pair then "-" quads/pair per step, 4 states per step), then compares
 //   x = beta x + alpha (U0 popc(up & dn) + dv2 + T_dn) y
 // with the plain ELL application.  Also checks the structural invariants: every hop of the table appears in exactly one
-// pass, no operand leaves its block, F1 and F2 are disjoint and not connected by a bond.
+// pass, no operand leaves its block, every bond misses the fixed sites of at least one pass, the plan fits its CTAs per SM.
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <vector>
 #include "../lanczosplusplus_b200/csrc/lpp_dblock_kernel.cuh"
 
-static int run_case(int nx, int ny, int npart, bool periodic, bool potential)
+static int run_case(int nx, int ny, int npart, bool periodic, bool potential, int layout = 0)
 {
 	const int nsite = nx * ny;
 	std::vector<uint32_t> words;
@@ -63,15 +63,19 @@ static int run_case(int nx, int ny, int npart, bool periodic, bool potential)
 	}
 	DbHostPlan hp;
 	std::string err;
-	if (!db_build_host_plan(words.data(), n, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)232448 - 1024, &hp, &err)) {
+	if (!db_build_host_plan(words.data(), n, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)232448, (size_t)233472, layout, &hp, &err)) {
 		std::printf("%dx%d N=%d %s: no plan (%s)\n", nx, ny, npart, periodic ? "pbc" : "open", err.c_str());
 		return nhops == 0 ? 0 : 2;
 	}
 	// invariants
-	if (hp.f1 & hp.f2) { std::printf("FAIL F1 and F2 overlap\n"); return 1; }
 	for (int i = 0; i < nsite; i++)
-		for (int j = 0; j < nsite; j++)
-			if (hop[i * nsite + j] != 0 && ((hp.f1 >> i) & 1) && ((hp.f2 >> j) & 1)) { std::printf("FAIL a bond joins F1 and F2\n"); return 1; }
+		for (int j = 0; j < nsite; j++) {
+			if (hop[i * nsite + j] == 0) continue;
+			bool free_pass = false;                                   // every bond misses the fixed sites of some pass
+			for (int k = 0; k < hp.npass; k++) free_pass = free_pass || !(((hp.fmask[k] >> i) | (hp.fmask[k] >> j)) & 1u);
+			if (!free_pass) { std::printf("FAIL a bond touches the fixed sites of every pass\n"); return 1; }
+		}
+	if (hp.smem_bytes + (size_t)hp.max_pos * 8 + 2048 > (size_t)233472 / hp.ctas_per_sm) { std::printf("FAIL plan does not fit %d CTA(s) per SM\n", hp.ctas_per_sm); return 1; }
 	// host walk of the tables (two columns are enough: the kernel treats columns independently)
 	const int ncol = 2;
 	std::vector<double> y(n * ncol), x(n * ncol), xr(n * ncol);
@@ -86,7 +90,7 @@ static int run_case(int nx, int ny, int npart, bool periodic, bool potential)
 			xr[s * ncol + c] = beta * xr[s * ncol + c] + alpha * acc;
 		}
 	uint64_t walked = 0;
-	for (int pass = 0; pass < 2; pass++) {
+	for (int pass = 0; pass < hp.npass; pass++) {
 		const DbHostPass& P = hp.pass[pass];
 		for (const DbBlock& b : P.blocks) {
 			const uint4* blob = P.blob.data() + b.blob_off;
@@ -148,9 +152,11 @@ static int run_case(int nx, int ny, int npart, bool periodic, bool potential)
 	double maxd = 0, maxv = 0;
 	for (size_t i = 0; i < x.size(); i++) { maxd = std::max(maxd, std::fabs(x[i] - xr[i])); maxv = std::max(maxv, std::fabs(xr[i])); }
 	const bool ok = walked == nhops && maxd <= 1e-13 * std::max(1.0, maxv);
-	std::printf("%dx%d N=%d %s%s: %llu states, F1 %#x F2 %#x, %zu + %zu blocks, hops %llu walked %llu, max diff %.2e %s\n", nx, ny, npart,
-	            periodic ? "pbc" : "open", potential ? " +V" : "", (unsigned long long)n, hp.f1, hp.f2, hp.pass[0].blocks.size(), hp.pass[1].blocks.size(),
-	            (unsigned long long)nhops, (unsigned long long)walked, maxd, ok ? "ok" : "MISMATCH");
+	uint64_t slots = 0;
+	for (int k = 0; k < hp.npass; k++) slots += hp.pass[k].exec_slots;
+	std::printf("%dx%d N=%d %s%s: %llu states, %d passes x %d CTA/SM, F %#x %#x %#x, max block %u, slots/state %.2f, hops %llu walked %llu, max diff %.2e %s\n", nx, ny,
+	            npart, periodic ? "pbc" : "open", potential ? " +V" : "", (unsigned long long)n, hp.npass, hp.ctas_per_sm, hp.fmask[0], hp.fmask[1], hp.fmask[2],
+	            hp.max_pos, (double)slots / (double)n, (unsigned long long)nhops, (unsigned long long)walked, maxd, ok ? "ok" : "MISMATCH");
 	return ok ? 0 : 1;
 }
 
@@ -164,6 +170,8 @@ int main()
 	bad += run_case(8, 1, 4, true, false);
 	bad += run_case(3, 3, 4, true, true);       // the 3x3 torus is not bipartite
 	bad += run_case(4, 4, 3, true, false);
+	bad += run_case(4, 4, 8, true, true);        // config 3: three passes, two CTAs per SM
+	bad += run_case(4, 4, 8, true, false, 1);    // the same basis in the one-CTA layout (two passes)
 	std::printf(bad ? "FAIL\n" : "OK\n");
 	return bad ? 1 : 0;
 }

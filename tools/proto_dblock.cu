@@ -59,12 +59,13 @@ int main(int argc, char** argv)
 {
 	int nx = 4, ny = 4, npart = 8, iters = 10;
 	uint64_t ncols_arg = 0;
-	int lag = 8, ngp = 1;
+	int lag = 8, ngp = 1, layout = 0;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--cols")) ncols_arg = strtoull(argv[++i], 0, 10);
 		else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--lag")) lag = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--ng")) ngp = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--layout")) layout = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--chain")) { nx = atoi(argv[++i]); ny = 1; npart = nx / 2; }
 	}
 	const int nsite = nx * ny;
@@ -118,22 +119,28 @@ int main(int argc, char** argv)
 	}
 	printf("basis %llu states, width %d, mean hops %.3f, cols %llu\n", (unsigned long long)n2, width, meanh / n2, (unsigned long long)ncols);
 
-	int dev = 0, maxsm = 0, nsm = 0;
+	int dev = 0, maxsm = 0, maxblk = 0, nsm = 0;
 	CK(cudaGetDevice(&dev));
-	CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	CK(cudaDeviceGetAttribute(&maxblk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	CK(cudaDeviceGetAttribute(&maxsm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
 	CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
 	std::vector<double> dv2(n2, 0.0);
 	DbHostPlan hp;
 	std::string err;
-	if (!db_build_host_plan(words.data(), n2, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)maxsm, &hp, &err)) {
+	if (!db_build_host_plan(words.data(), n2, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)maxblk, (size_t)maxsm, layout, &hp, &err)) {
 		printf("plan failed: %s\n", err.c_str());
 		return 1;
 	}
-	printf("F1 mask %#x F2 mask %#x | pass1: %zu blocks, max %u pos, hops %.3f/state | pass2: %zu blocks, max %u pos, hops %.3f/state | smem %zu\n",
-	       hp.f1, hp.f2, hp.pass[0].blocks.size(), hp.pass[0].max_pos, hp.pass[0].mean_hops, hp.pass[1].blocks.size(), hp.pass[1].max_pos,
-	       hp.pass[1].mean_hops, hp.smem_bytes);
-	printf("executed state-slots per state (padding included): pass1 %.3f pass2 %.3f | lag %d ng %d\n", (double)hp.pass[0].exec_slots / n2,
-	       (double)hp.pass[1].exec_slots / n2, lag, ngp);
+	printf("%d passes, %d CTA(s) x %d threads per SM, smem %zu, lag %d, fill mode %d\n", hp.npass, hp.ctas_per_sm, hp.threads,
+	       hp.smem_bytes + (size_t)hp.max_pos * 8, lag, DB_FILL_MODE);
+	double slots = 0;
+	for (int k = 0; k < hp.npass; k++) {
+		printf("  pass %d: F %#x, %zu blocks, max %u pos, hops %.3f/state, executed slots %.3f/state\n", k + 1, hp.fmask[k], hp.pass[k].blocks.size(),
+		       hp.pass[k].max_pos, hp.pass[k].mean_hops, (double)hp.pass[k].exec_slots / n2);
+		slots += (double)hp.pass[k].exec_slots / n2;
+	}
+	printf("executed state-slots per state (padding included): %.3f\n", slots);
+	(void)ngp;
 
 	// device data
 	const uint64_t pitch = ncols;
@@ -208,18 +215,19 @@ int main(int argc, char** argv)
 #ifdef DB_PROFILE
 	{
 		long long* dprof;
-		CK(cudaMalloc(&dprof, nsm * 8 * sizeof(long long)));
-		CK(cudaMemset(dprof, 0, nsm * 8 * sizeof(long long)));
+		const int nctas = nsm * hp.ctas_per_sm;
+		CK(cudaMalloc(&dprof, nctas * 8 * sizeof(long long)));
+		CK(cudaMemset(dprof, 0, nctas * 8 * sizeof(long long)));
 		dp.profile = dprof;
 		db_launch(dp, a, nsm, 0);
 		CK(cudaDeviceSynchronize());
-		std::vector<long long> hpf(nsm * 8);
+		std::vector<long long> hpf(nctas * 8);
 		CK(cudaMemcpy(hpf.data(), dprof, hpf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-		const char* names[8] = {"ticket + fill issue", "pass-2 wait", "fill in flight", "compute P1 (warp 0)", "compute P2 (warp 0)", "end barrier", "-", "-"};
+		const char* names[8] = {"ticket + fill issue", "wait for previous pass", "fill in flight", "compute pass 1 (warp 0)", "compute later passes", "end barrier", "-", "-"};
 		for (int i = 0; i < 6; i++) {
 			double s = 0, mx = 0;
-			for (int b = 0; b < nsm; b++) { s += hpf[b * 8 + i]; mx = std::max<double>(mx, (double)hpf[b * 8 + i]); }
-			printf("  phase %-22s mean %10.0f cycles per CTA, max %10.0f\n", names[i], s / nsm, mx);
+			for (int b = 0; b < nctas; b++) { s += hpf[b * 8 + i]; mx = std::max<double>(mx, (double)hpf[b * 8 + i]); }
+			printf("  phase %-26s mean %10.0f cycles per CTA, max %10.0f\n", names[i], s / nctas, mx);
 		}
 		dp.profile = nullptr;
 	}
