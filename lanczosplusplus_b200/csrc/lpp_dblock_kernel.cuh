@@ -61,7 +61,7 @@ struct DbHostPlan {
 // ---------------------------------------------------------------------------------------------------------------
 template <class W>
 static bool db_build_pass(const W* words, uint64_t n, const uint32_t* idx, const double* val, const uint32_t* cnt, const double* dv2,
-                          const uint64_t* masks, int npass, int which, DbHostPass* out, std::string* err)
+                          const uint64_t* masks, int npass, int which, int nwarps, DbHostPass* out, std::string* err)
 {
 	const uint64_t fmask_group = masks[which];
 	// group states by their occupation of the fixed sites
@@ -106,8 +106,37 @@ static bool db_build_pass(const W* words, uint64_t n, const uint32_t* idx, const
 			if (pa != pb) return pa > pb;
 			return np2(minus[a].size()) > np2(minus[b].size());
 		});
-		for (uint32_t p = 0; p < ns; p++) pos_of[key[b0 + order[p]].second] = p;
 		const uint32_t npos = (ns + 3) & ~3u, nsteps = npos / 4;
+		// warp w walks the steps w, w + nwarps, ...: spread the steps over the warps by longest-processing-time-first so that they
+		// reach the end of the tile together (in sorted order warp 0 would get the longest step of every round).  A partial last
+		// step keeps its place, so that the padding positions stay at the end of the tile.
+		if (nwarps > 1 && nsteps > 1) {
+			auto step_cost = [&](uint32_t st) {
+				uint32_t pp = 0, pm = 0;
+				for (uint32_t p = st * 4; p < st * 4 + 4 && p < ns; p++) { pp = std::max(pp, np2(plus[order[p]].size())); pm = std::max(pm, np2(minus[order[p]].size())); }
+				return 3u * (pp + pm) + 4u;
+			};
+			std::vector<uint32_t> cap(nwarps, 0), load(nwarps, 0), taken(nwarps, 0);
+			for (uint32_t st = 0; st < nsteps; st++) cap[st % nwarps]++;
+			const bool pinned = (ns & 3u) != 0;
+			const uint32_t nfree = pinned ? nsteps - 1 : nsteps;
+			if (pinned) { cap[(nsteps - 1) % nwarps]--; load[(nsteps - 1) % nwarps] += step_cost(nsteps - 1); }
+			std::vector<uint32_t> sorted_steps(nfree);
+			for (uint32_t st = 0; st < nfree; st++) sorted_steps[st] = st;
+			std::stable_sort(sorted_steps.begin(), sorted_steps.end(), [&](uint32_t a, uint32_t b) { return step_cost(a) > step_cost(b); });
+			std::vector<uint32_t> order2(order);
+			for (uint32_t old_st : sorted_steps) {
+				uint32_t best = nwarps;
+				for (uint32_t w = 0; w < (uint32_t)nwarps; w++)
+					if (taken[w] < cap[w] && (best == (uint32_t)nwarps || load[w] < load[best])) best = w;
+				const uint32_t new_st = best + taken[best] * (uint32_t)nwarps;
+				taken[best]++;
+				load[best] += step_cost(old_st);
+				for (int q = 0; q < 4; q++) order2[new_st * 4 + q] = order[old_st * 4 + q];
+			}
+			order.swap(order2);
+		}
+		for (uint32_t p = 0; p < ns; p++) pos_of[key[b0 + order[p]].second] = p;
 		DbBlock blk;
 		blk.nstates = ns;
 		blk.nsteps = nsteps;
@@ -278,7 +307,7 @@ static bool db_build_host_plan(const W* words, uint64_t n, int nbits, const uint
 				uint32_t mp = 0, mb = 0;
 				for (int k = 0; k < npass && ok; k++) {
 					cand.fmask[k] = (uint32_t)masks[k];
-					ok = db_build_pass(words, n, idx, val, cnt, dv2, masks, npass, k, &cand.pass[k], &e2);
+					ok = db_build_pass(words, n, idx, val, cnt, dv2, masks, npass, k, cand.threads / 32, &cand.pass[k], &e2);
 					mp = std::max(mp, cand.pass[k].max_pos);
 					mb = std::max(mb, cand.pass[k].max_blob);
 				}
@@ -452,6 +481,62 @@ __device__ __forceinline__ void db_mbar_wait(uint32_t bar, uint32_t phase)
 	asm volatile("{\n.reg .pred p;\nDBW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DBD_%=;\nbra DBW_%=;\nDBD_%=:\n}" ::"r"(bar), "r"(phase) : "memory");
 }
 
+struct DbStepCtx {
+	const uint4* meta_s;
+	const uint32_t* info_s;
+	uint32_t tab_sa, lane_off, nsteps;
+	double* x;                          // x + this lane's first column
+	uint64_t pitch;
+	double alpha, beta, tmag;
+};
+
+// the steps of one tile.  FIRST: the first pass (x = beta x + alpha (diag y + hops)), otherwise x += alpha hops.  READX: the old
+// x is read (always but for the first pass with beta == 0).  DOTNOW: returns this thread's share of y . x_new.
+template <bool FIRST, bool READX, bool DOTNOW, uint32_t NW>
+__device__ __forceinline__ double db_steps(const DbStepCtx& sc, int wid, int q, bool colok, double U0, const uint32_t* k1, const double* dv1)
+{
+	double contrib = 0.0;
+	for (uint32_t st = (uint32_t)wid; st < sc.nsteps; st += NW) {
+		const uint32_t pos = st * 4u + (uint32_t)q;
+		const uint32_t info = sc.info_s[st];
+		const uint32_t row = sc.meta_s[pos].x;
+		const bool valid = colok && row != DB_ROW_NONE;
+		double* xp = sc.x + (uint64_t)row * sc.pitch;
+		double2 xo = make_double2(0.0, 0.0);
+		if (READX && valid) xo = __ldcg(reinterpret_cast<const double2*>(xp));
+		double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+		uint32_t ta = sc.tab_sa + (info & 0x000fffffu) * 32u;
+		const uint32_t pp = (info >> 20) & 63u, pm = info >> 26;
+#pragma unroll 1
+		for (uint32_t g = 0; g < (pp >> 1); g++, ta += 64u) db_quad(ta + (uint32_t)q * 16u, sc.lane_off, a0, a1, b0, b1);
+		if (pp & 1u) { db_pair(ta + (uint32_t)q * 8u, sc.lane_off, a0, a1, b0, b1); ta += 32u; }
+#pragma unroll 1
+		for (uint32_t g = 0; g < (pm >> 1); g++, ta += 64u) db_quad(ta + (uint32_t)q * 16u, sc.lane_off, c0, c1, d0, d1);
+		if (pm & 1u) db_pair(ta + (uint32_t)q * 8u, sc.lane_off, c0, c1, d0, d1);
+		double h0 = sc.tmag * ((a0 + b0) - (c0 + d0)), h1 = sc.tmag * ((a1 + b1) - (c1 + d1));
+		double yo0 = 0.0, yo1 = 0.0;                           // the state's own element: loaded late, not live across the gathers
+		if (FIRST || DOTNOW) db_ld2(sc.lane_off + (pos + 1u) * DB_LINE, yo0, yo1);
+		double xn0, xn1;
+		if (FIRST) {
+			const uint4 m = sc.meta_s[pos];
+			const double dv2 = __hiloint2double((int)m.w, (int)m.z);
+			h0 += (U0 * (double)__popc(k1[0] & m.y) + dv1[0] + dv2) * yo0;
+			h1 += (U0 * (double)__popc(k1[1] & m.y) + dv1[1] + dv2) * yo1;
+			xn0 = sc.alpha * h0;
+			xn1 = sc.alpha * h1;
+			if (READX) { xn0 += sc.beta * xo.x; xn1 += sc.beta * xo.y; }
+		} else {
+			xn0 = xo.x + sc.alpha * h0;
+			xn1 = xo.y + sc.alpha * h1;
+		}
+		if (valid) {
+			__stcg(reinterpret_cast<double2*>(xp), make_double2(xn0, xn1));
+			if (DOTNOW) contrib += yo0 * xn0 + yo1 * xn1;
+		}
+	}
+	return contrib;
+}
+
 struct DbTileRef {
 	uint32_t pass, panel, blk;
 	bool valid;
@@ -570,12 +655,6 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_dblock(const DbKern
 				             : "memory");
 #endif
 		}
-		uint32_t k1[2] = {0u, 0u};
-		double dv1[2] = {0.0, 0.0};
-		if (pass == 0 && colok) {
-			k1[0] = __ldg(a.w1 + mycol); k1[1] = __ldg(a.w1 + mycol + 1);
-			dv1[0] = __ldg(a.dv1 + mycol); dv1[1] = __ldg(a.dv1 + mycol + 1);
-		}
 		DB_TICK(0);
 		if (pass != 0 && tid == 0) {
 			// wait until every tile of the previous pass of this panel has written its x
@@ -598,49 +677,33 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_dblock(const DbKern
 		stage_next(nxt, buf ^ 1u);
 		asm volatile("cp.async.commit_group;" ::: "memory");
 
-		// ---- compute: a warp takes 4 states per step, 8 lanes (2 columns each) per state
-		const uint4* meta_s = blob_s;
-		const uint32_t* info_s = reinterpret_cast<const uint32_t*>(blob_s + bd.nsteps * 4u);
-		const uint32_t tab_sa = blob_sa + (bd.nsteps * 4u + ((bd.nsteps + 3u) >> 2)) * 16u;
-		const bool read_x = pass != 0 || need_x1;
-		const bool want_dot = DOT && pass == last;
+		// ---- compute: a warp takes 4 states per step, 8 lanes (2 columns each) per state.  One instantiation of the step loop
+		// per kind of pass, so that the first pass's diagonal operands and the last pass's dot product cost the others no registers
+		DbStepCtx sc;
+		sc.meta_s = blob_s;
+		sc.info_s = reinterpret_cast<const uint32_t*>(blob_s + bd.nsteps * 4u);
+		sc.tab_sa = blob_sa + (bd.nsteps * 4u + ((bd.nsteps + 3u) >> 2)) * 16u;
+		sc.lane_off = lane_off;
+		sc.nsteps = bd.nsteps;
+		sc.x = a.x + mycol;
+		sc.pitch = a.pitch;
+		sc.alpha = a.alpha;
+		sc.beta = a.beta;
+		sc.tmag = a.tmag;
 		double contrib = 0.0;
-		for (uint32_t st = wid; st < bd.nsteps; st += NW) {
-			const uint32_t pos = st * 4u + q;
-			const uint32_t info = info_s[st];
-			const uint4 m = meta_s[pos];
-			const bool valid = colok && m.x != DB_ROW_NONE;
-			double* xp = a.x + (uint64_t)m.x * a.pitch + mycol;
-			double2 xo = make_double2(0.0, 0.0);
-			if (valid && read_x) xo = __ldcg(reinterpret_cast<const double2*>(xp));
-			double yo0 = 0.0, yo1 = 0.0;
-			if (pass == 0 || want_dot) db_ld2(lane_off + (pos + 1u) * DB_LINE, yo0, yo1);
-			double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0, c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-			uint32_t ta = tab_sa + (info & 0x000fffffu) * 32u;
-			const uint32_t pp = (info >> 20) & 63u, pm = info >> 26;
-#pragma unroll 1
-			for (uint32_t g = 0; g < (pp >> 1); g++, ta += 64u) db_quad(ta + (uint32_t)q * 16u, lane_off, a0, a1, b0, b1);
-			if (pp & 1u) { db_pair(ta + (uint32_t)q * 8u, lane_off, a0, a1, b0, b1); ta += 32u; }
-#pragma unroll 1
-			for (uint32_t g = 0; g < (pm >> 1); g++, ta += 64u) db_quad(ta + (uint32_t)q * 16u, lane_off, c0, c1, d0, d1);
-			if (pm & 1u) db_pair(ta + (uint32_t)q * 8u, lane_off, c0, c1, d0, d1);
-			double h0 = a.tmag * ((a0 + b0) - (c0 + d0)), h1 = a.tmag * ((a1 + b1) - (c1 + d1));
-			double xn0, xn1;
-			if (pass == 0) {
-				const double dv2 = __hiloint2double((int)m.w, (int)m.z);
-				h0 += (a.U0 * (double)__popc(k1[0] & m.y) + dv1[0] + dv2) * yo0;
-				h1 += (a.U0 * (double)__popc(k1[1] & m.y) + dv1[1] + dv2) * yo1;
-				xn0 = a.alpha * h0;
-				xn1 = a.alpha * h1;
-				if (need_x1) { xn0 += a.beta * xo.x; xn1 += a.beta * xo.y; }
-			} else {
-				xn0 = xo.x + a.alpha * h0;
-				xn1 = xo.y + a.alpha * h1;
+		if (pass == 0) {
+			uint32_t k1[2] = {0u, 0u};
+			double dv1[2] = {0.0, 0.0};
+			if (colok) {
+				k1[0] = __ldg(a.w1 + mycol); k1[1] = __ldg(a.w1 + mycol + 1);
+				dv1[0] = __ldg(a.dv1 + mycol); dv1[1] = __ldg(a.dv1 + mycol + 1);
 			}
-			if (valid) {
-				__stcg(reinterpret_cast<double2*>(xp), make_double2(xn0, xn1));
-				if (want_dot) contrib += yo0 * xn0 + yo1 * xn1;
-			}
+			if (need_x1) db_steps<true, true, false, NW>(sc, wid, q, colok, a.U0, k1, dv1);
+			else db_steps<true, false, false, NW>(sc, wid, q, colok, a.U0, k1, dv1);
+		} else if (DOT && pass == last) {
+			contrib = db_steps<false, true, true, NW>(sc, wid, q, colok, 0.0, nullptr, nullptr);
+		} else {
+			db_steps<false, true, false, NW>(sc, wid, q, colok, 0.0, nullptr, nullptr);
 		}
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		DB_TICK(pass == 0 ? 3 : 4);

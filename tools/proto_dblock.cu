@@ -59,13 +59,14 @@ int main(int argc, char** argv)
 {
 	int nx = 4, ny = 4, npart = 8, iters = 10;
 	uint64_t ncols_arg = 0;
-	int lag = 8, ngp = 1, layout = 0;
+	int lag = 8, ngp = 1, layout = 0, want_dot = 0;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--cols")) ncols_arg = strtoull(argv[++i], 0, 10);
 		else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--lag")) lag = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--ng")) ngp = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--layout")) layout = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "--dot")) want_dot = 1;
 		else if (!strcmp(argv[i], "--chain")) { nx = atoi(argv[++i]); ny = 1; npart = nx / 2; }
 	}
 	const int nsite = nx * ny;
@@ -185,6 +186,11 @@ int main(int argc, char** argv)
 	DbArgs a;
 	a.x = dx; a.y = dy; a.pitch = pitch; a.ncols = ncols; a.alpha = alpha; a.beta = beta; a.U0 = U0; a.w1 = dw1; a.dv1 = ddv1; a.tmag = 1.0;
 	a.dot_partials = nullptr;
+	if (want_dot) {
+		const size_t np = ((ncols + DB_COLS - 1) / DB_COLS) * hp.pass[hp.npass - 1].blocks.size();
+		CK(cudaMalloc(&a.dot_partials, np * 8));
+		printf("fused dot: %zu partial sums\n", np);
+	}
 	a.alpha_dev = nullptr;
 	a.beta_dev = nullptr;
 	if (db_launch(dp, a, nsm, 0)) { printf("launch failed\n"); return 1; }
