@@ -356,7 +356,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "x += H y = %s, 24 B/row algorithmic, per GPU; duration = CUDA events around the launches "
                                    "on the engine's stream" % KERNELS.get(args.workload, "engine AUTO kernels"),
-                         "traffic_source": "profiles/traffic_r02.json (ncu --set full, dram read+write of both sweeps)"
+                         "traffic_source": "profiles/traffic_r02.json (ncu --set full, dram read+write of both sweeps: r02/prof_dblock_2cta_raw.csv + prof_sweeps_r02_raw.csv)"
                                            if traffic else None,
                          "ncu_kernels": traffic_kernels},
             "gpu_launches": int(launches), "clocks": clocks,
