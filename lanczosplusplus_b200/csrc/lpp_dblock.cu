@@ -47,9 +47,11 @@ int lpp_dblock_create(const ModelDev& m, const HopTable& dn, const DiagTables& d
 	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
 	DownBlockPlan* p = new DownBlockPlan();
 	std::string err;
-	const char* lay = getenv("LPP_DBLOCK_LAYOUT");                  // 1: one CTA of 1024 threads per SM only (A/B timing)
+	const char* lay = getenv("LPP_DBLOCK_LAYOUT");                  // 1: one CTA of 1024 threads per SM only (A/B timing, tests)
+	const char* psv = getenv("LPP_DBLOCK_PASSES");                  // 2 or 3: exactly that many passes (tests)
+	const int passes = psv ? atoi(psv) : 0;
 	if (!db_build_host_plan(w2.data(), n2, m.nbits, hidx.data(), hval.data(), hcnt.data(), W, dv2.data(), (size_t)maxblk, (size_t)maxsm,
-	                        lay ? atoi(lay) : 0, &p->host, &err)) {
+	                        lay ? atoi(lay) : 0, (passes == 2 || passes == 3) ? passes : 0, &p->host, &err)) {
 		g_dberr = err;
 		delete p;
 		return 1;

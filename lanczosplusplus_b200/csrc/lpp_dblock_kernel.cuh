@@ -3,7 +3,8 @@
 //
 // Pick K sets of sites F_1 .. F_K such that every bond misses at least one of them.  Pass k groups the down states by their
 // occupation of F_k ("blocks") and applies the hops that touch F_1 .. F_{k-1} but not F_k: such a hop cannot leave its block.
-// Two sets do when no bond joins them; three pairwise disjoint sets always do (a bond has two ends).  A tile = (block, 16
+// Two sets do when no bond joins them; three pairwise disjoint sets always do (a bond has two ends; built and tested, but
+// slower than the streaming sweep, so only on request).  A tile = (block, 16
 // columns of the Ndn x Nup matrix) of y is staged in shared memory; each hop operand is a conflict-free 16-byte shared-memory
 // load (the 8 lanes of a state read one 128-byte line).  No operand lies outside the tile: the global traffic is y once and x
 // read + write per pass.  A persistent grid takes tiles from a ticket counter in panel-major order, pass k of a panel LAG
@@ -257,11 +258,13 @@ static bool db_pick_sets(int nbits, const std::vector<uint64_t>& adj, int npass,
 
 // words: one-spin basis (any order), nbits sites; ELL hop table (column-major idx/val, cnt) on the host.
 // smem_block = the opt-in shared-memory limit of one CTA, smem_sm = shared memory of one SM.  layout: 0 = best (two CTAs per
-// SM when some plan fits, else one), 1 = one CTA per SM only (the round-2 first version; kept for A/B timing).
+// SM when some plan fits, else one), 1 = one CTA per SM only (the round-2 first version; kept for A/B timing).  passes: 0 or 2 = two
+// passes; 3 = three passes, on request only: a pass costs about 0.5 ms on config 3 whatever its hop count (y in, x in and out), and
+// three of them (2.52 ms) lose to the streaming sweep (2.09 ms), so a lattice without two separated site sets keeps that sweep.
 // Returns false (with *err) when the block scheme does not apply (then the caller keeps the streaming sweep).
 template <class W>
 static bool db_build_host_plan(const W* words, uint64_t n, int nbits, const uint32_t* idx, const double* val, const uint32_t* cnt, int width,
-                               const double* dv2, size_t smem_block, size_t smem_sm, int layout, DbHostPlan* hp, std::string* err)
+                               const double* dv2, size_t smem_block, size_t smem_sm, int layout, int passes, DbHostPlan* hp, std::string* err)
 {
 	(void)width;
 	if (n == 0 || n >= (1ull << 24)) { *err = "basis size out of range"; return false; }
@@ -288,7 +291,7 @@ static bool db_build_host_plan(const W* words, uint64_t n, int nbits, const uint
 		const size_t per_cta = std::min(smem_block, smem_sm / (size_t)cps);
 		if (per_cta <= fixed + 4096) continue;
 		const size_t budget = per_cta - fixed;
-		for (int npass = 2; npass <= DB_MAX_PASS; npass++)
+		for (int npass = (passes ? passes : 2); npass <= (passes ? passes : 2); npass++)
 			// the smallest number of fixed sites whose largest block fits
 			for (int f = 1; f <= nbits / 2; f++) {
 				uint64_t masks[DB_MAX_PASS] = {0, 0, 0};

@@ -1801,7 +1801,7 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		int rb = lpp_dblock_create(m, dn, dt, s, &p->dblock);
 		if (rb < 0) { g_terr = std::string("down block plan: ") + lpp_dblock_error(); delete p; return -1; }
 		if (getenv("LPP_VERBOSE")) {
-			char buf[256] = "";
+			char buf[640] = "";
 			if (p->dblock) lpp_dblock_describe(p->dblock, buf, sizeof(buf));
 			fprintf(stderr, "[lpp tiled] block down sweep: %s\n", p->dblock ? buf : lpp_dblock_error());
 		}

@@ -10,7 +10,7 @@
 #include <vector>
 #include "../lanczosplusplus_b200/csrc/lpp_dblock_kernel.cuh"
 
-static int run_case(int nx, int ny, int npart, bool periodic, bool potential, int layout = 0)
+static int run_case(int nx, int ny, int npart, bool periodic, bool potential, int layout = 0, int passes = 0)
 {
 	const int nsite = nx * ny;
 	std::vector<uint32_t> words;
@@ -63,7 +63,7 @@ static int run_case(int nx, int ny, int npart, bool periodic, bool potential, in
 	}
 	DbHostPlan hp;
 	std::string err;
-	if (!db_build_host_plan(words.data(), n, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)232448, (size_t)233472, layout, &hp, &err)) {
+	if (!db_build_host_plan(words.data(), n, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)232448, (size_t)233472, layout, passes, &hp, &err)) {
 		std::printf("%dx%d N=%d %s: no plan (%s)\n", nx, ny, npart, periodic ? "pbc" : "open", err.c_str());
 		return nhops == 0 ? 0 : 2;
 	}
@@ -75,6 +75,7 @@ static int run_case(int nx, int ny, int npart, bool periodic, bool potential, in
 			for (int k = 0; k < hp.npass; k++) free_pass = free_pass || !(((hp.fmask[k] >> i) | (hp.fmask[k] >> j)) & 1u);
 			if (!free_pass) { std::printf("FAIL a bond touches the fixed sites of every pass\n"); return 1; }
 		}
+	if (passes && hp.npass != passes) { std::printf("FAIL %d passes asked for, %d planned\n", passes, hp.npass); return 1; }
 	if (hp.smem_bytes + (size_t)hp.max_pos * 8 + 2048 > (size_t)233472 / hp.ctas_per_sm) { std::printf("FAIL plan does not fit %d CTA(s) per SM\n", hp.ctas_per_sm); return 1; }
 	// host walk of the tables (two columns are enough: the kernel treats columns independently)
 	const int ncol = 2;
@@ -172,6 +173,9 @@ int main()
 	bad += run_case(4, 4, 3, true, false);
 	bad += run_case(4, 4, 8, true, true);        // config 3: three passes, two CTAs per SM
 	bad += run_case(4, 4, 8, true, false, 1);    // the same basis in the one-CTA layout (two passes)
+	bad += run_case(4, 4, 8, true, true, 0, 3);  // three passes over three disjoint site sets
+	bad += run_case(4, 3, 6, true, true, 1, 3);  // three passes, one CTA per SM
+	bad += run_case(3, 3, 4, true, false, 0, 3);
 	std::printf(bad ? "FAIL\n" : "OK\n");
 	return bad ? 1 : 0;
 }

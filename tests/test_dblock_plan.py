@@ -28,9 +28,10 @@ def test_block_plan_applies_every_hop_once():
     r = subprocess.run([EXE], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout
     lines = [l for l in r.stdout.splitlines() if "states" in l]
-    assert len(lines) == 9
+    assert len(lines) == 12
     assert "2 CTA/SM" in lines[7] and "max block 464" in lines[7]      # config 3 fits two CTAs per SM
     assert "1 CTA/SM" in lines[8] and "max block 924" in lines[8]
+    assert all("3 passes" in l for l in lines[9:12])                         # the forced three-pass plans
     for l in lines:
         m = re.search(r"hops (\d+) walked (\d+), max diff (\S+) (\w+)", l)
         assert m and m.group(1) == m.group(2) and float(m.group(3)) <= 1e-13 and m.group(4) == "ok", l

@@ -738,6 +738,37 @@ def test_block_down_sweep_cases(lpp, oracle, monkeypatch):
             e.close()
 
 
+@pytest.mark.parametrize("layout,passes", [("1", "0"), ("0", "3"), ("1", "3")])
+def test_block_down_sweep_layouts(lpp, oracle, monkeypatch, capfd, layout, passes):
+    """The code paths of k_dblock that config 3 does not take by default: one CTA of 1024 threads per SM (LPP_DBLOCK_LAYOUT=1, what a
+    lattice gets whose blocks do not fit twice into an SM) and three passes over three disjoint site sets (LPP_DBLOCK_PASSES=3,
+    what a lattice gets that has no two separated site sets), against the oracle: mat-vec with the old x (beta != 0), the fused
+    Lanczos recurrence, and the last panel of a column count that is not a multiple of 16."""
+    monkeypatch.setenv("LPP_DBLOCK_LAYOUT", layout)
+    monkeypatch.setenv("LPP_DBLOCK_PASSES", passes)
+    monkeypatch.setenv("LPP_VERBOSE", "1")                    # the plan is described on stderr: the forced path must be the one that ran
+    want = ("3 passes" if passes == "3" else "2 passes", "1 CTA(s) of 1024 threads" if layout == "1" else "2 CTA(s) of 512 threads")
+    V12 = np.linspace(-0.4, 0.6, 12)
+    for case in (cases.hubbard_square(4, 3, 6, 6), cases.hubbard_chain(12, 5, 6, V=V12), cases.hubbard_square(4, 3, 5, 7)):
+        capfd.readouterr()
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        n = o.rows()
+        y = geo.splitmix64_vector(n, 42)
+        x0 = geo.splitmix64_vector(n, 7)
+        xref = x0.copy()
+        o.matvec(xref, y, faithful=False)
+        e = cases.make_engine(lpp, case)
+        x = x0.copy()
+        e.matrixVectorProduct(x, y, kernel=lpp.KERNEL_TILED)
+        said = [l for l in capfd.readouterr().err.splitlines() if "block down sweep:" in l]
+        assert said and all(w in said[-1] for w in want), said
+        assert relerr(x, xref) <= 1e-13, (case["nsite"], case["nup"], case["ndown"], layout, passes)
+        a, b, _ = lpp.LanczosSolver(e, lpp.ParametersForSolver(steps=12, eps=0.0)).decomposition(y)
+        a0, b0 = o.decomposition(y, steps=12, eps=0.0)
+        assert relerr(a, a0) <= 1e-10 and relerr(b[:-1], b0[:-1]) <= 1e-10
+        e.close()
+
+
 def test_many_point_matches_oracle_chain(lpp, oracle):
     """Engine::manyPoint (Engine.h:341-389): <gs| O_n ... O_1 |gs> through the chain of sectors, on the device, against the
     oracle's accModifiedState_ restatement applied step by step (same ground-state vector on both sides); also against

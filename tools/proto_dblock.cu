@@ -59,7 +59,7 @@ int main(int argc, char** argv)
 {
 	int nx = 4, ny = 4, npart = 8, iters = 10;
 	uint64_t ncols_arg = 0;
-	int lag = 8, ngp = 1, layout = 0, want_dot = 0;
+	int lag = 8, ngp = 1, layout = 0, want_dot = 0, passes = 0;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--cols")) ncols_arg = strtoull(argv[++i], 0, 10);
 		else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
@@ -67,6 +67,7 @@ int main(int argc, char** argv)
 		else if (!strcmp(argv[i], "--ng")) ngp = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--layout")) layout = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--dot")) want_dot = 1;
+		else if (!strcmp(argv[i], "--passes")) passes = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--chain")) { nx = atoi(argv[++i]); ny = 1; npart = nx / 2; }
 	}
 	const int nsite = nx * ny;
@@ -128,7 +129,7 @@ int main(int argc, char** argv)
 	std::vector<double> dv2(n2, 0.0);
 	DbHostPlan hp;
 	std::string err;
-	if (!db_build_host_plan(words.data(), n2, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)maxblk, (size_t)maxsm, layout, &hp, &err)) {
+	if (!db_build_host_plan(words.data(), n2, nsite, idx.data(), val.data(), cnt.data(), width, dv2.data(), (size_t)maxblk, (size_t)maxsm, layout, passes, &hp, &err)) {
 		printf("plan failed: %s\n", err.c_str());
 		return 1;
 	}
