@@ -142,6 +142,14 @@ struct lpp_handle {
 	cudaStream_t copy_streams[4] = {};    // extra copy streams of the pack: the remote blocks go out on several copy engines
 	cudaEvent_t ev_copies[4] = {};
 	const double* packed_vec = nullptr;   // vector whose column-shard copy (ycol on every rank) is already in place
+	// pipelined two-layout recurrence (lanczos_pipelined): third work vector, norm partials of the unpack in flight, streams
+	double* vz = nullptr;
+	double* partials3 = nullptr;
+	int partials3_cap = 0;
+	cudaStream_t pipe_up[2] = {};          // the up-sweep chunks alternate between two high-priority streams (the second fills the tail waves of the first)
+	cudaStream_t pipe_unpack = nullptr;    // the unpack chunks (low priority: they fill in beside the up sweep)
+	cudaEvent_t ev_pipe_chunk[8] = {};     // unpack of chunk k has written its rows of the new vector
+	cudaEvent_t ev_pipe_dot = nullptr, ev_pipe_up[2] = {}, ev_pipe_y = nullptr;
 	int phases = -1;
 	cudaEvent_t pev[8] = {};
 	cudaEvent_t cev[2] = {};      // around the pack on the second stream
@@ -285,6 +293,14 @@ extern "C" int lpp_destroy(lpp_handle* h)
 	if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
 	if (h->copy_stream2) cudaStreamDestroy(h->copy_stream2);
 	if (h->ev_copy2) cudaEventDestroy(h->ev_copy2);
+	for (int k = 0; k < 4; k++) {
+		if (h->copy_streams[k]) cudaStreamDestroy(h->copy_streams[k]);
+		if (h->ev_copies[k]) cudaEventDestroy(h->ev_copies[k]);
+	}
+	for (cudaStream_t st : h->pipe_up) if (st) cudaStreamDestroy(st);
+	if (h->pipe_unpack) cudaStreamDestroy(h->pipe_unpack);
+	for (cudaEvent_t e : h->ev_pipe_chunk) if (e) cudaEventDestroy(e);
+	for (cudaEvent_t e : {h->ev_pipe_dot, h->ev_pipe_up[0], h->ev_pipe_up[1], h->ev_pipe_y}) if (e) cudaEventDestroy(e);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	delete h;
 	return 0;
@@ -1205,6 +1221,196 @@ struct LoopTiming {
 	int64_t launches_at_from = 0, launches_at_to = 0;
 };
 
+// The sharded recurrence with the exchange pipelined behind the sweeps (peer-memory two-layout handles, device-resident scalars).
+// In lanczos_loop's plain form an iteration is a chain  [pack || up sweep] -> down sweep -> unpack -> norm all-reduce -> next,
+// and the unpack (remote loads over NVLink) overlaps with nothing.  Here the sweeps run with alpha = 1, beta = 0 (the up sweep into
+// a third vector z), and every scalar enters in the unpack:  U_{j+1} = (z + pieces)/n_j - (a_j/n_j) U_j - (b_j/n_{j-1}) U_{j-1}.
+// |U_{j+1}| is then needed by the NEXT unpack only, so the next up sweep and the next pack start chunk by chunk of rows as soon
+// as the unpack has written them, and the norm rides on the all-reduce that doubles as the "packs have landed" barrier:
+//   S   : up(c0) up(c2) ..          | all-reduce A {norm of the previous unpack} | down sweep | all-reduce B {dot}
+//   S2  :    up(c1) up(c3) ..       |
+//   DMA :  pack(c0) pack(c1) ..     |                                             (copy engines, into the peers' column shards)
+//   U   :                                                                          unpack(c0) unpack(c1) ..   -> events per chunk
+// Buffer safety: a peer overwrites my ycol (its next pack) only after all-reduce B of this iteration, which I enter after my
+// down sweep; I overwrite xcol (my next down sweep) only after all-reduce A of the next iteration, which every peer enters
+// after its up sweeps, i.e. after all of its unpack chunks.  All all-reduces are issued on S, in the same order on every rank.
+static int lanczos_pipelined(lpp_handle* h, const lpp_solver_params* p, int steps, bool check_convergence, double nj0, double* x, double* y,
+                             double* a, double* b, int* nsteps, LoopTiming* tm, int nchunks)
+{
+	NvtxRange nvtx("lpp:lanczos pipelined");
+	cudaStream_t S = h->stream;
+	const int G = h->desc.nranks, me = h->desc.rank;
+	const uint64_t n1 = h->md.n1, nrows = h->nloc / n1, d0loc = h->row0 / n1, ncme = h->ncols;
+	if (!h->vz) CKR(dev_alloc(h, &h->vz, h->nloc));
+	const int gy = lpp_unpack3_partials_per_row(n1);
+	const int npb = (int)nrows * gy;
+	if (h->partials3_cap < npb) {
+		if (h->partials3) dev_free(h, h->partials3);
+		h->partials3 = nullptr;
+		CKR(dev_alloc(h, &h->partials3, (size_t)npb));
+		h->partials3_cap = npb;
+	}
+	if (!h->pipe_unpack) {
+		int least = 0, greatest = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+		for (int k = 0; k < 2; k++) {
+			CK(cudaStreamCreateWithPriority(&h->pipe_up[k], cudaStreamNonBlocking, greatest));
+			CK(cudaEventCreateWithFlags(&h->ev_pipe_up[k], cudaEventDisableTiming));
+		}
+		CK(cudaStreamCreateWithPriority(&h->pipe_unpack, cudaStreamNonBlocking, least));
+		for (cudaEvent_t& e : h->ev_pipe_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->ev_pipe_dot, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->ev_pipe_y, cudaEventDisableTiming));
+	}
+	// the unpack runs beside the next up sweep; LPP_PIPE_UNPACK_CPS = n limits its grid to n CTAs per SM striding over the rows.
+	// Measured on 2 x B200 (config 3, 4 chunks): 1 / 2 / 4 CTAs per SM 5.12 / 3.75 / 3.08 ms per iteration, no limit 2.88 ms
+	static const int unpack_cps = getenv("LPP_PIPE_UNPACK_CPS") ? atoi(getenv("LPP_PIPE_UNPACK_CPS")) : 0;
+	int nsm = 148;
+	CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device));
+	const int unpack_rows = unpack_cps > 0 ? std::max(1, unpack_cps * nsm / std::max(1, lpp_unpack3_partials_per_row(n1))) : 0;
+	const int ncopy = 4;
+	for (int k = 0; k < ncopy; k++)
+		if (!h->copy_streams[k]) {
+			CK(cudaStreamCreateWithFlags(&h->copy_streams[k], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&h->ev_copies[k], cudaEventDisableTiming));
+		}
+	// chunks of rows (even sizes: the up sweep takes two rows per CTA)
+	nchunks = std::max(1, std::min(nchunks, 8));
+	uint64_t cb[9];
+	for (int k = 0; k <= nchunks; k++) cb[k] = std::min(nrows, ((nrows * (uint64_t)k / (uint64_t)nchunks) + 1) & ~(uint64_t)1);
+	cb[nchunks] = nrows;
+	const int nbB = lpp_tiled_up_rows_blocks(h->tiled, nrows);
+	int up_blocks_before[9];
+	up_blocks_before[0] = 0;
+	for (int k = 0; k < nchunks; k++) up_blocks_before[k + 1] = up_blocks_before[k] + lpp_tiled_up_rows_blocks(h->tiled, cb[k + 1] - cb[k]);
+	CKR(ensure_partials(h, std::max(std::max(nbB, up_blocks_before[nchunks]), lpp_vec_blocks(h->nloc))));
+	double* coefs = h->lz_coefs;
+	double* a_dev = h->lz_ab;
+	double* b_dev = h->lz_ab + h->lz_ab_cap;
+	double* z = h->vz;
+	lpp_launch_lzp_init(nj0, coefs, S);
+	h->launches += 1;
+	const bool watch = check_convergence && p->eps > 0;
+	static const int sync_env = getenv("LPP_SYNC_EVERY") ? atoi(getenv("LPP_SYNC_EVERY")) : 0;
+	const int sync_every = std::max(1, sync_env > 0 ? sync_env : (watch ? 8 : 32));
+	bool in_flight = false;          // unpack chunks of the previous iteration are (possibly) still running on pipe_unpack
+	bool norm_pending = false;       // their norm partials have not been reduced yet
+	double eold = 100.0;
+	int j = 0;
+	bool stop = false;
+	// S waits for every unpack chunk, reduces the pending norm over the ranks (n = 1) or just meets them (n = 0)
+	auto close_norm = [&](bool barrier_anyway) -> int {
+		if (in_flight)
+			for (int k = 0; k < nchunks; k++) CK(cudaStreamWaitEvent(S, h->ev_pipe_chunk[k], 0));
+		in_flight = false;
+		if (norm_pending) {
+			lpp_launch_finalize_sum(h->partials3, npb, h->scal_dev + 2, S);
+			CKR(allreduce_small(h, h->scal_dev + 2, 1, S));
+			lpp_launch_lzp_after_norm(h->scal_dev + 2, coefs, b_dev, S);
+			h->launches += 2;
+			norm_pending = false;
+		} else if (barrier_anyway) {
+			CKR(allreduce_small(h, h->scal_dev + 4, 0, S));
+		}
+		return 0;
+	};
+	while (j < steps && !stop) {
+		const int j0 = j, j1 = std::min(steps, j + sync_every);
+		for (int jj = j0; jj < j1; jj++) {
+			if (tm && jj == tm->from) {
+				CKR(close_norm(false));                           // the timed region starts with nothing in flight
+				CK(cudaEventRecord(h->ev0, S));
+				tm->launches_at_from = h->launches;
+			}
+			// ---- up sweep (z = T_up y) and pack (y -> the peers' column shards), chunk by chunk behind the previous unpack
+			CK(cudaEventRecord(h->ev_pipe_y, S));                  // everything S has done so far (y final when nothing is in flight)
+			for (int k = 0; k < 2; k++) CK(cudaStreamWaitEvent(h->pipe_up[k], h->ev_pipe_y, 0));
+			if (!in_flight)
+				for (int k = 0; k < ncopy; k++) CK(cudaStreamWaitEvent(h->copy_streams[k], h->ev_pipe_y, 0));
+			int ncp = 0;
+			for (int k = 0; k < nchunks; k++) {
+				const uint64_t r0 = cb[k], nr = cb[k + 1] - cb[k];
+				if (nr == 0) continue;
+				cudaStream_t us = h->pipe_up[k & 1];
+				if (in_flight) {
+					CK(cudaStreamWaitEvent(us, h->ev_pipe_chunk[k], 0));
+					for (int c = 0; c < ncopy; c++) CK(cudaStreamWaitEvent(h->copy_streams[c], h->ev_pipe_chunk[k], 0));
+				}
+				SpmvArgs ab;
+				ab.alpha = 1.0; ab.beta = 0.0; ab.x = z + r0 * n1; ab.y = y + r0 * n1; ab.row0 = 0; ab.nloc = nr * n1;
+				ab.dot_partials = h->partials + up_blocks_before[k];
+				if (lpp_tiled_sweep_up_rows(h->tiled, h->md, ab, nr, us) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+				for (int q = 0; q < G; q++) {
+					const int qq = (me + q) % G;
+					const uint64_t ncq = h->cols.cs[qq + 1] - h->cols.cs[qq];
+					if (ncq == 0) continue;
+					CK(cudaMemcpy2DAsync(h->peer_ycol.p[qq] + (d0loc + r0) * ncq, ncq * sizeof(double), y + r0 * n1 + h->cols.cs[qq], n1 * sizeof(double),
+					                     ncq * sizeof(double), nr, cudaMemcpyDefault, h->copy_streams[ncp % ncopy]));
+					ncp++;
+				}
+			}
+			for (int k = 0; k < 2; k++) {
+				CK(cudaEventRecord(h->ev_pipe_up[k], h->pipe_up[k]));
+				CK(cudaStreamWaitEvent(S, h->ev_pipe_up[k], 0));
+			}
+			for (int k = 0; k < ncopy; k++) {
+				CK(cudaEventRecord(h->ev_copies[k], h->copy_streams[k]));
+				CK(cudaStreamWaitEvent(S, h->ev_copies[k], 0));
+			}
+			h->launches += nchunks;
+			// ---- all-reduce A: the norm of the vector the previous unpack built; every rank's pack has landed behind it
+			in_flight = false;                                   // S has waited for every chunk through its up sweeps
+			CKR(close_norm(true));
+			// ---- down sweep on the column shard, dot = <y, z> + <ycol, xcol>
+			SpmvArgs aa;
+			aa.alpha = 1.0; aa.beta = 0.0; aa.x = h->xcol; aa.y = h->ycol; aa.row0 = 0; aa.nloc = h->md.n2 * ncme;
+			aa.dot_partials = h->partials2;
+			if (lpp_tiled_sweep_down_cols(h->tiled, h->md, h->dn, h->dt, aa, h->ucol0, ncme, S) < 0) return fail(LPP_ERR_CUDA, lpp_tiled_error());
+			lpp_launch_finalize_sum(h->partials, up_blocks_before[nchunks], h->scal_dev, S);
+			lpp_launch_finalize_sum(h->partials2, h->partials2_cap, h->scal_dev + 1, S);
+			CKR(allreduce_small(h, h->scal_dev, 2, S));            // also: every rank's xcol is final
+			lpp_launch_lzp_after_dot(h->scal_dev, coefs, a_dev, S);
+			h->launches += 4;
+			// ---- unpack: x = C1 (z + pieces) - C2 y - C3 x, chunk by chunk on its own stream
+			CK(cudaEventRecord(h->ev_pipe_dot, S));
+			CK(cudaStreamWaitEvent(h->pipe_unpack, h->ev_pipe_dot, 0));
+			for (int k = 0; k < nchunks; k++) {
+				const uint64_t r0 = cb[k], nr = cb[k + 1] - cb[k];
+				lpp_launch_unpack3_norm_p2p(x + r0 * n1, y + r0 * n1, z + r0 * n1, coefs, h->peer_xcol, nr, n1, h->cols, d0loc + r0,
+				                            h->partials3 + r0 * (uint64_t)gy, unpack_rows, h->pipe_unpack);
+				CK(cudaEventRecord(h->ev_pipe_chunk[k], h->pipe_unpack));
+			}
+			h->launches += nchunks;
+			in_flight = true;
+			norm_pending = true;
+			if (tm && jj + 1 == tm->to) {
+				CKR(close_norm(false));                           // the timed region ends with the iteration complete, b_j included
+				CK(cudaEventRecord(h->ev1, S));
+				tm->launches_at_to = h->launches;
+			}
+			std::swap(x, y);
+		}
+		CKR(close_norm(false));
+		CK(cudaMemcpyAsync(h->lz_ab_host + j0, a_dev + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, S));
+		CK(cudaMemcpyAsync(h->lz_ab_host + h->lz_ab_cap + j0, b_dev + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, S));
+		CK(cudaStreamSynchronize(S));
+		if (h->psx_err && *h->psx_err) return fail(LPP_ERR_STATE, "peer-memory scalar exchange timed out (a rank did not arrive)");
+		for (j = j0; j < j1; j++) {
+			a[j] = h->lz_ab_host[j];
+			b[j] = h->lz_ab_host[h->lz_ab_cap + j];
+			if (watch && j >= h->conv_index) {
+				double enew = tridiag_kth(j + 1, a, b, h->conv_index);
+				if (fabs(enew - eold) < p->eps && (j >= p->minsteps || h->rows <= 4)) { j++; stop = true; break; }
+				eold = enew;
+			}
+		}
+	}
+	*nsteps = j;
+	h->packed_vec = nullptr;
+	CK(cudaGetLastError());
+	return 0;
+}
+
 // PsimagLite::LanczosSolver::decomposition with the three vector sweeps fused into two:
 // the dot <y,x> rides on the SpMV epilogue, the swap/scale sweep is folded into scalar coefficients.
 // State: y = U_j (unnormalised Lanczos vector, v_j = U_j/n_j), x = U_{j-1}.
@@ -1250,7 +1456,7 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 	static const bool dev_scalars_on = !(getenv("LPP_DEV_SCALARS") && getenv("LPP_DEV_SCALARS")[0] == '0');
 	const bool nccl_two_layout = h->two_layout == 1 && !h->p2p;      // send/recv exchange keeps its own host synchronisation
 	if (dev_scalars_on && !reortho && !zcoef && !nccl_two_layout && (h->desc.nranks == 1 || h->comm)) {
-		if (!h->lz_coefs) CKR(dev_alloc(h, &h->lz_coefs, 8));
+		if (!h->lz_coefs) CKR(dev_alloc(h, &h->lz_coefs, 16));
 		if (h->lz_ab_cap < steps) {
 			if (h->lz_ab) dev_free(h, h->lz_ab);
 			if (h->lz_ab_host) cudaFreeHost(h->lz_ab_host);
@@ -1259,6 +1465,16 @@ static int lanczos_loop(lpp_handle* h, const lpp_solver_params* p, int steps, bo
 			CKR(dev_alloc(h, &h->lz_ab, 2 * (size_t)steps));
 			CK(cudaMallocHost((void**)&h->lz_ab_host, 2 * (size_t)steps * sizeof(double)));
 			h->lz_ab_cap = steps;
+		}
+		// LPP_PIPELINE=<chunks>: the exchange pipelined behind the sweeps (lanczos_pipelined); peer-memory two-layout handles whose
+		// column split is even (16-byte accesses).  Opt-in: on 2 x B200 it is slower than the plain chain (2.85-2.94 ms against
+		// 2.63 ms per iteration of config 3) -- the unpack needs the whole GPU to run at NVLink speed, beside the up sweep both slow down
+		{
+			static const int pipe_chunks = getenv("LPP_PIPELINE") ? atoi(getenv("LPP_PIPELINE")) : 0;
+			bool even = (h->md.n1 % 2 == 0) && reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0;
+			if (h->two_layout == 1) for (int q = 0; q <= h->desc.nranks; q++) even = even && (h->cols.cs[q] % 2 == 0);
+			if (pipe_chunks > 0 && h->two_layout == 1 && h->p2p && even && h->nloc / h->md.n1 >= (uint64_t)(4 * pipe_chunks))
+				return lanczos_pipelined(h, p, steps, check_convergence, nj, x, y, a, b, nsteps, tm, pipe_chunks);
 		}
 		double* coefs = h->lz_coefs;
 		double* a_dev = h->lz_ab;

@@ -686,6 +686,41 @@ __global__ void k_lz_after_norm(const double* __restrict__ b2, double* coefs, do
 	coefs[LPP_LZ_BETA] = -(bj / nprev);
 	coefs[LPP_LZ_STEP] = (double)(j + 1);
 }
+__global__ void k_lzp_init(double nj, double* coefs)
+{
+	coefs[LPP_LZ_NORM] = nj;
+	coefs[LPP_LZP_C1] = 1.0 / nj;
+	coefs[LPP_LZP_C2] = 0.0;
+	coefs[LPP_LZP_C3] = 0.0;
+	coefs[LPP_LZP_STEPA] = 0.0;
+	coefs[LPP_LZP_STEPB] = 0.0;
+}
+// dot_parts[0] + dot_parts[1] = <y, H y> with y = U_j = n_j v_j:  a_j = dot / n_j^2
+__global__ void k_lzp_after_dot(const double* __restrict__ dot_parts, double* coefs, double* __restrict__ a_out)
+{
+	const double nj = coefs[LPP_LZ_NORM];
+	const double aj = (dot_parts[0] + dot_parts[1]) / nj / nj;
+	const int j = (int)coefs[LPP_LZP_STEPA];
+	a_out[j] = aj;
+	coefs[LPP_LZP_C1] = 1.0 / nj;
+	coefs[LPP_LZP_C2] = aj / nj;
+	coefs[LPP_LZP_STEPA] = (double)(j + 1);
+}
+// *b2 = |U_{j+1}|^2:  b_j = its root, the next n, and the weight b_j / n_j of U_j in the step after
+__global__ void k_lzp_after_norm(const double* __restrict__ b2, double* coefs, double* __restrict__ b_out)
+{
+	const double bj = sqrt(*b2);
+	const int j = (int)coefs[LPP_LZP_STEPB];
+	b_out[j] = bj;
+	const double nprev = coefs[LPP_LZ_NORM];
+	const double nj = (bj < 1e-10) ? 1.0 : bj;
+	coefs[LPP_LZ_NORM] = nj;
+	coefs[LPP_LZP_C3] = bj / nprev;
+	coefs[LPP_LZP_STEPB] = (double)(j + 1);
+}
+void lpp_launch_lzp_init(double nj, double* coefs, cudaStream_t s) { k_lzp_init<<<1, 1, 0, s>>>(nj, coefs); }
+void lpp_launch_lzp_after_dot(const double* dot_parts, double* coefs, double* a_out, cudaStream_t s) { k_lzp_after_dot<<<1, 1, 0, s>>>(dot_parts, coefs, a_out); }
+void lpp_launch_lzp_after_norm(const double* b2, double* coefs, double* b_out, cudaStream_t s) { k_lzp_after_norm<<<1, 1, 0, s>>>(b2, coefs, b_out); }
 void lpp_launch_lz_init(double nj, double* coefs, cudaStream_t s) { k_lz_init<<<1, 1, 0, s>>>(nj, coefs); }
 void lpp_launch_lz_after_dot(const double* dot_parts, int nparts, double* coefs, double* a_out, cudaStream_t s)
 {
@@ -879,6 +914,54 @@ __global__ void __launch_bounds__(LPP_TPB) k_unpack_axpy_norm_p2p_v2(double* __r
 	if (threadIdx.x == 0) partials[(uint64_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
 }
 
+// Pipelined recurrence: x = C1 (z + pieces) - C2 y - C3 x on a block of rows, 16-byte accesses, column walk rotated per rank as in
+// k_unpack_axpy_norm_p2p_v2; partial sums of squares per (row, column chunk).
+__global__ void __launch_bounds__(LPP_TPB) k_unpack3_norm_p2p(double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                                                             const double* __restrict__ coefs, const __grid_constant__ PeerPtrs xcols,
+                                                             uint64_t nrows, uint64_t n1, const __grid_constant__ ColSplit c, uint64_t d0loc,
+                                                             double* __restrict__ partials)
+{
+	const double c1 = coefs[LPP_LZP_C1], c2 = coefs[LPP_LZP_C2], c3 = coefs[LPP_LZP_C3];
+	const bool use_x = c3 != 0.0;                     // first step: x is uninitialised memory, not a vector
+	const uint64_t npair = n1 >> 1;
+	const uint64_t stride = (uint64_t)gridDim.y * LPP_TPB;
+	const uint64_t rot = c.cs[(c.me + 1) % c.nranks] >> 1;
+	// the grid may hold fewer CTA rows than the block has matrix rows (a small footprint beside the up sweep): stride over the rows
+	for (uint64_t r = blockIdx.x; r < nrows; r += gridDim.x) {
+		double2* __restrict__ xrow = reinterpret_cast<double2*>(x + r * n1);
+		const double2* __restrict__ yrow = reinterpret_cast<const double2*>(y + r * n1);
+		const double2* __restrict__ zrow = reinterpret_cast<const double2*>(z + r * n1);
+		double s = 0.0;
+		for (uint64_t l0 = (uint64_t)blockIdx.y * LPP_TPB + threadIdx.x; l0 < npair; l0 += 2 * stride) {
+			const uint64_t l1 = l0 + stride;
+			const bool two = l1 < npair;
+			uint64_t p0 = l0 + rot, p1 = (two ? l1 : l0) + rot;
+			if (p0 >= npair) p0 -= npair;
+			if (p1 >= npair) p1 -= npair;
+			const uint64_t u0 = 2 * p0, u1 = 2 * p1;
+			const int q0 = lpp_col_owner(c, u0), q1 = lpp_col_owner(c, u1);
+			const uint64_t nc0 = c.cs[q0 + 1] - c.cs[q0], nc1 = c.cs[q1 + 1] - c.cs[q1];
+			const double2 r0 = *reinterpret_cast<const double2*>(xcols.p[q0] + (d0loc + r) * nc0 + (u0 - c.cs[q0]));
+			const double2 r1 = *reinterpret_cast<const double2*>(xcols.p[q1] + (d0loc + r) * nc1 + (u1 - c.cs[q1]));
+			const double2 ya = yrow[p0], za = zrow[p0];
+			const double2 xa = use_x ? xrow[p0] : make_double2(0.0, 0.0);
+			const double2 va = make_double2(c1 * (za.x + r0.x) - c2 * ya.x - c3 * xa.x, c1 * (za.y + r0.y) - c2 * ya.y - c3 * xa.y);
+			xrow[p0] = va;
+			s += va.x * va.x + va.y * va.y;
+			if (two) {
+				const double2 yb = yrow[p1], zb = zrow[p1];
+				const double2 xb = use_x ? xrow[p1] : make_double2(0.0, 0.0);
+				const double2 vb = make_double2(c1 * (zb.x + r1.x) - c2 * yb.x - c3 * xb.x, c1 * (zb.y + r1.y) - c2 * yb.y - c3 * xb.y);
+				xrow[p1] = vb;
+				s += vb.x * vb.x + vb.y * vb.y;
+			}
+		}
+		s = lpp_block_sum(s);
+		if (threadIdx.x == 0) partials[r * gridDim.y + blockIdx.y] = s;
+		__syncthreads();                               // lpp_block_sum's shared scratch is reused by the next row
+	}
+}
+
 __global__ void __launch_bounds__(32) k_psx_allreduce(double* __restrict__ vals, int nvals, const __grid_constant__ PeerPtrs areas, int me,
                                                       int nranks, unsigned long long seq, int* __restrict__ err)
 {
@@ -957,6 +1040,15 @@ void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, co
 	else k_unpack_axpy_norm_p2p<false><<<g, LPP_TPB, 0, s>>>(x, y, coef, coef_dev, xcols, yc, nrows, n1, c, d0loc, partials);
 }
 
+int lpp_unpack3_partials_per_row(uint64_t n1) { return (int)lpp_rowwise_grid(1, n1).y; }
+void lpp_launch_unpack3_norm_p2p(double* x, const double* y, const double* z, const double* coefs, const PeerPtrs& xcols, uint64_t nrows,
+                                 uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, int max_cta_rows, cudaStream_t s)
+{
+	if (nrows == 0) return;
+	dim3 g = lpp_rowwise_grid(nrows, n1);
+	if (max_cta_rows > 0 && g.x > (unsigned)max_cta_rows) g.x = (unsigned)max_cta_rows;
+	k_unpack3_norm_p2p<<<g, LPP_TPB, 0, s>>>(x, y, z, coefs, xcols, nrows, n1, c, d0loc, partials);
+}
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,
                           uint64_t d0loc, cudaStream_t s)
 {

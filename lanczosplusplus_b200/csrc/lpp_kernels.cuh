@@ -129,6 +129,23 @@ void lpp_launch_unpack_axpy_norm_p2p(double* x, const double* y, double coef, co
 #define LPP_LZ_NORM 3
 #define LPP_LZ_STEP 4
 void lpp_launch_lz_init(double nj, double* coefs, cudaStream_t s);
+// Pipelined two-layout recurrence (lanczos_loop, LPP_PIPELINE): the sweeps run with alpha = 1, beta = 0 into a third buffer z and
+// every scalar enters in the fused unpack, U_{j+1} = C1 (z + column-shard pieces) - C2 y - C3 x with C1 = 1/n_j, C2 = a_j/n_j,
+// C3 = b_j/n_{j-1}.  The norm of U_{j+1} is only needed by the NEXT unpack, so the next up sweep and pack start chunk by chunk
+// behind the unpack instead of after its all-reduce.  coefs slots (the array has 16 doubles):
+#define LPP_LZP_C1 8
+#define LPP_LZP_C2 9
+#define LPP_LZP_C3 10
+#define LPP_LZP_STEPA 11      // next index of a[]
+#define LPP_LZP_STEPB 12      // next index of b[]
+void lpp_launch_lzp_init(double nj, double* coefs, cudaStream_t s);
+void lpp_launch_lzp_after_dot(const double* dot_parts, double* coefs, double* a_out, cudaStream_t s);
+void lpp_launch_lzp_after_norm(const double* b2, double* coefs, double* b_out, cudaStream_t s);
+// rows [0, nrows) of the blocks x, y, z handed in (the caller offsets the pointers and d0loc for a chunk of rows):
+// x = C1 (z + pieces of the peers' column-shard results) - C2 y - C3 x, partials[r * gy + chunk] = sum of squares
+int lpp_unpack3_partials_per_row(uint64_t n1);
+void lpp_launch_unpack3_norm_p2p(double* x, const double* y, const double* z, const double* coefs, const PeerPtrs& xcols, uint64_t nrows,
+                                 uint64_t n1, const ColSplit& c, uint64_t d0loc, double* partials, int max_cta_rows, cudaStream_t s);
 void lpp_launch_lz_after_dot(const double* dot_parts, int nparts, double* coefs, double* a_out, cudaStream_t s);
 void lpp_launch_lz_after_norm(const double* b2, double* coefs, double* b_out, cudaStream_t s);
 void lpp_launch_pack_cols(const double* src, double* sendbuf, double* ycol, uint64_t nrows, uint64_t n1, const ColSplit& c,

@@ -709,6 +709,12 @@ def test_multi_gpu_matches_single(lpp):
     r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL OK" in r.stdout
+    # the same cases through the opt-in pipelined recurrence (LPP_PIPELINE: unpack of step j beside the up sweep of step j+1)
+    env = dict(os.environ, LPP_PIPELINE="3", LPP_CHECK_FULL="0")
+    cmd[cmd.index("29731")] = "29733"
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ALL OK" in r.stdout
 
 
 def test_block_down_sweep_cases(lpp, oracle, monkeypatch):
