@@ -68,6 +68,26 @@ class ClockSampler:
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
+        self.skip = 0
+
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms before its first line; a 100 ms timed region could end without a sample.  Wait for
+        the first line and drop what was sampled before the load starts."""
+        if self.p is None:
+            return
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.01)
+        try:
+            with open(self.f.name) as g:
+                self.skip = len(g.read().splitlines())
+        except OSError:
+            self.skip = 0
 
     def stop(self):
         if self.p is None:
@@ -79,7 +99,7 @@ class ClockSampler:
         self.f.seek(0)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().strip().splitlines():
+        for line in self.f.read().strip().splitlines()[self.skip:]:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 8:
                 continue
@@ -305,9 +325,10 @@ def main():
     spmv_ms, spmv_launches = eng.bench_spmv(args.steps, args.warmup)
     spmv_ms = maxranks(spmv_ms)
     # --- the step: one Lanczos iteration, device resident, CUDA events on the engine's stream, max over ranks
-    barrier()
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    barrier()
     iter_ms, launches = eng.bench_lanczos(args.steps, args.warmup)
     barrier()
     clocks = sampler.stop() if rank == 0 else None

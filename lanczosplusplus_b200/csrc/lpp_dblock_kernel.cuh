@@ -403,6 +403,9 @@ static void db_free_plan(DbDevPlan* dp)
 #ifndef DB_SKIP_PADDING
 #define DB_SKIP_PADDING 0                // 1: predicate padded operands off (measured 1.92 ms against 1.88 ms without)
 #endif
+#ifndef DB_RED_LATER_PASSES
+#define DB_RED_LATER_PASSES 1           // the passes after the first add into x with red.global.add.f64 instead of load + store (1.741 -> 1.711 ms); 0: load + store
+#endif
 #ifndef DB_FILL_MODE
 #define DB_FILL_MODE 0                  // 0: 16-byte cp.async per thread; 2: one 128-byte bulk copy (TMA) per state on the tile's mbarrier
 #endif
@@ -533,6 +536,14 @@ __device__ __forceinline__ double db_steps(const DbStepCtx& sc, int wid, int q, 
 			xn1 = xo.y + sc.alpha * h1;
 		}
 		if (valid) {
+#if DB_RED_LATER_PASSES
+			if (!FIRST && !READX) {
+				// x += alpha h as two reductions at L2 (one add per element, so the result equals load + add + store bit for bit):
+				// the pass does not read x at all
+				asm volatile("red.global.add.f64 [%0], %1;" ::"l"(xp), "d"(xn0) : "memory");
+				asm volatile("red.global.add.f64 [%0], %1;" ::"l"(xp + 1), "d"(xn1) : "memory");
+			} else
+#endif
 			__stcg(reinterpret_cast<double2*>(xp), make_double2(xn0, xn1));
 			if (DOTNOW) contrib += yo0 * xn0 + yo1 * xn1;
 		}
@@ -706,7 +717,11 @@ __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1)) k_dblock(const DbKern
 		} else if (DOT && pass == last) {
 			contrib = db_steps<false, true, true, NW>(sc, wid, q, colok, 0.0, nullptr, nullptr);
 		} else {
+#if DB_RED_LATER_PASSES
+			db_steps<false, false, false, NW>(sc, wid, q, colok, 0.0, nullptr, nullptr);
+#else
 			db_steps<false, true, false, NW>(sc, wid, q, colok, 0.0, nullptr, nullptr);
+#endif
 		}
 		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		DB_TICK(pass == 0 ? 3 : 4);
