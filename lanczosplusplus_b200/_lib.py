@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "liblpp_b200.so")
 SOURCES = ["lpp_kernels.cu", "lpp_tiled.cu", "lpp_dtile.cu", "lpp_dblock.cu", "lpp_engine.cu"]
 HEADERS = ["lpp_device.cuh", "lpp_kernels.cuh", "lpp_tiled.cuh", "lpp_dtile.cuh", "lpp_dblock.cuh", "lpp_dblock_kernel.cuh",
-           "lpp_sweep_common.cuh", "lpp_setup.h"]
+           "lpp_sweep_common.cuh", "lpp_smem_attr.cuh", "lpp_setup.h"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
               "-shared"]
 

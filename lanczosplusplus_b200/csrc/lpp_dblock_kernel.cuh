@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
+#include "lpp_smem_attr.cuh"
 
 #define DB_MAX_PASS 3
 #define DB_COLS 16
@@ -757,8 +758,8 @@ template <int NT>
 static int db_launch_nt(DbDevPlan& dp, const DbKernelArgs& ka, unsigned grid, size_t smem, bool dot, cudaStream_t s)
 {
 	if (!dp.attr_set) {
-		if (cudaFuncSetAttribute(k_dblock<false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-		if (cudaFuncSetAttribute(k_dblock<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+		if (lpp_raise_smem(k_dblock<false, NT>, (size_t)(smem)) != cudaSuccess) return -1;
+		if (lpp_raise_smem(k_dblock<true, NT>, (size_t)(smem)) != cudaSuccess) return -1;
 		dp.attr_set = true;
 	}
 	if (dot) k_dblock<true, NT><<<grid, NT, smem, s>>>(ka);

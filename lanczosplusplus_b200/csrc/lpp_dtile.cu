@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 #include "lpp_dtile.cuh"
+#include "lpp_smem_attr.cuh"
 
 static thread_local std::string g_derr;
 const char* lpp_dtile_error() { return g_derr.c_str(); }
@@ -523,8 +524,8 @@ int lpp_dtile_create(const ModelDev& m, const HopTable& dn, const double* dv2_de
 		return -1;
 	}
 	p->dev.rec = reinterpret_cast<const uint4*>(recdev);
-	cudaError_t e1 = cudaFuncSetAttribute(k_down_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
-	cudaError_t e2 = cudaFuncSetAttribute(k_down_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem);
+	cudaError_t e1 = lpp_raise_smem(k_down_tile<true>, (size_t)(p->smem));
+	cudaError_t e2 = lpp_raise_smem(k_down_tile<false>, (size_t)(p->smem));
 	if (e1 != cudaSuccess || e2 != cudaSuccess) {
 		g_derr = std::string("cudaFuncSetAttribute(k_down_tile): ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);
 		lpp_dtile_destroy(p);

@@ -19,6 +19,7 @@
 #include "lpp_tiled.cuh"
 #include "lpp_sweep_common.cuh"
 #include "lpp_dtile.cuh"
+#include "lpp_smem_attr.cuh"
 #include "lpp_dblock.cuh"
 
 static thread_local std::string g_terr;
@@ -1659,17 +1660,17 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 			p->ntilesA_blocks = (uint32_t)p->tilesA_host.size();
 			p->npanels = (uint32_t)((m.n1 + p->W - 1) / p->W);
 			cudaError_t e1 = cudaSuccess;
-			if (p->W == 8) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
-			if (p->W == 16) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
-			if (p->W == 32) e1 = cudaFuncSetAttribute(k_sweep_down_blocks<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA);
+			if (p->W == 8) e1 = lpp_raise_smem(k_sweep_down_blocks<8>, (size_t)(p->smemA));
+			if (p->W == 16) e1 = lpp_raise_smem(k_sweep_down_blocks<16>, (size_t)(p->smemA));
+			if (p->W == 32) e1 = lpp_raise_smem(k_sweep_down_blocks<32>, (size_t)(p->smemA));
 			cudaError_t e2 = p->R == 2
-			                     ? cudaFuncSetAttribute(k_sweep_up_blocks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB)
-			                     : cudaFuncSetAttribute(k_sweep_up_blocks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB);
+			                     ? lpp_raise_smem(k_sweep_up_blocks<2>, (size_t)(p->smemB))
+			                     : lpp_raise_smem(k_sweep_up_blocks<1>, (size_t)(p->smemB));
 			cudaError_t e3 = cudaSuccess;
-#define SETB(R_, N_) if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_sweep_up_pipe<R_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemB)
+#define SETB(R_, N_) if (e3 == cudaSuccess) e3 = lpp_raise_smem(k_sweep_up_pipe<R_, N_>, (size_t)(p->smemB))
 			SETB(1, 16); SETB(1, 24); SETB(1, 32); SETB(2, 16); SETB(2, 24); SETB(2, 32);
 #undef SETB
-#define SETA3(W_, T_, B_) if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_sweep_down_blocks3<W_, T_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemA3)
+#define SETA3(W_, T_, B_) if (e3 == cudaSuccess) e3 = lpp_raise_smem(k_sweep_down_blocks3<W_, T_, B_>, (size_t)(p->smemA3))
 			SETA3(8, 1024, 1); SETA3(16, 1024, 1); SETA3(32, 1024, 1); SETA3(8, 512, 2); SETA3(16, 512, 2); SETA3(32, 512, 2);
 #undef SETA3
 			if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { g_terr = "cudaFuncSetAttribute(smem) failed"; delete p; return -1; }
@@ -1681,7 +1682,7 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		p->up_smem_bytes = (size_t)m.n1 * sizeof(double);
 		p->up_in_smem = (p->up_smem_bytes + 1024 <= (size_t)maxsm) ? 1 : 0;
 		if (p->up_in_smem && !p->v2) {
-			cudaError_t e = cudaFuncSetAttribute(k_sweep_up_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->up_smem_bytes);
+			cudaError_t e = lpp_raise_smem(k_sweep_up_smem, (size_t)(p->up_smem_bytes));
 			if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
 		}
 	}
@@ -1697,17 +1698,17 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 		}
 		cudaError_t e = cudaSuccess;
 		if (p->leanA && p->smemAL > 48 * 1024) {
-			e = cudaFuncSetAttribute(k_sweep_down_lean<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
-			if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_down_lean<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemAL);
+			e = lpp_raise_smem(k_sweep_down_lean<1>, (size_t)(p->smemAL));
+			if (e == cudaSuccess) e = lpp_raise_smem(k_sweep_down_lean<2>, (size_t)(p->smemAL));
 		}
-#define SETL(R_, U_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_lean<R_, 32, U_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBL)
+#define SETL(R_, U_) if (e == cudaSuccess) e = lpp_raise_smem(k_sweep_up_lean<R_, 32, U_>, (size_t)(p->smemBL))
 		if (p->leanB) { SETL(1, true); SETL(1, false); SETL(2, true); SETL(2, false); }
 #undef SETL
 		const char* envp = getenv("LPP_TILED_PACKED");
 		p->smemBP = ((size_t)m.n1 + 16 / p->R) * p->R * 8 + ((size_t)(m.n1 + 31) / 32) * 5 + 16;
 		p->packedB = p->v2 && p->R == 2 && p->up.nblocks == 1 && p->tabP != nullptr && !(envp && envp[0] == '0') && (lean & 2) &&
 		             p->smemBP + 1024 <= (size_t)maxsm;
-#define SETP(U_, E_, NG_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_up_packed<2, U_, E_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemBP)
+#define SETP(U_, E_, NG_) if (e == cudaSuccess) e = lpp_raise_smem(k_sweep_up_packed<2, U_, E_, NG_>, (size_t)(p->smemBP))
 		if (p->packedB) { SETP(true, true, 8); SETP(false, true, 8); SETP(true, true, 12); SETP(false, true, 12); SETP(true, false, 8); SETP(false, false, 8); }
 #undef SETP
 		if (e != cudaSuccess) { g_terr = cudaGetErrorString(e); delete p; return -1; }
@@ -1777,7 +1778,7 @@ int lpp_tiled_create(const ModelDev& m, const double* hop_host, const HopTable& 
 				p->stWidth = WP;
 				p->stSplit = split;
 				cudaError_t e = cudaSuccess;
-#define SETS(PC_, NB_) if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_down_staged<PC_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemST)
+#define SETS(PC_, NB_) if (e == cudaSuccess) e = lpp_raise_smem(k_sweep_down_staged<PC_, NB_>, (size_t)(p->smemST))
 				SETS(64, 4); SETS(64, 8); SETS(128, 4); SETS(128, 8);
 #undef SETS
 				{ const char* envn = getenv("LPP_DSTAGE_NB"); p->stNR = (envn && atoi(envn) == 4) ? 4 : 8; }
