@@ -180,3 +180,38 @@ def test_states_below_and_two_point_in_the_oracle(oracle):
     assert np.abs(rho - rho.T).max() < 1e-12 and abs(np.trace(rho) - case["nup"]) < 1e-12
     occ = np.linalg.eigvalsh(rho)
     assert occ.min() > -1e-12 and occ.max() < 1 + 1e-12
+
+
+def test_feas_two_spin_terms_conserve_up_xor_down(oracle):
+    """The entry classes a multi-GPU layout for FeAsBasedSc has to serve (tools/feas_three_layouts.py): every
+    off-diagonal entry of the oracle's matrix changes the down word only (row layout), the up word only (column layout) or both --
+    and the ones that change both (FeBasedSc.h:376-432, spin flip and pair hop on one site) flip the same two bits in both words,
+    so up XOR down is the same on both sides: a layout sharded by it keeps them local."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("feas_three_layouts", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                      "tools", "feas_three_layouts.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    for case in (cases.feas_cluster(2, 2, 3, 3), cases.feas_chain(3, 3, 2, inter_orbital=0.5)):
+        o = cases.make_oracle(oracle, case, fast_rank=1)
+        cl = tool.classify(o)
+        two = cl["kind"] == 2
+        assert two.sum() > 0 and (cl["kind"] == 0).sum() > 0 and (cl["kind"] == 1).sum() > 0
+        assert np.array_equal(cl["dup"][two], cl["ddn"][two])
+        w = cl["up"] ^ cl["dn"]
+        assert np.array_equal(w[cl["rows"][two]], w[cl["cols"][two]])
+        assert all(bin(int(d)).count("1") == 2 for d in np.unique(cl["dup"][two]))
+        # the three classes together are the matrix: applying them one after the other reproduces the oracle's mat-vec
+        y = geo.splitmix64_vector(cl["n"], 5)
+        x = np.zeros(cl["n"])
+        rowptr = cl["rowptr"]
+        rows_all = np.repeat(np.arange(cl["n"]), np.diff(rowptr))
+        diag = rows_all == cl["colind"]
+        np.add.at(x, rows_all[diag], cl["allvals"][diag] * y[cl["colind"][diag]])
+        for k in range(3):
+            sel = cl["kind"] == k
+            np.add.at(x, cl["rows"][sel], cl["vals"][sel] * y[cl["cols"][sel]])
+        xref = np.zeros(cl["n"])
+        o.matvec(xref, y, faithful=False)
+        assert np.abs(x - xref).max() <= 1e-12 * max(1.0, np.abs(xref).max())
