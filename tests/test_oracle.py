@@ -215,3 +215,31 @@ def test_feas_two_spin_terms_conserve_up_xor_down(oracle):
         xref = np.zeros(cl["n"])
         o.matvec(xref, y, faithful=False)
         assert np.abs(x - xref).max() <= 1e-12 * max(1.0, np.abs(xref).max())
+
+
+def test_pipelined_recurrence_formula_matches_the_oracle(oracle):
+    """The algebra of lanczos_pipelined (csrc/lpp_engine.cu, opt-in LPP_PIPELINE): with un-normalised vectors U_j = n_j v_j the sweeps
+    can run without any scalar (w = H U_j) when every scalar enters afterwards,
+        a_j = <U_j, w> / n_j^2,   U_{j+1} = w / n_j - (a_j / n_j) U_j - (b_j / n_{j-1}) U_{j-1},   b_{j+1} = n_{j+1} = |U_{j+1}|,
+    which is what k_lzp_after_dot / k_lzp_after_norm / k_unpack3_norm_p2p compute.  Checked against the oracle's decomposition
+    (LanczosSolver semantics) on a small Hubbard case."""
+    case = cases.hubbard_chain(8, 4, 4, periodic=True, V=np.linspace(-0.3, 0.4, 8))
+    o = cases.make_oracle(oracle, case, fast_rank=1)
+    n = o.rows()
+    init = geo.splitmix64_vector(n, 1234)
+    steps = 25
+    a0, b0 = o.decomposition(init, steps=steps, eps=0.0)
+    u, uprev = init.copy(), np.zeros(n)
+    nj, nprev, bj = float(np.sqrt(init @ init)), 1.0, 0.0
+    a, b = [], []
+    for _ in range(steps):
+        w = np.zeros(n)
+        o.matvec(w, u, faithful=False)
+        aj = float(u @ w) / nj / nj
+        unext = w / nj - (aj / nj) * u - (bj / nprev) * uprev
+        a.append(aj)
+        bj = float(np.sqrt(unext @ unext))
+        b.append(bj)
+        uprev, u, nprev, nj = u, unext, nj, bj
+    assert np.abs(np.array(a) - a0[:steps]).max() <= 1e-10 * np.abs(a0).max()
+    assert np.abs(np.array(b[:-1]) - b0[:steps - 1]).max() <= 1e-10 * np.abs(b0).max()
