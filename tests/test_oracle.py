@@ -184,7 +184,7 @@ def test_states_below_and_two_point_in_the_oracle(oracle):
 
 def test_feas_two_spin_terms_conserve_up_xor_down(oracle):
     """The entry classes a multi-GPU layout for FeAsBasedSc has to serve (tools/feas_three_layouts.py): every
-    off-diagonal entry of the oracle's matrix changes the down word only (row layout), the up word only (column layout) or both --
+    off-diagonal entry of the oracle's matrix changes the down word only (column layout), the up word only (row layout) or both --
     and the ones that change both (FeBasedSc.h:376-432, spin flip and pair hop on one site) flip the same two bits in both words,
     so up XOR down is the same on both sides: a layout sharded by it keeps them local."""
     import importlib.util
@@ -215,6 +215,12 @@ def test_feas_two_spin_terms_conserve_up_xor_down(oracle):
         xref = np.zeros(cl["n"])
         o.matvec(xref, y, faithful=False)
         assert np.abs(x - xref).max() <= 1e-12 * max(1.0, np.abs(xref).max())
+        # the mat-vec as 2 and 3 ranks would do it: no entry joins two ranks in the layout of its class, the shards are balanced
+        for nranks in (2, 3):
+            x3, moved = tool.three_layout_matvec(cl, len(o.basis(0)), nranks, y)
+            assert np.abs(x3 - xref).max() <= 1e-12 * max(1.0, np.abs(xref).max())
+            load = tool.owners(cl, len(o.basis(0)), nranks)[3]
+            assert load.sum() == cl["n"] and load.max() - load.min() <= 0.1 * cl["n"] / nranks
 
 
 def test_pipelined_recurrence_formula_matches_the_oracle(oracle):

@@ -8,8 +8,8 @@ that change BOTH words.  They flip the same two bits in both, so  w = up XOR dow
 by w keeps them local.  This script takes the oracle's CRS matrix (oracle/lanczos_oracle.c, pinned to the reference's own
 FeBasedSc.h by tests/test_reference_pin.py), sorts every off-diagonal entry into
 
-    down hop  (up word unchanged)      -> local in the ROW layout
-    up hop    (down word unchanged)    -> local in the COLUMN layout
+    down hop  (up word unchanged)      -> local in the COLUMN layout (a range of up states with all their down states)
+    up hop    (down word unchanged)    -> local in the ROW layout    (a range of down states with all their up states)
     two-spin  (both words change)      -> local in the XOR layout, if  up XOR down  is the same on both sides
 
 and reports, for N ranks, the vector elements a rank needs from other ranks under (a) the row-sharded gather scheme of today
@@ -54,6 +54,47 @@ def halo_of_gather(cl, nranks):
     return out, bounds
 
 
+def owners(cl, nup_states, nranks):
+    """owner rank of every vector element in the three layouts.  idx = iup + idn * Nup (BasisFeAsBasedSc perfectIndex order)."""
+    n = cl["n"]
+    idx = np.arange(n, dtype=np.int64)
+    iup, idn = idx % nup_states, idx // nup_states
+    ndn_states = n // nup_states
+    row_owner = (idn * nranks) // ndn_states                      # ROW layout: ranges of down states, every up state of them
+    col_owner = (iup * nranks) // nup_states                      # COLUMN layout: ranges of up states, every down state of them
+    w = cl["up"] ^ cl["dn"]
+    classes, inv, counts = np.unique(w, return_inverse=True, return_counts=True)
+    load = np.zeros(nranks, dtype=np.int64)                       # XOR layout: whole classes, largest first onto the lightest rank
+    cls_owner = np.zeros(len(classes), dtype=np.int64)
+    for c in np.argsort(-counts, kind="stable"):
+        r = int(np.argmin(load))
+        cls_owner[c] = r
+        load[r] += counts[c]
+    return row_owner, col_owner, cls_owner[inv], load
+
+
+def three_layout_matvec(cl, nup_states, nranks, y):
+    """x = H y the way N ranks would do it: every rank applies a class of entries only to the elements it owns in the layout that
+    keeps the class local, and reads only elements it owns in that layout.  Returns (x, elements moved per all-to-all)."""
+    n = cl["n"]
+    row_owner, col_owner, xor_owner, _ = owners(cl, nup_states, nranks)
+    layout_of_kind = (col_owner, row_owner, xor_owner)            # down hops, up hops, two-spin terms
+    x = np.zeros(n)
+    rows_all = np.repeat(np.arange(n), np.diff(cl["rowptr"]))
+    diag = rows_all == cl["colind"]
+    np.add.at(x, rows_all[diag], cl["allvals"][diag] * y[cl["colind"][diag]])     # the diagonal is local in every layout
+    for k in range(3):
+        own = layout_of_kind[k]
+        sel = cl["kind"] == k
+        r, c = cl["rows"][sel], cl["cols"][sel]
+        if not np.array_equal(own[r], own[c]):
+            raise AssertionError("an entry of class %d joins two ranks in its layout" % k)
+        np.add.at(x, r, cl["vals"][sel] * y[c])
+    # an all-to-all between the row layout and another one moves the elements whose owner differs
+    moved = [int((row_owner != col_owner).sum()), int((row_owner != xor_owner).sum())]
+    return x, moved
+
+
 def main(argv):
     lx, ly, nup, ndn = (int(a) for a in argv[1:5]) if len(argv) >= 5 else (2, 3, 4, 4)
     nranks = int(argv[5]) if len(argv) >= 6 else 8
@@ -61,7 +102,7 @@ def main(argv):
     o = cases.make_oracle(orc, case, fast_rank=1)
     cl = classify(o)
     n = cl["n"]
-    names = ("down hops (row layout)", "up hops (column layout)", "two-spin terms (XOR layout)")
+    names = ("down hops (column layout)", "up hops (row layout)", "two-spin terms (XOR layout)")
     print("FeAs %dx%d, 2 orbitals, %d up %d down: %d rows, %d off-diagonal entries" % (lx, ly, nup, ndn, n, len(cl["kind"])))
     for k in range(3):
         print("  %-30s %9d entries (%.2f per row)" % (names[k], int((cl["kind"] == k).sum()), (cl["kind"] == k).sum() / n))
@@ -76,6 +117,14 @@ def main(argv):
           % (min(halo), max(halo), float(np.mean(halo)) / float(np.mean(loc)), n - min(loc)))
     print("    three layouts: 4 all-to-alls (row->column, column->row, row->XOR, XOR->row) of the %d local rows each = %.2f x its own shard"
           % (int(np.mean(loc)), 4.0 * (nranks - 1) / nranks))
+    nup_states = len(o.basis(0))
+    y = np.cos(0.37 * np.arange(n) + 0.1)
+    x, moved = three_layout_matvec(cl, nup_states, nranks, y)
+    xref = np.zeros(n)
+    o.matvec(xref, y, faithful=False)
+    _, _, _, load = owners(cl, nup_states, nranks)
+    print("    emulated on %d ranks: max |x - oracle| = %.2e; elements that change owner row<->column %d, row<->XOR %d of %d; XOR shards %d..%d rows"
+          % (nranks, float(np.abs(x - xref).max()), moved[0], moved[1], n, int(load.min()), int(load.max())))
     classes = np.unique(cl["up"] ^ cl["dn"])
     sizes = np.array([int(((cl["up"] ^ cl["dn"]) == w).sum()) for w in classes])
     print("    XOR classes: %d, sizes %d..%d (largest = %.3f of a shard): whole classes can be dealt to the ranks"
