@@ -1,4 +1,4 @@
-// tools/proto_dblock.cu -- standalone prototype of the two-pass BLOCK down sweep  x = beta x + alpha (D + 1 (x) T_dn) y.
+// tools/proto_dblock.cu -- standalone timing harness of the BLOCK down sweep (csrc/lpp_dblock_kernel.cuh)  x = beta x + alpha (D + 1 (x) T_dn) y.
 //
 // Idea: pick two disjoint site sets F1, F2 with no hopping between them.  Pass 1 groups the down states by their occupation of
 // F1 ("blocks": every hop that does not touch F1 stays inside its block); pass 2 groups them by F2 and applies the hops that
@@ -7,6 +7,11 @@
 // are no operands outside the tile, so the only global traffic is y once and x read+write per pass.
 // A persistent grid takes tiles from a ticket counter in panel-major order, pass 2 of a panel LAG panels behind pass 1, so
 // the panel's x and y stay L2 resident between the passes.
+//
+// Options: --layout 1 (one CTA of 1024 threads per SM), --passes 3 (three disjoint site sets), --lag <panels>, --dot (fused
+// dot product in the last pass), --cols <n> (fewer columns), --chain <sites> (open chain instead of the 4 x 4 torus), --iters <n>.
+// Compile-time variants: -DDB_FILL_MODE=2 (bulk-copy tile lines), -DDB_RED_LATER_PASSES=0, -DDB_SKIP_PADDING=1, -DDB_PROFILE
+// (cycle counters per phase).  The numbers of profiles/README.md ("Two CTAs per SM for the block down sweep") come from here.
 //
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/proto_dblock tools/proto_dblock.cu
 #include <algorithm>
@@ -59,12 +64,11 @@ int main(int argc, char** argv)
 {
 	int nx = 4, ny = 4, npart = 8, iters = 10;
 	uint64_t ncols_arg = 0;
-	int lag = 8, ngp = 1, layout = 0, want_dot = 0, passes = 0;
+	int lag = 8, layout = 0, want_dot = 0, passes = 0;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "--cols")) ncols_arg = strtoull(argv[++i], 0, 10);
 		else if (!strcmp(argv[i], "--iters")) iters = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--lag")) lag = atoi(argv[++i]);
-		else if (!strcmp(argv[i], "--ng")) ngp = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--layout")) layout = atoi(argv[++i]);
 		else if (!strcmp(argv[i], "--dot")) want_dot = 1;
 		else if (!strcmp(argv[i], "--passes")) passes = atoi(argv[++i]);
@@ -142,7 +146,6 @@ int main(int argc, char** argv)
 		slots += (double)hp.pass[k].exec_slots / n2;
 	}
 	printf("executed state-slots per state (padding included): %.3f\n", slots);
-	(void)ngp;
 
 	// device data
 	const uint64_t pitch = ncols;
