@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""tools/feas_three_layouts.py -- host-side measurement for FeAs (config 4) on several GPUs without the full-vector gather.
+"""tests/feas_three_layouts.py -- host-side measurement for FeAs (config 4) on several GPUs without the full-vector gather.
 
 The Hubbard two-layout exchange works because every off-diagonal term changes ONE of the two words of a
 row: down hops stay inside a row shard, up hops inside a column shard.  FeAsBasedSc adds on-site two-spin terms
@@ -16,7 +16,7 @@ and reports, for N ranks, the vector elements a rank needs from other ranks unde
 (distinct source rows outside the own shard) and (b) the three-layout scheme (four all-to-alls of the local vector per mat-vec).
 Used by tests/test_oracle.py::test_feas_two_spin_terms_conserve_up_xor_down.
 
-    python tools/feas_three_layouts.py [lx ly nup ndown [nranks]]      (default: 2 x 3 lattice, 4 up 4 down, 8 ranks)
+    python tests/feas_three_layouts.py [lx ly nup ndown [nranks]]      (default: 2 x 3 lattice, 4 up 4 down, 8 ranks)
 """
 import os
 import sys

@@ -1,5 +1,5 @@
-"""tools/sanitize_small.py -- one small invocation of every kernel that is AUTO for some BASELINE config, for
-`compute-sanitizer --tool memcheck|racecheck python tools/sanitize_small.py` (summaries under profiles/).
+"""tests/sanitize_small.py -- one small invocation of every kernel that is AUTO for some BASELINE config, for
+`compute-sanitizer --tool memcheck|racecheck python tests/sanitize_small.py` (summaries under profiles/).
 
   Hubbard 4x3, 6 up 6 down (dim 853 776): k_sweep_down_lean + k_sweep_up_packed, k_axpy_norm, device-resident Lanczos scalars,
                                            stored CRS (k_crs_count/fill, k_spmv_crs), k_apply_op, k_spmv_table, k_spmv_generic

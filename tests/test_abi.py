@@ -90,5 +90,12 @@ def test_product_never_touches_the_oracle():
                     if re.search(pat, text, flags=re.M):
                         bad.append((os.path.join(sub, f), pat))
     assert not bad, bad
+    # tools/: only the two fixture generators (their outputs are the committed tests/golden files) use the oracle; every other
+    # checker script that does lives under tests/
+    allowed = {"make_golden.py", "make_fullsize_pins.py"}
+    for f in sorted(os.listdir(os.path.join(ROOT, "tools"))):
+        if f.endswith(".py") and f not in allowed:
+            text = open(os.path.join(ROOT, "tools", f), errors="replace").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
     # and the build line of the product library names only its own sources
     assert all(s.startswith("lpp_") for s in __import__("lanczosplusplus_b200")._lib.SOURCES)

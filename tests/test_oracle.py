@@ -183,14 +183,13 @@ def test_states_below_and_two_point_in_the_oracle(oracle):
 
 
 def test_feas_two_spin_terms_conserve_up_xor_down(oracle):
-    """The entry classes a multi-GPU layout for FeAsBasedSc has to serve (tools/feas_three_layouts.py): every
+    """The entry classes a multi-GPU layout for FeAsBasedSc has to serve (tests/feas_three_layouts.py): every
     off-diagonal entry of the oracle's matrix changes the down word only (column layout), the up word only (row layout) or both --
     and the ones that change both (FeBasedSc.h:376-432, spin flip and pair hop on one site) flip the same two bits in both words,
     so up XOR down is the same on both sides: a layout sharded by it keeps them local."""
     import importlib.util
     import os
-    spec = importlib.util.spec_from_file_location("feas_three_layouts", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                                                                      "tools", "feas_three_layouts.py"))
+    spec = importlib.util.spec_from_file_location("feas_three_layouts", os.path.join(os.path.dirname(os.path.abspath(__file__)), "feas_three_layouts.py"))
     tool = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(tool)
     for case in (cases.feas_cluster(2, 2, 3, 3), cases.feas_chain(3, 3, 2, inter_orbital=0.5)):
